@@ -1,0 +1,119 @@
+/* include/swarm_b200.h — C ABI of the B200 amplicon neighbour-search engine (libswarm_b200.so).
+ *
+ * The reference (torognes/swarm 3.1.6, /root/reference) has no plugin or FFI interface: its
+ * clustering algorithms are C++ functions called once from main() after db_read() and they pull
+ * their input through global accessors.  This header is the drop-in boundary a
+ * maintainer would bind in their place; every entry point names the reference code it replaces.
+ * Plain C: opaque context, caller-owned host buffers in, caller-owned host buffers out, int status,
+ * thread-local error text.  The library never prints and never calls exit(): the host maps a
+ * status to the reference's own message + exit code 1 (src/utils/fatal.h:27,38-46).
+ *
+ * Amplicon ids are indices into the database in the reference's order — abundance descending, then
+ * strcmp(header) ascending (src/db.cc:392-406).  UINT32_MAX is "none" (`no_swarm`, src/algod1.cc:80).
+ */
+#ifndef SWARM_B200_H
+#define SWARM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB200_NONE 0xFFFFFFFFu
+
+enum {
+  SWB200_OK = 0,
+  SWB200_ECUDA = 1,        /* CUDA runtime error; text in swb200_last_error() */
+  SWB200_EINVAL = 2,       /* bad argument / call order */
+  SWB200_EDUPLICATE = 3,   /* identical sequences in the database (reference: fatal, src/algod1.cc:1141-1150) */
+  SWB200_ENOMEM = 4,
+  SWB200_EUNSUPPORTED = 5  /* e.g. sequence too long for the on-chip Zobrist table */
+};
+
+/* neighbour-enumeration strategy of swb200_d1_network (results are identical) */
+enum {
+  SWB200_ENUM_FULL = 0,  /* every seed probes all <= 7L+4 microvariants, exactly the reference's
+                            enumeration (src/variants.cc:184-249) */
+  SWB200_ENUM_HALF = 1   /* each unordered neighbour pair is discovered once (substitutions towards a
+                            higher base code + deletions only); both directed links are derived from
+                            the abundances.  ~3x fewer probes. Default. */
+};
+
+typedef struct swb200_ctx swb200_ctx;   /* owns the CUDA device, stream, and all device buffers */
+
+/* Create a context on CUDA device `device` (one context per GPU / per process rank). */
+int  swb200_create(swb200_ctx **out, int device);
+void swb200_destroy(swb200_ctx *ctx);
+const char *swb200_last_error(void);
+
+/* Tunables (call before swb200_d1_index).  key: "enum_mode" (SWB200_ENUM_*), "bloom_bytes_per_slot"
+ * (1,2,4,8: filter size = table slots * this; reference uses 1, src/algod1.cc:1127),
+ * "collect_stats" (0/1), "shard_rank"/"shard_world" (seeds [rank*n/world, (rank+1)*n/world) are
+ * this context's share of the network build). */
+int  swb200_set_option(swb200_ctx *ctx, const char *key, int64_t value);
+
+/* Replaces db_getsequence/len/abundance/count (src/db.h:35-53, src/db.cc:806-906) as the engine's
+ * input: uploads the sorted, 2-bit packed database.  words: n*stride_words 64-bit words, amplicon i
+ * at words[i*stride_words], 2 bits/nt LSB first (A0 C1 G2 T3, src/db.cc:100-114,561), zero padded;
+ * len[i] in nt; abundance[i].  Host pointers; copied (pinned staging) to the device. */
+int  swb200_load_db(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words,
+                    const uint32_t *len, const uint64_t *abundance, uint32_t n);
+
+/* Replaces the "Hashing sequences" phase: zobrist_hash of every amplicon (src/db.cc:761,
+ * src/zobrist.cc:134-184), hash_alloc + hash_insert + bloom_set (src/algod1.cc:1118-1139,188-208),
+ * duplicate detection (:174-185).  Returns SWB200_EDUPLICATE when two amplicons are identical. */
+int  swb200_d1_index(swb200_ctx *ctx);
+
+/* Replaces the "Building network" phase: network_thread -> check_variants -> generate_variants +
+ * find_variant_matches + check_variant (src/algod1.cc:558-670, src/variants.cc:118-249,
+ * src/bloompat.cc:68-71, src/hashtable.cc:47-87).  A directed link u->v exists iff v is a
+ * microvariant of u and (no_cluster_breaking or abundance(u) >= abundance(v)) (:580-583).
+ * n_links: number of directed links found by this context's shard. */
+int  swb200_d1_network(swb200_ctx *ctx, int no_cluster_breaking, uint64_t *n_links);
+
+/* The network as CSR = `ampinfo[i].link_start/link_count` + `network_v` (src/algod1.cc:94-95,162),
+ * rows sorted ascending like the -j writer (:769-772).  row_ptr: n+1 entries; col: n_links. */
+int  swb200_d1_get_network(swb200_ctx *ctx, uint64_t *row_ptr, uint32_t *col);
+
+/* Multi-GPU exchange step: raw link list of this shard as (src,dst) pairs, and
+ * replacement of the context's link list by the gathered one.  pairs: 2*n_links uint32. */
+int  swb200_d1_export_links(swb200_ctx *ctx, uint32_t *pairs);
+int  swb200_d1_import_links(swb200_ctx *ctx, const uint32_t *pairs, uint64_t n_links);
+/* device-resident variants for NCCL all-gatherv (pointers are CUDA device addresses) */
+int  swb200_d1_links_device(swb200_ctx *ctx, void **d_pairs, uint64_t *n_links);
+int  swb200_d1_import_links_device(swb200_ctx *ctx, const void *d_pairs, uint64_t n_links);
+
+/* Replaces the "Clustering" phase (greedy BFS, src/algod1.cc:1185-1280, process_seed :673-718):
+ * swarm_of[i] = amplicon id of the seed of i's swarm; generation[i] = BFS depth; parent[i] =
+ * the amplicon that claimed i (SWB200_NONE for seeds).  Any output pointer may be NULL. */
+int  swb200_d1_cluster(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent);
+
+/* Replaces the fastidious passes (mark_light_thread / check_heavy_thread, src/algod1.cc:374-552):
+ * for every amplicon l of a light swarm (mass < boundary), graft_cand[l] = the smallest amplicon id h
+ * belonging to a heavy swarm such that h and l share a microvariant, else SWB200_NONE (:244-258).
+ * The attach order (:274-336) is applied by the host from this array.  Requires swb200_d1_cluster.
+ * Returns via n_light / n_heavy the amplicon counts; graft_cand is all NONE when either is zero. */
+int  swb200_d1_fastidious(swb200_ctx *ctx, uint64_t boundary, uint32_t *graft_cand,
+                          uint64_t *n_light_amplicons, uint64_t *n_heavy_amplicons);
+
+/* Device time (CUDA events on the engine's stream) of the last call, and accumulated per phase.
+ * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 5 csr */
+double swb200_last_device_seconds(swb200_ctx *ctx);
+double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
+
+/* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
+ * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create. */
+int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
+
+/* Test hook: enumerate the microvariants of amplicon `seed` on the device exactly as the network
+ * kernel does (mode = SWB200_ENUM_*); out_hash/out_code hold up to cap entries, code =
+ * type<<30 | base<<28 | pos (type 0 sub, 1 del, 2 ins).  Also returns the engine's Zobrist table
+ * (zlen*4 values, position-major) when ztab != NULL. */
+int  swb200_debug_variants(swb200_ctx *ctx, uint32_t seed, int mode, uint64_t *out_hash,
+                           uint32_t *out_code, uint32_t cap, uint32_t *count,
+                           uint64_t *ztab, uint32_t ztab_cap, uint32_t *zlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,60 @@
+/* include/swarm_b200_host.h — C ABI of the host layer (libswarm_b200_host.so): the FASTA database
+ * and the output writers, i.e. the host mirror of the reference's src/db.cc and of the writers in
+ * src/algod1.cc:755-1095.  No CUDA here; the arrays it exposes are exactly the arguments of
+ * swb200_load_db() (include/swarm_b200.h).
+ */
+#ifndef SWARM_B200_HOST_H
+#define SWARM_B200_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swbh_db swbh_db;
+
+const char *swbh_last_error(void);
+
+/* db_read (src/db.cc:432-803): parse, 2-bit pack, abundance annotations, uniqueness checks, sort.
+ * usearch_abundance = -z, append_abundance = -a (0 = off), check_dup_sequences = d>1 behaviour.
+ * Returns 0, or 1 with the reference's error text (without the "\nError: " prefix) in swbh_last_error(). */
+int  swbh_db_read_fasta(const char *path, int usearch_abundance, int64_t append_abundance,
+                        int check_dup_sequences, swbh_db **out);
+int  swbh_db_parse(const char *text, uint64_t size, int usearch_abundance, int64_t append_abundance,
+                   int check_dup_sequences, swbh_db **out);
+void swbh_db_free(swbh_db *db);
+
+uint32_t swbh_db_count(const swbh_db *db);            /* db_getsequencecount   src/db.cc:806-809 */
+uint32_t swbh_db_longest(const swbh_db *db);          /* db_getlongestsequence src/db.cc:812-815 */
+uint32_t swbh_db_stride_words(const swbh_db *db);
+uint64_t swbh_db_nucleotides(const swbh_db *db);
+const uint64_t *swbh_db_words(const swbh_db *db);     /* db_getsequence  (fixed stride)           */
+const uint32_t *swbh_db_lengths(const swbh_db *db);   /* db_getsequencelen                        */
+const uint64_t *swbh_db_abundances(const swbh_db *db);/* db_getabundance                          */
+const char *swbh_db_header(const swbh_db *db, uint32_t i);  /* db_getheader                       */
+
+/* d=1 result assembly + writers (src/algod1.cc:791-815 `-o`, :1043-1062 `-s`, :990-1040 `-i`,
+ * :755-788 `-j`, :937-987 `-w`, :818-849 `-r`).  Inputs are the engine's outputs: swarm_of /
+ * generation / parent per amplicon, and graft_cand (may be NULL = no fastidious).  Each writer
+ * appends to a malloc'ed buffer returned through out/out_len (free with swbh_free). */
+typedef struct swbh_result swbh_result;
+int  swbh_d1_assemble(const swbh_db *db, const uint32_t *swarm_of, const uint32_t *generation,
+                      const uint32_t *parent, const uint32_t *graft_cand, uint64_t boundary,
+                      swbh_result **out);
+void swbh_result_free(swbh_result *r);
+uint64_t swbh_result_swarms(const swbh_result *r);    /* swarm count after grafting */
+uint32_t swbh_result_largest(const swbh_result *r);
+uint32_t swbh_result_maxgen(const swbh_result *r);
+uint64_t swbh_result_grafts(const swbh_result *r);
+int  swbh_write_swarms(const swbh_db *db, const swbh_result *r, int mothur, int64_t differences,
+                       int usearch_abundance, int64_t append_abundance, char **out, uint64_t *out_len);
+int  swbh_write_stats(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_write_structure(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_write_seeds(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_write_network(const swbh_db *db, const uint64_t *row_ptr, const uint32_t *col,
+                        int usearch_abundance, int64_t append_abundance, char **out, uint64_t *out_len);
+void swbh_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

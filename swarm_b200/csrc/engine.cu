@@ -1,0 +1,524 @@
+// swarm_b200/csrc/engine.cu — the C-ABI of include/swarm_b200.h: context, device memory, phase
+// orchestration, CUDA-event timing.  Kernels live in d1_kernels.cuh (+ fastidious / d>1 files).
+// There is NO CPU fallback in this library: every entry point runs CUDA kernels or fails.
+#include "../../include/swarm_b200.h"
+#include "d1_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace swb;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaFail {
+  int code;
+};
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      throw CudaFail{e_ == cudaErrorMemoryAllocation ? SWB200_ENOMEM : SWB200_ECUDA};              \
+    }                                                                                              \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    CK(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+uint64_t splitmix64(uint64_t &x) {
+  x += 0x9e3779b97f4a7c15ULL;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+
+// smallest power of two >= 10(n+1)/7 — same sizing rule as the reference
+// (src/utils/hashtable_size.cc:29-42), computed in integers.
+uint64_t table_slots(uint64_t n) {
+  const uint64_t want = 10 * (n + 1) / 7;
+  uint64_t s = 2;
+  while (s < want) s <<= 1;
+  return s;
+}
+
+}  // namespace
+
+struct swb200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // options
+  int enum_mode = SWB200_ENUM_HALF;
+  int bloom_bytes_per_slot = 1;
+  int collect_stats = 0;
+  int shard_rank = 0, shard_world = 1;
+  // database
+  uint32_t n = 0, n_padded = 0, stride = 0, longest = 0, batch = 2, zlen = 0;
+  DevBuf<uint64_t> words, abundance, ztab, hashes;
+  DevBuf<uint32_t> len;
+  std::vector<uint64_t> h_ztab;
+  // index
+  DevBuf<Slot> slots;
+  DevBuf<uint2> filter;
+  uint64_t n_slots = 0, n_filter_blocks = 0;
+  bool indexed = false;
+  // network
+  DevBuf<uint2> edges;
+  DevBuf<unsigned long long> counters;   // [0] edge_count, [1..4] stats, [8] dup flag(u32), [9] changed(u32)
+  uint64_t n_edges = 0;
+  bool have_network = false;
+  int ncb = 0;
+  // clustering
+  DevBuf<uint32_t> label, generation, parent;
+  DevBuf<unsigned long long> key;
+  bool clustered = false;
+  // pinned staging
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // timing
+  double last_s = 0;
+  double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+  uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  void *staging(size_t bytes) {
+    if (bytes > pinned_bytes) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      CK(cudaMallocHost(&pinned, bytes));
+      pinned_bytes = bytes;
+    }
+    return pinned;
+  }
+  void tic() { CK(cudaEventRecord(ev0, stream)); }
+  double toc(int phase) {
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_s = ms * 1e-3;
+    phase_s[phase] = last_s;
+    return last_s;
+  }
+  D1Params params() {
+    D1Params P{};
+    P.words = words.p; P.len = len.p; P.abundance = abundance.p;
+    P.n = n; P.stride = stride; P.batch = batch;
+    P.ztab = ztab.p; P.zlen = zlen;
+    P.slots = slots.p; P.slot_mask = n_slots - 1;
+    P.filter = filter.p; P.filter_mask = static_cast<uint32_t>(n_filter_blocks - 1);
+    P.hashes = hashes.p;
+    P.edges = edges.p; P.edge_count = counters.p; P.edge_cap = edges.n;
+    P.stats = collect_stats ? counters.p + 1 : nullptr;
+    P.dup_flag = reinterpret_cast<uint32_t *>(counters.p + 8);
+    P.no_cluster_breaking = ncb;
+    return P;
+  }
+  size_t network_smem() const {
+    const size_t zwords = (static_cast<size_t>(zlen) * 4 + 1) & ~static_cast<size_t>(1);
+    return zwords * 8 + static_cast<size_t>(kWarpsPerCta) * 2 * batch * stride * 8 +
+           static_cast<size_t>(kWarpsPerCta) * sizeof(WarpScratch) + kWarpsPerCta * 2 * 8;
+  }
+};
+
+#define API_BEGIN(ctx)                                       \
+  if (!(ctx)) { g_err = "null context"; return SWB200_EINVAL; } \
+  try {                                                      \
+    CK(cudaSetDevice((ctx)->device));
+#define API_END()                    \
+  }                                  \
+  catch (const CudaFail &f) {        \
+    return f.code;                   \
+  }                                  \
+  catch (const std::bad_alloc &) {   \
+    g_err = "host allocation failed"; \
+    return SWB200_ENOMEM;            \
+  }                                  \
+  return SWB200_OK;
+
+extern "C" {
+
+const char *swb200_last_error(void) { return g_err.c_str(); }
+
+int swb200_create(swb200_ctx **out, int device) {
+  if (!out) { g_err = "null out pointer"; return SWB200_EINVAL; }
+  *out = nullptr;
+  swb200_ctx *c = nullptr;
+  try {
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) { g_err = "no such CUDA device"; return SWB200_EINVAL; }
+    CK(cudaSetDevice(device));
+    c = new swb200_ctx();
+    c->device = device;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    c->counters.alloc(16);
+  } catch (const CudaFail &f) {
+    delete c;
+    return f.code;
+  }
+  *out = c;
+  return SWB200_OK;
+}
+
+void swb200_destroy(swb200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
+  c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
+  c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
+  if (!c || !key) { g_err = "null argument"; return SWB200_EINVAL; }
+  const std::string k(key);
+  if (k == "enum_mode" && (v == SWB200_ENUM_FULL || v == SWB200_ENUM_HALF)) c->enum_mode = static_cast<int>(v);
+  else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
+  else if (k == "collect_stats") c->collect_stats = v != 0;
+  else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
+  else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
+  else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
+  return SWB200_OK;
+}
+
+int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
+                   const uint64_t *abundance, uint32_t n) {
+  API_BEGIN(c)
+  if (!words || !len || !abundance || n == 0 || stride_words == 0) { g_err = "load_db: bad argument"; return SWB200_EINVAL; }
+  if (n >= 0xFFFFFFF0u) { g_err = "load_db: too many amplicons"; return SWB200_EINVAL; }
+  c->indexed = c->have_network = c->clustered = false;
+  // seeds per TMA batch: even, <= kMaxBatch, batch*stride*8 bytes <= 2 KB per buffer
+  uint32_t batch = 256 / stride_words;
+  batch = std::max<uint32_t>(2, std::min<uint32_t>(kMaxBatch, batch & ~1u));
+  c->batch = batch;
+  c->n = n;
+  c->stride = stride_words;
+  c->n_padded = (n + batch - 1) / batch * batch;
+  const size_t wbytes = static_cast<size_t>(n) * stride_words * 8;
+  c->words.alloc(static_cast<size_t>(c->n_padded) * stride_words);
+  c->len.alloc(n);
+  c->abundance.alloc(n);
+  c->tic();
+  // pinned staging in chunks so the H2D copies run at full PCIe rate for pageable callers
+  const size_t chunk = 64u << 20;
+  char *stage = static_cast<char *>(c->staging(2 * chunk));
+  auto upload = [&](void *dst, const void *src, size_t bytes) {
+    size_t off = 0;
+    int which = 0;
+    cudaEvent_t done[2];
+    CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    bool used[2] = {false, false};
+    while (off < bytes) {
+      const size_t nb = std::min(chunk, bytes - off);
+      if (used[which]) CK(cudaEventSynchronize(done[which]));
+      std::memcpy(stage + which * chunk, static_cast<const char *>(src) + off, nb);
+      CK(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage + which * chunk, nb, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaEventRecord(done[which], c->stream));
+      used[which] = true;
+      which ^= 1;
+      off += nb;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+  };
+  cudaPointerAttributes attr{};
+  const bool is_pinned = cudaPointerGetAttributes(&attr, words) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (is_pinned) {
+    CK(cudaMemcpyAsync(c->words.p, words, wbytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->len.p, len, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->abundance.p, abundance, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    upload(c->words.p, words, wbytes);
+    upload(c->len.p, len, static_cast<size_t>(n) * 4);
+    upload(c->abundance.p, abundance, static_cast<size_t>(n) * 8);
+  }
+  if (c->n_padded > n)
+    CK(cudaMemsetAsync(c->words.p + static_cast<size_t>(n) * stride_words, 0,
+                       static_cast<size_t>(c->n_padded - n) * stride_words * 8, c->stream));
+  // Zobrist table: zlen = longest + 2 positions (two insertions, src/db.cc:652), 4 values each,
+  // position-major.  Values come from splitmix64 — results do not depend on the hash function
+  // (every hit is verified exactly).
+  c->longest = stride_words * 32;
+  c->zlen = c->longest + 2;
+  if (static_cast<size_t>(c->zlen) * 32 > 160 * 1024) {
+    g_err = "sequences longer than 5,000 nt are not supported by the on-chip Zobrist table";
+    return SWB200_EUNSUPPORTED;
+  }
+  c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
+  uint64_t sm = 0x5eedb200c0ffeeULL;
+  for (auto &z : c->h_ztab) z = splitmix64(sm);
+  c->ztab.alloc(c->h_ztab.size());
+  CK(cudaMemcpyAsync(c->ztab.p, c->h_ztab.data(), c->h_ztab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  c->toc(0);
+  API_END()
+}
+
+int swb200_d1_index(swb200_ctx *c) {
+  API_BEGIN(c)
+  if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
+  c->n_slots = table_slots(c->n);
+  c->n_filter_blocks = std::max<uint64_t>(1, c->n_slots * c->bloom_bytes_per_slot / 8);
+  if (c->n_filter_blocks > (1ull << 32)) c->n_filter_blocks = 1ull << 32;
+  c->slots.alloc(c->n_slots);
+  c->filter.alloc(c->n_filter_blocks);
+  c->hashes.alloc(c->n);
+  c->tic();
+  CK(cudaMemsetAsync(c->slots.p, 0xFF, c->n_slots * sizeof(Slot), c->stream));
+  CK(cudaMemsetAsync(c->filter.p, 0, c->n_filter_blocks * 8, c->stream));
+  CK(cudaMemsetAsync(c->counters.p, 0, 16 * 8, c->stream));
+  D1Params P = c->params();
+  const size_t zbytes = static_cast<size_t>(c->zlen) * 32;
+  CK(cudaFuncSetAttribute(k_d1_index, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
+  const int grid = c->sm_count * 8;
+  k_d1_index<<<grid, 256, zbytes, c->stream>>>(P);
+  CK(cudaGetLastError());
+  k_d1_dupcheck<<<(c->n + 255) / 256, 256, 0, c->stream>>>(P);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  uint32_t dup = 0;
+  CK(cudaMemcpyAsync(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+  c->toc(1);
+  c->indexed = true;
+  c->have_network = c->clustered = false;
+  if (dup) { g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
+  API_END()
+}
+
+static void run_network(swb200_ctx *c) {
+  D1Params P = c->params();
+  // this context's share of the seeds: contiguous, batch-aligned range
+  const uint64_t per = (static_cast<uint64_t>(c->n_padded / c->batch) + c->shard_world - 1) / c->shard_world;
+  const uint64_t b0 = std::min<uint64_t>(per * c->shard_rank, c->n_padded / c->batch);
+  const uint64_t b1 = std::min<uint64_t>(b0 + per, c->n_padded / c->batch);
+  P.seed_begin = static_cast<uint32_t>(b0 * c->batch);
+  P.seed_end = static_cast<uint32_t>(std::min<uint64_t>(b1 * c->batch, c->n));
+  if (P.seed_begin > P.seed_end) P.seed_begin = P.seed_end;
+  const size_t smem = c->network_smem();
+  int occ = 1;
+  if (c->enum_mode == SWB200_ENUM_FULL) {
+    CK(cudaFuncSetAttribute(k_d1_network<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_d1_network<0>, kWarpsPerCta * 32, smem));
+    occ = std::max(occ, 1);
+    k_d1_network<0><<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
+  } else {
+    CK(cudaFuncSetAttribute(k_d1_network<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_d1_network<1>, kWarpsPerCta * 32, smem));
+    occ = std::max(occ, 1);
+    k_d1_network<1><<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
+  }
+  CK(cudaGetLastError());
+  c->launches += 1;
+}
+
+int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links) {
+  API_BEGIN(c)
+  if (!c->indexed) { g_err = "d1_network: call swb200_d1_index first"; return SWB200_EINVAL; }
+  c->ncb = no_cluster_breaking ? 1 : 0;
+  if (c->edges.n == 0) c->edges.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 4, 1u << 16));
+  c->tic();
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CK(cudaMemsetAsync(c->counters.p, 0, 8 * 8, c->stream));
+    run_network(c);
+    unsigned long long host[5];
+    CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->n_edges = host[0];
+    for (int i = 0; i < 4; ++i) c->stats[i] = host[1 + i];
+    c->stats[4] = c->n_edges;
+    if (c->n_edges <= c->edges.n) break;
+    c->edges.alloc(c->n_edges + c->n_edges / 8);    // link list overflowed: grow and redo (dense data)
+  }
+  c->toc(2);
+  c->have_network = true;
+  c->clustered = false;
+  if (n_links) *n_links = c->n_edges;
+  API_END()
+}
+
+int swb200_d1_export_links(swb200_ctx *c, uint32_t *pairs) {
+  API_BEGIN(c)
+  if (!c->have_network || !pairs) { g_err = "export_links: no network / null buffer"; return SWB200_EINVAL; }
+  CK(cudaMemcpyAsync(pairs, c->edges.p, c->n_edges * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+int swb200_d1_import_links(swb200_ctx *c, const uint32_t *pairs, uint64_t n_links) {
+  API_BEGIN(c)
+  if (!c->indexed || (!pairs && n_links)) { g_err = "import_links: bad state / null buffer"; return SWB200_EINVAL; }
+  c->edges.alloc(std::max<uint64_t>(n_links, 1));
+  CK(cudaMemcpyAsync(c->edges.p, pairs, n_links * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_edges = n_links;
+  c->have_network = true;
+  c->clustered = false;
+  API_END()
+}
+
+int swb200_d1_links_device(swb200_ctx *c, void **d_pairs, uint64_t *n_links) {
+  if (!c || !c->have_network) { g_err = "links_device: no network"; return SWB200_EINVAL; }
+  if (d_pairs) *d_pairs = c->edges.p;
+  if (n_links) *n_links = c->n_edges;
+  return SWB200_OK;
+}
+
+int swb200_d1_import_links_device(swb200_ctx *c, const void *d_pairs, uint64_t n_links) {
+  API_BEGIN(c)
+  if (!c->indexed || (!d_pairs && n_links)) { g_err = "import_links_device: bad state"; return SWB200_EINVAL; }
+  if (d_pairs != c->edges.p) {
+    DevBuf<uint2> fresh;
+    fresh.alloc(std::max<uint64_t>(n_links, 1));
+    CK(cudaMemcpyAsync(fresh.p, d_pairs, n_links * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->edges.release();
+    c->edges = fresh;
+  }
+  c->n_edges = n_links;
+  c->have_network = true;
+  c->clustered = false;
+  API_END()
+}
+
+int swb200_d1_get_network(swb200_ctx *c, uint64_t *row_ptr, uint32_t *col) {
+  API_BEGIN(c)
+  if (!c->have_network || !row_ptr) { g_err = "get_network: no network / null buffer"; return SWB200_EINVAL; }
+  // output path (-j writer), not the timed hot path: counting sort by source on the host, rows ascending
+  std::vector<uint2> e(c->n_edges);
+  CK(cudaMemcpyAsync(e.data(), c->edges.p, c->n_edges * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::fill(row_ptr, row_ptr + c->n + 1, 0);
+  for (const uint2 &x : e) row_ptr[x.x + 1]++;
+  for (uint32_t i = 0; i < c->n; ++i) row_ptr[i + 1] += row_ptr[i];
+  if (col) {
+    std::vector<uint64_t> cur(row_ptr, row_ptr + c->n);
+    for (const uint2 &x : e) col[cur[x.x]++] = x.y;
+    for (uint32_t i = 0; i < c->n; ++i) std::sort(col + row_ptr[i], col + row_ptr[i + 1]);
+  }
+  API_END()
+}
+
+int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
+  API_BEGIN(c)
+  if (!c->have_network) { g_err = "d1_cluster: call swb200_d1_network first"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  const uint64_t m = c->n_edges;
+  c->label.alloc(n); c->generation.alloc(n); c->parent.alloc(n); c->key.alloc(n);
+  uint32_t *changed = reinterpret_cast<uint32_t *>(c->counters.p + 9);
+  const int vb = (n + 255) / 256;
+  const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
+  uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
+  c->tic();
+  k_label_init<<<vb, 256, 0, c->stream>>>(c->label.p, n);
+  c->launches++;
+  for (int round = 0; m > 0 && round < 1 << 20; ++round) {
+    CK(cudaMemsetAsync(changed, 0, 4, c->stream));
+    k_label_edges<<<std::max(eb, 1), 256, 0, c->stream>>>(c->edges.p, m, c->label.p, changed);
+    k_label_jump<<<vb, 256, 0, c->stream>>>(c->label.p, n, changed);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(h_changed, changed, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (*h_changed == 0) break;
+  }
+  k_bfs_init<<<vb, 256, 0, c->stream>>>(c->label.p, c->key.p, n);
+  c->launches++;
+  for (int round = 0; m > 0 && round < 1 << 20; ++round) {
+    CK(cudaMemsetAsync(changed, 0, 4, c->stream));
+    k_bfs_relax<<<std::max(eb, 1), 256, 0, c->stream>>>(c->edges.p, m, c->label.p, c->key.p, changed);
+    c->launches++;
+    CK(cudaMemcpyAsync(h_changed, changed, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (*h_changed == 0) break;
+  }
+  k_bfs_unpack<<<vb, 256, 0, c->stream>>>(c->key.p, c->generation.p, c->parent.p, n);
+  c->launches++;
+  CK(cudaGetLastError());
+  c->toc(3);
+  c->clustered = true;
+  if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (parent) CK(cudaMemcpyAsync(parent, c->parent.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+int swb200_d1_fastidious(swb200_ctx *c, uint64_t, uint32_t *, uint64_t *, uint64_t *) {
+  if (!c) { g_err = "null context"; return SWB200_EINVAL; }
+  g_err = "d1_fastidious: not built yet";
+  return SWB200_EUNSUPPORTED;
+}
+
+double swb200_last_device_seconds(swb200_ctx *c) { return c ? c->last_s : 0.0; }
+double swb200_phase_device_seconds(swb200_ctx *c, int phase) { return (c && phase >= 0 && phase < 8) ? c->phase_s[phase] : 0.0; }
+
+int swb200_get_stats(swb200_ctx *c, uint64_t *out, int n) {
+  if (!c || !out) { g_err = "null argument"; return SWB200_EINVAL; }
+  c->stats[5] = c->launches;
+  for (int i = 0; i < n && i < 8; ++i) out[i] = c->stats[i];
+  return SWB200_OK;
+}
+
+int swb200_debug_variants(swb200_ctx *c, uint32_t seed, int mode, uint64_t *out_hash, uint32_t *out_code, uint32_t cap,
+                          uint32_t *count, uint64_t *ztab, uint32_t ztab_cap, uint32_t *zlen) {
+  API_BEGIN(c)
+  if (c->n == 0 || seed >= c->n || !out_hash || !out_code || !count) { g_err = "debug_variants: bad argument"; return SWB200_EINVAL; }
+  if (c->stride > 1024) { g_err = "debug_variants: sequence too long"; return SWB200_EUNSUPPORTED; }
+  DevBuf<uint64_t> dh;
+  DevBuf<uint32_t> dc, dn;
+  dh.alloc(cap); dc.alloc(cap); dn.alloc(1);
+  D1Params P = c->params();
+  const size_t zbytes = static_cast<size_t>(c->zlen) * 32;
+  if (mode == SWB200_ENUM_FULL) {
+    CK(cudaFuncSetAttribute(k_d1_debug_variants<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
+    k_d1_debug_variants<0><<<1, 32, zbytes, c->stream>>>(P, seed, dh.p, dc.p, cap, dn.p);
+  } else {
+    CK(cudaFuncSetAttribute(k_d1_debug_variants<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
+    k_d1_debug_variants<1><<<1, 32, zbytes, c->stream>>>(P, seed, dh.p, dc.p, cap, dn.p);
+  }
+  CK(cudaGetLastError());
+  c->launches++;
+  CK(cudaMemcpyAsync(count, dn.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const uint32_t m = std::min(*count, cap);
+  CK(cudaMemcpy(out_hash, dh.p, static_cast<size_t>(m) * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_code, dc.p, static_cast<size_t>(m) * 4, cudaMemcpyDeviceToHost));
+  if (zlen) *zlen = c->zlen;
+  if (ztab) std::memcpy(ztab, c->h_ztab.data(), std::min<size_t>(ztab_cap, c->h_ztab.size()) * 8);
+  dh.release(); dc.release(); dn.release();
+  API_END()
+}
+
+}  // extern "C"

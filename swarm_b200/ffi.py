@@ -1,0 +1,350 @@
+"""ctypes bindings of include/swarm_b200.h and include/swarm_b200_host.h (no algorithm code here)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+ENUM_FULL, ENUM_HALF = 0, 1
+NONE = 0xFFFFFFFF
+_STATUS = {1: "CUDA error", 2: "invalid argument", 3: "duplicate sequences", 4: "out of memory", 5: "unsupported"}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"swarm_b200 status {status} ({_STATUS.get(status, '?')}): {text}")
+        self.status = status
+        self.text = text
+
+
+def lib_paths() -> dict:
+    return {"engine": _HERE / "libswarm_b200.so", "host": _HERE / "libswarm_b200_host.so"}
+
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(ty) if a is not None else None
+
+
+_engine_lib = None
+_host_lib = None
+
+
+def engine_lib():
+    """Load libswarm_b200.so (fails loudly if it has not been built)."""
+    global _engine_lib
+    if _engine_lib is None:
+        p = lib_paths()["engine"]
+        if not p.exists():
+            raise FileNotFoundError(f"{p} is missing: run `make engine` (or __graft_entry__.build())")
+        L = C.CDLL(str(p))
+        vp = C.c_void_p
+        L.swb200_last_error.restype = C.c_char_p
+        L.swb200_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.swb200_destroy.argtypes = [vp]
+        L.swb200_destroy.restype = None
+        L.swb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.swb200_load_db.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32]
+        L.swb200_d1_index.argtypes = [vp]
+        L.swb200_d1_network.argtypes = [vp, C.c_int, _u64p]
+        L.swb200_d1_get_network.argtypes = [vp, _u64p, _u32p]
+        L.swb200_d1_export_links.argtypes = [vp, _u32p]
+        L.swb200_d1_import_links.argtypes = [vp, _u32p, C.c_uint64]
+        L.swb200_d1_links_device.argtypes = [vp, C.POINTER(vp), _u64p]
+        L.swb200_d1_import_links_device.argtypes = [vp, vp, C.c_uint64]
+        L.swb200_d1_cluster.argtypes = [vp, _u32p, _u32p, _u32p]
+        L.swb200_d1_fastidious.argtypes = [vp, C.c_uint64, _u32p, _u64p, _u64p]
+        L.swb200_last_device_seconds.argtypes = [vp]
+        L.swb200_last_device_seconds.restype = C.c_double
+        L.swb200_phase_device_seconds.argtypes = [vp, C.c_int]
+        L.swb200_phase_device_seconds.restype = C.c_double
+        L.swb200_get_stats.argtypes = [vp, _u64p, C.c_int]
+        L.swb200_debug_variants.argtypes = [vp, C.c_uint32, C.c_int, _u64p, _u32p, C.c_uint32, _u32p, _u64p, C.c_uint32, _u32p]
+        _engine_lib = L
+    return _engine_lib
+
+
+def host_lib():
+    global _host_lib
+    if _host_lib is None:
+        p = lib_paths()["host"]
+        if not p.exists():
+            raise FileNotFoundError(f"{p} is missing: run `make host` (or __graft_entry__.build())")
+        L = C.CDLL(str(p))
+        vp = C.c_void_p
+        L.swbh_last_error.restype = C.c_char_p
+        L.swbh_db_read_fasta.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int, C.POINTER(vp)]
+        L.swbh_db_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.POINTER(vp)]
+        L.swbh_db_free.argtypes = [vp]
+        L.swbh_db_free.restype = None
+        for f in ("count", "longest", "stride_words"):
+            getattr(L, f"swbh_db_{f}").argtypes = [vp]
+            getattr(L, f"swbh_db_{f}").restype = C.c_uint32
+        L.swbh_db_nucleotides.argtypes = [vp]
+        L.swbh_db_nucleotides.restype = C.c_uint64
+        L.swbh_db_words.argtypes = [vp]
+        L.swbh_db_words.restype = _u64p
+        L.swbh_db_lengths.argtypes = [vp]
+        L.swbh_db_lengths.restype = _u32p
+        L.swbh_db_abundances.argtypes = [vp]
+        L.swbh_db_abundances.restype = _u64p
+        L.swbh_db_header.argtypes = [vp, C.c_uint32]
+        L.swbh_db_header.restype = C.c_char_p
+        L.swbh_d1_assemble.argtypes = [vp, _u32p, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(vp)]
+        L.swbh_result_free.argtypes = [vp]
+        L.swbh_result_free.restype = None
+        L.swbh_result_swarms.argtypes = [vp]
+        L.swbh_result_swarms.restype = C.c_uint64
+        L.swbh_result_grafts.argtypes = [vp]
+        L.swbh_result_grafts.restype = C.c_uint64
+        L.swbh_result_largest.argtypes = [vp]
+        L.swbh_result_largest.restype = C.c_uint32
+        L.swbh_result_maxgen.argtypes = [vp]
+        L.swbh_result_maxgen.restype = C.c_uint32
+        cpp = C.POINTER(C.c_char_p)
+        L.swbh_write_swarms.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
+        L.swbh_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_write_seeds.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_write_network.argtypes = [vp, _u64p, _u32p, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
+        L.swbh_free.argtypes = [vp]
+        L.swbh_free.restype = None
+        del cpp
+        _host_lib = L
+    return _host_lib
+
+
+class HostDb:
+    """The sorted, 2-bit packed amplicon database (host mirror of the reference's db.cc)."""
+
+    def __init__(self, path: str | os.PathLike | None = None, text: bytes | None = None, usearch_abundance=False,
+                 append_abundance=0, check_dup_sequences=False):
+        L = host_lib()
+        h = C.c_void_p()
+        self.opts = (int(bool(usearch_abundance)), int(append_abundance))
+        if text is not None:
+            rc = L.swbh_db_parse(text, len(text), self.opts[0], self.opts[1], int(check_dup_sequences), C.byref(h))
+        else:
+            rc = L.swbh_db_read_fasta(str(path).encode(), self.opts[0], self.opts[1], int(check_dup_sequences), C.byref(h))
+        if rc != 0:
+            raise ValueError(L.swbh_last_error().decode())
+        self._h = h
+        self.n = L.swbh_db_count(h)
+        self.longest = L.swbh_db_longest(h)
+        self.stride = L.swbh_db_stride_words(h)
+        self.nucleotides = L.swbh_db_nucleotides(h)
+        self.words = np.ctypeslib.as_array(L.swbh_db_words(h), shape=(self.n * self.stride,))
+        self.len = np.ctypeslib.as_array(L.swbh_db_lengths(h), shape=(self.n,))
+        self.abundance = np.ctypeslib.as_array(L.swbh_db_abundances(h), shape=(self.n,))
+
+    def header(self, i: int) -> str:
+        return host_lib().swbh_db_header(self._h, int(i)).decode()
+
+    def headers(self):
+        L = host_lib()
+        return [L.swbh_db_header(self._h, i).decode() for i in range(self.n)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.words = self.len = self.abundance = None
+            host_lib().swbh_db_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class D1Result:
+    """Swarm lists / stats / structure built by the host writers from the engine's arrays."""
+
+    def __init__(self, db: HostDb, swarm_of, generation, parent, graft_cand=None, boundary=3):
+        L = host_lib()
+        self.db = db
+        self._keep = [np.ascontiguousarray(a, dtype=np.uint32) for a in (swarm_of, generation, parent)]
+        gc = np.ascontiguousarray(graft_cand, dtype=np.uint32) if graft_cand is not None else None
+        h = C.c_void_p()
+        rc = L.swbh_d1_assemble(db._h, *[_ptr(a, _u32p) for a in self._keep], _ptr(gc, _u32p), int(boundary), C.byref(h))
+        if rc != 0:
+            raise ValueError(L.swbh_last_error().decode())
+        self._h = h
+        self.swarms = L.swbh_result_swarms(h)
+        self.grafts = L.swbh_result_grafts(h)
+        self.largest = L.swbh_result_largest(h)
+        self.maxgen = L.swbh_result_maxgen(h)
+
+    def _text(self, fn, *args) -> bytes:
+        L = host_lib()
+        out = C.c_void_p()
+        n = C.c_uint64()
+        rc = fn(*args, C.byref(out), C.byref(n))
+        if rc != 0:
+            raise ValueError(L.swbh_last_error().decode())
+        data = C.string_at(out, n.value)
+        L.swbh_free(out)
+        return data
+
+    def swarms_text(self, mothur=False, differences=1) -> bytes:
+        L = host_lib()
+        return self._text(L.swbh_write_swarms, self.db._h, self._h, int(mothur), int(differences), *self.db.opts)
+
+    def stats_text(self) -> bytes:
+        L = host_lib()
+        return self._text(L.swbh_write_stats, self.db._h, self._h, self.db.opts[0])
+
+    def structure_text(self) -> bytes:
+        L = host_lib()
+        return self._text(L.swbh_write_structure, self.db._h, self._h, self.db.opts[0])
+
+    def seeds_text(self) -> bytes:
+        L = host_lib()
+        return self._text(L.swbh_write_seeds, self.db._h, self._h, self.db.opts[0])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            host_lib().swbh_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def network_text(db: HostDb, row_ptr, col) -> bytes:
+    L = host_lib()
+    out = C.c_void_p()
+    n = C.c_uint64()
+    rp = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+    cc = np.ascontiguousarray(col, dtype=np.uint32)
+    rc = L.swbh_write_network(db._h, _ptr(rp, _u64p), _ptr(cc, _u32p), *db.opts, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise ValueError(L.swbh_last_error().decode())
+    data = C.string_at(out, n.value)
+    L.swbh_free(out)
+    return data
+
+
+class Engine:
+    """One CUDA context of the engine (one per GPU / per rank)."""
+
+    def __init__(self, device: int = 0, **options):
+        L = engine_lib()
+        h = C.c_void_p()
+        rc = L.swb200_create(C.byref(h), int(device))
+        if rc != 0:
+            raise EngineError(rc, L.swb200_last_error().decode())
+        self._h = h
+        self.n = 0
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(rc, engine_lib().swb200_last_error().decode())
+
+    def set_option(self, key: str, value: int):
+        self._ck(engine_lib().swb200_set_option(self._h, key.encode(), int(value)))
+
+    def load_db(self, words, stride, lengths, abundance):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        abundance = np.ascontiguousarray(abundance, dtype=np.uint64)
+        n = lengths.shape[0]
+        assert words.shape[0] == n * stride and abundance.shape[0] == n
+        self._ck(engine_lib().swb200_load_db(self._h, _ptr(words, _u64p), int(stride), _ptr(lengths, _u32p),
+                                            _ptr(abundance, _u64p), n))
+        self.n = n
+
+    def load(self, db: HostDb):
+        self.load_db(db.words, db.stride, db.len, db.abundance)
+
+    def d1_index(self):
+        self._ck(engine_lib().swb200_d1_index(self._h))
+
+    def d1_network(self, no_cluster_breaking=False) -> int:
+        m = C.c_uint64()
+        self._ck(engine_lib().swb200_d1_network(self._h, int(bool(no_cluster_breaking)), C.byref(m)))
+        self.n_links = m.value
+        return m.value
+
+    def d1_get_network(self):
+        rp = np.zeros(self.n + 1, dtype=np.uint64)
+        col = np.zeros(max(self.n_links, 1), dtype=np.uint32)
+        self._ck(engine_lib().swb200_d1_get_network(self._h, _ptr(rp, _u64p), _ptr(col, _u32p)))
+        return rp, col[: self.n_links]
+
+    def d1_export_links(self):
+        pairs = np.zeros((max(self.n_links, 1), 2), dtype=np.uint32)
+        self._ck(engine_lib().swb200_d1_export_links(self._h, _ptr(pairs, _u32p)))
+        return pairs[: self.n_links]
+
+    def d1_import_links(self, pairs):
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self._ck(engine_lib().swb200_d1_import_links(self._h, _ptr(pairs, _u32p), pairs.shape[0]))
+        self.n_links = pairs.shape[0]
+
+    def d1_links_device(self):
+        p = C.c_void_p()
+        m = C.c_uint64()
+        self._ck(engine_lib().swb200_d1_links_device(self._h, C.byref(p), C.byref(m)))
+        return p.value, m.value
+
+    def d1_import_links_device(self, dptr: int, n_links: int):
+        self._ck(engine_lib().swb200_d1_import_links_device(self._h, C.c_void_p(dptr), int(n_links)))
+        self.n_links = int(n_links)
+
+    def d1_cluster(self, want=("swarm_of", "generation", "parent")):
+        outs = {k: (np.empty(self.n, dtype=np.uint32) if k in want else None) for k in ("swarm_of", "generation", "parent")}
+        self._ck(engine_lib().swb200_d1_cluster(self._h, _ptr(outs["swarm_of"], _u32p), _ptr(outs["generation"], _u32p),
+                                               _ptr(outs["parent"], _u32p)))
+        return outs["swarm_of"], outs["generation"], outs["parent"]
+
+    def d1_fastidious(self, boundary=3):
+        gc = np.empty(self.n, dtype=np.uint32)
+        nl, nh = C.c_uint64(), C.c_uint64()
+        self._ck(engine_lib().swb200_d1_fastidious(self._h, int(boundary), _ptr(gc, _u32p), C.byref(nl), C.byref(nh)))
+        return gc, nl.value, nh.value
+
+    def last_device_seconds(self) -> float:
+        return engine_lib().swb200_last_device_seconds(self._h)
+
+    def phase_seconds(self, phase: int) -> float:
+        return engine_lib().swb200_phase_device_seconds(self._h, int(phase))
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 8))
+        return {"variants": int(out[0]), "filter_pass": int(out[1]), "slots_visited": int(out[2]),
+                "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5])}
+
+    def debug_variants(self, seed: int, mode: int, cap: int = 1 << 16):
+        h = np.zeros(cap, dtype=np.uint64)
+        c = np.zeros(cap, dtype=np.uint32)
+        cnt = C.c_uint32()
+        zl = C.c_uint32()
+        z = np.zeros(4 * 8192, dtype=np.uint64)
+        self._ck(engine_lib().swb200_debug_variants(self._h, int(seed), int(mode), _ptr(h, _u64p), _ptr(c, _u32p), cap,
+                                                   C.byref(cnt), _ptr(z, _u64p), z.shape[0], C.byref(zl)))
+        m = min(cnt.value, cap)
+        return h[:m], c[:m], z[: zl.value * 4].reshape(-1, 4)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            engine_lib().swb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

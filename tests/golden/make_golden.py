@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures of tests/golden/ by running the UNMODIFIED reference binary
+(oracle/_ref/swarm, built by oracle/Makefile from /root/reference) on small inputs.
+
+    python tests/golden/make_golden.py          # only possible where oracle/_ref/swarm exists
+
+Each case <name>.fasta gets: <name>.o (swarms), .s (stats), .i (structure), .j (network) at d=1;
+<name>.n.o with -n; <name>.f.o/.f.s/.f.i with --fastidious (-t 1: the reference's light pass has
+unsynchronised inserts).  Inputs come from tools/gen_amplicons.c (seeded) or are
+hand-made below.  The fixtures are committed; this script is their provenance.
+"""
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parent))
+sys.path.insert(0, str(HERE.parent.parent))
+import helpers  # noqa: E402
+
+HANDMADE = b""">seedA_100
+ACGTACGTACGTACGTACGTACGTACGTACGTAAAACCCCGGGGTTTT
+>subB_40
+ACGTACGTACGTACGTACGTACGTACGTACGTAAAACCCCGGGGTTTA
+>delC_12
+ACGTACGTACGTACGTACGTACGTACGTACGTAAACCCCGGGGTTTT
+>insD_12
+ACGTACGTACGTACGTACGTACGTACGTACGTAAAACCCCGGGGGTTTT
+>lower_u_7
+acguacguacguacguacguacguacguacguaaaaccccgggguuca
+>gen2_3
+ACGTACGTACGTACGTACGTACGTACGTACGTAAACCCCGGGGTTTA
+>tieX_5
+TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT
+>tieY_5
+TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT
+>tieZ_5
+TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTGTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT
+>crlf_2\r
+GGGGGGGGCCCCCCCC\r
+AAAATTTT\r
+>orph_1
+ACGTACGTACGTACGTACGTACGTACGTACGTAAAACCCCGGGGTTAA
+>orph2_1
+ACGTACGTACGTACGTACGTACGTACGTACGTAAAACCCCGGGTTTAA
+>lonely_1
+CATCATCATCATCATCATCAT
+>one_9
+A
+>two_4
+AC
+>three_1
+C
+"""
+
+CASES = [
+    # name, n, L, seed, ab_mode, orphan_p
+    ("c1_1k_150", 1000, 150, 42, 0, 0.2),
+    ("tie_1500_60", 1500, 60, 7, 1, 0.1),
+    ("short_600_20", 600, 20, 3, 0, 0.2),
+    ("w32_400", 400, 32, 5, 0, 0.2),
+    ("w64_400", 400, 64, 6, 1, 0.2),
+    ("w65_300", 300, 65, 8, 0, 0.3),
+]
+
+
+def main():
+    if not helpers.have_ref():
+        sys.exit("oracle/_ref/swarm missing: run `make -C oracle ref` where /root/reference exists")
+    (HERE / "handmade.fasta").write_bytes(HANDMADE)
+    names = ["handmade"]
+    for name, n, L, seed, mode, op in CASES:
+        helpers.make_fasta(HERE / f"{name}.fasta", n, L, seed, mode, op)
+        names.append(name)
+    for name in names:
+        fa = HERE / f"{name}.fasta"
+        r = helpers.run_ref(fa, outputs=("o", "s", "i", "j", "w"))
+        assert r["rc"] == 0, r["stderr"]
+        for k in "osijw":
+            (HERE / f"{name}.{k}").write_bytes(r[k])
+        r = helpers.run_ref(fa, "-n", outputs=("o",))
+        (HERE / f"{name}.n.o").write_bytes(r["o"])
+        r = helpers.run_ref(fa, "-f", outputs=("o", "s", "i"), threads=1)
+        assert r["rc"] == 0, r["stderr"]
+        for k in "osi":
+            (HERE / f"{name}.f.{k}").write_bytes(r[k])
+        r = helpers.run_ref(fa, "-f", "-b", "10", outputs=("o",), threads=1)
+        (HERE / f"{name}.f.b10.o").write_bytes(r["o"])
+        print(name, "ok")
+    # usearch-style headers (-z) + mothur (-r): derived from c1 by rewriting headers
+    src = (HERE / "c1_1k_150.fasta").read_bytes().splitlines()
+    out = []
+    for ln in src[:600]:
+        if ln.startswith(b">"):
+            lab, ab = ln[1:].rsplit(b"_", 1)
+            out.append(b">" + lab + b";size=" + ab + b";")
+        else:
+            out.append(ln)
+    (HERE / "usearch_300.fasta").write_bytes(b"\n".join(out) + b"\n")
+    r = helpers.run_ref(HERE / "usearch_300.fasta", "-z", outputs=("o", "s", "i", "w"))
+    assert r["rc"] == 0, r["stderr"]
+    for k in "osiw":
+        (HERE / f"usearch_300.{k}").write_bytes(r[k])
+    r = helpers.run_ref(HERE / "usearch_300.fasta", "-z", "-r", outputs=("o",))
+    (HERE / "usearch_300.r.o").write_bytes(r["o"])
+    print("usearch ok")
+
+
+if __name__ == "__main__":
+    main()

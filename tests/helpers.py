@@ -1,0 +1,201 @@
+"""Test-side bindings: the CPU oracle (oracle/liboracle.so), the reference binary (oracle/_ref/swarm,
+when present), the synthetic generator, and output canonicalisation.  Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = ROOT / "tests" / "golden"
+REF_BIN = ROOT / "oracle" / "_ref" / "swarm"
+NONE = 0xFFFFFFFF
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(ty)
+
+
+class OrcDb(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("longest", C.c_uint32), ("words", _u64p), ("off", _u64p),
+                ("len", _u32p), ("abundance", _u64p)]
+
+
+class OrcVar(C.Structure):
+    _fields_ = [("hash", C.c_uint64), ("pos", C.c_uint32), ("type", C.c_uint8), ("base", C.c_uint8), ("pad", C.c_uint16)]
+
+
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        L = C.CDLL(str(ROOT / "oracle" / "liboracle.so"))
+        L.orc_zobrist_init.argtypes = [C.c_uint32]
+        L.orc_zobrist_value.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_zobrist_value.restype = C.c_uint64
+        L.orc_zobrist_hash.argtypes = [_u64p, C.c_uint32]
+        L.orc_zobrist_hash.restype = C.c_uint64
+        L.orc_mt19937_64_next.restype = C.c_uint64
+        L.orc_generate_variants.argtypes = [_u64p, C.c_uint32, C.c_uint64, C.POINTER(OrcVar)]
+        L.orc_generate_variants.restype = C.c_uint32
+        L.orc_hashtable_size.argtypes = [C.c_uint64]
+        L.orc_hashtable_size.restype = C.c_uint64
+        L.orc_d1_network.argtypes = [C.POINTER(OrcDb), C.c_int, _u32p, _u32p, C.POINTER(_u32p), _u64p, _u64p]
+        L.orc_d1_cluster.argtypes = [C.POINTER(OrcDb), _u32p, _u32p, _u32p] + [_u32p] * 4 + [_u32p] * 5 + [_u64p] * 2
+        L.orc_d1_cluster.restype = C.c_uint32
+        L.orc_d1_fastidious.argtypes = [C.POINTER(OrcDb), C.c_uint64, C.c_uint32, C.c_uint32, _u32p, _u32p,
+                                        _u32p, _u32p, _u32p, _u32p, _u64p, _u64p, _u8p, _u32p, _u64p]
+        L.orc_d1_fastidious.restype = C.c_int64
+        L.orc_free.argtypes = [C.c_void_p]
+        _orc = L
+    return _orc
+
+
+class Oracle:
+    """CPU restatement of the d=1 path over a HostDb (fixed-stride words)."""
+
+    def __init__(self, db):
+        self.db = db
+        n = db.n
+        self.words = np.ascontiguousarray(db.words, dtype=np.uint64)
+        self.off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(db.stride))
+        self.len = np.ascontiguousarray(db.len, dtype=np.uint32)
+        self.ab = np.ascontiguousarray(db.abundance, dtype=np.uint64)
+        self.c = OrcDb(n, db.longest, _p(self.words, _u64p), _p(self.off, _u64p), _p(self.len, _u32p), _p(self.ab, _u64p))
+
+    def network(self, no_cluster_breaking=False):
+        L = oracle_lib()
+        n = self.db.n
+        ls = np.zeros(n, dtype=np.uint32)
+        lc = np.zeros(n, dtype=np.uint32)
+        net = _u32p()
+        m = C.c_uint64()
+        st = np.zeros(4, dtype=np.uint64)
+        rc = L.orc_d1_network(C.byref(self.c), int(no_cluster_breaking), _p(ls, _u32p), _p(lc, _u32p), C.byref(net),
+                              C.byref(m), _p(st, _u64p))
+        if rc != 0:
+            return None
+        arr = np.ctypeslib.as_array(net, shape=(max(m.value, 1),))[: m.value].copy()
+        L.orc_free(net)
+        self.link_start, self.link_count, self.net, self.net_stats = ls, lc, arr, st
+        return ls, lc, arr
+
+    def links(self):
+        """directed links as a sorted (src, dst) array"""
+        src = np.repeat(np.arange(self.db.n, dtype=np.uint32), self.link_count)
+        # rows are contiguous and in seed order in the oracle's network
+        pairs = np.stack([src, self.net], axis=1)
+        return pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+
+    def cluster(self):
+        L = oracle_lib()
+        n = self.db.n
+        a32 = lambda: np.zeros(n, dtype=np.uint32)
+        a64 = lambda: np.zeros(n, dtype=np.uint64)
+        self.swarmid, self.generation, self.parent, self.next = a32(), a32(), a32(), a32()
+        self.sw_seed, self.sw_last, self.sw_size, self.sw_singletons, self.sw_maxgen = a32(), a32(), a32(), a32(), a32()
+        self.sw_mass, self.sw_sumlen = a64(), a64()
+        net = self.net if self.net.size else np.zeros(1, dtype=np.uint32)
+        self.nswarms = L.orc_d1_cluster(C.byref(self.c), _p(self.link_start, _u32p), _p(self.link_count, _u32p), _p(net, _u32p),
+                                        _p(self.swarmid, _u32p), _p(self.generation, _u32p), _p(self.parent, _u32p),
+                                        _p(self.next, _u32p), _p(self.sw_seed, _u32p), _p(self.sw_last, _u32p),
+                                        _p(self.sw_size, _u32p), _p(self.sw_singletons, _u32p), _p(self.sw_maxgen, _u32p),
+                                        _p(self.sw_mass, _u64p), _p(self.sw_sumlen, _u64p))
+        self.swarm_of = self.sw_seed[self.swarmid]
+        return self.swarm_of, self.generation, self.parent
+
+    def fastidious(self, boundary=3, bloom_bits=16):
+        L = oracle_lib()
+        n = self.db.n
+        self.sw_attached = np.zeros(n, dtype=np.uint8)
+        self.graft_cand = np.zeros(n, dtype=np.uint32)
+        st = np.zeros(4, dtype=np.uint64)
+        g = L.orc_d1_fastidious(C.byref(self.c), int(boundary), int(bloom_bits), int(self.nswarms), _p(self.swarmid, _u32p),
+                                _p(self.next, _u32p), _p(self.sw_seed, _u32p), _p(self.sw_last, _u32p), _p(self.sw_size, _u32p),
+                                _p(self.sw_singletons, _u32p), _p(self.sw_mass, _u64p), _p(self.sw_sumlen, _u64p),
+                                _p(self.sw_attached, _u8p), _p(self.graft_cand, _u32p), _p(st, _u64p))
+        self.fast_stats = st
+        return g
+
+    def swarm_lists(self):
+        """final member lists (list order) of the non-attached swarms, following `next`"""
+        out = []
+        att = getattr(self, "sw_attached", None)
+        for s in range(self.nswarms):
+            if att is not None and att[s]:
+                continue
+            a = int(self.sw_seed[s])
+            cur = []
+            while a != NONE:
+                cur.append(a)
+                a = int(self.next[a])
+            out.append(cur)
+        return out
+
+
+_gen = None
+
+
+def gen_lib():
+    global _gen
+    if _gen is None:
+        L = C.CDLL(str(ROOT / "tools" / "libgen_amplicons.so"))
+        L.gen_create.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_double]
+        L.gen_create.restype = C.c_void_p
+        L.gen_count.argtypes = [C.c_void_p]
+        L.gen_count.restype = C.c_uint64
+        L.gen_write_fasta.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64]
+        L.gen_free.argtypes = [C.c_void_p]
+        L.gen_free.restype = None
+        _gen = L
+    return _gen
+
+
+def make_fasta(path, n, L, seed=42, ab_mode=0, orphan_p=0.2):
+    G = gen_lib()
+    g = G.gen_create(int(n), int(L), int(seed), int(ab_mode), float(orphan_p))
+    assert g
+    rc = G.gen_write_fasta(g, str(path).encode(), 0, int(n))
+    G.gen_free(g)
+    assert rc == 0
+    return path
+
+
+def canonical(text: bytes) -> bytes:
+    """sort ids inside each line, then sort lines"""
+    lines = [b" ".join(sorted(l.split())) for l in text.splitlines() if l.strip()]
+    return b"\n".join(sorted(lines)) + b"\n"
+
+
+def have_ref() -> bool:
+    return REF_BIN.exists() and os.access(REF_BIN, os.X_OK)
+
+
+def run_ref(fasta, *flags, outputs=("o",), threads=1):
+    """run the unmodified reference binary; returns {flag: bytes}"""
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [str(REF_BIN), "-t", str(threads), "-l", os.path.join(td, "log")]
+        for o in outputs:
+            cmd += ["-" + o, os.path.join(td, o)]
+        if "o" not in outputs:
+            cmd += ["-o", os.devnull]
+        cmd += list(flags) + [str(fasta)]
+        p = subprocess.run(cmd, capture_output=True)
+        res["rc"] = p.returncode
+        res["stderr"] = p.stderr
+        for o in outputs:
+            f = os.path.join(td, o)
+            res[o] = open(f, "rb").read() if os.path.exists(f) else b""
+        res["log"] = open(os.path.join(td, "log"), "rb").read() if os.path.exists(os.path.join(td, "log")) else b""
+    return res

@@ -1,0 +1,136 @@
+"""CPU tests (no GPU): pin the oracle restatement (oracle/oracle_d1.c) and the host layer
+(FASTA database + writers) against the golden outputs of the unmodified reference binary
+committed under tests/golden/ (provenance: tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN, Oracle
+from swarm_b200 import D1Result, HostDb
+from swarm_b200.ffi import network_text
+
+CASES = ["handmade", "c1_1k_150", "tie_1500_60", "short_600_20", "w32_400", "w64_400", "w65_300"]
+
+
+def test_mt19937_64_known_answer(built):
+    # C++11 [rand.predef]: the 10000th consecutive invocation of a default-constructed
+    # std::mt19937_64 produces 9981545732273789042.
+    L = helpers.oracle_lib()
+    L.orc_zobrist_exit()
+    import ctypes as C
+    # default seed 5489 is what orc_mt19937_64_next uses before any orc_zobrist_init
+    vals = [L.orc_mt19937_64_next() for _ in range(10000)]
+    assert vals[-1] == 9981545732273789042
+
+
+def test_hashtable_size_known_answers(built):
+    # /root/reference src/utils/hashtable_size.cc:61-68 (table in the source comments) + SURVEY §8
+    L = helpers.oracle_lib()
+    table = {11: 32, 179: 512, 2867: 8192, 45875: 131072, 734003: 2097152, 11744051: 33554432,
+             187904819: 536870912, 1000: 2048, 1000000: 2097152, 10000000: 16777216, 100000000: 268435456}
+    for n, want in table.items():
+        assert L.orc_hashtable_size(n) == want, n
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request, built):
+    name = request.param
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    assert orc.network() is not None
+    orc.cluster()
+    return name, db, orc
+
+
+def test_variant_count_bound(case):
+    name, db, orc = case
+    # |V| = 6L + runs + 4 <= 7L + 4 (src/variants.cc:184-249)
+    assert int(orc.net_stats[0]) <= int((7 * db.len.astype(np.int64) + 4).sum())
+
+
+def test_swarms_stats_structure_match_reference(case):
+    name, db, orc = case
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent)
+    assert res.swarms_text() == (GOLDEN / f"{name}.o").read_bytes()
+    assert res.stats_text() == (GOLDEN / f"{name}.s").read_bytes()
+    assert res.structure_text() == (GOLDEN / f"{name}.i").read_bytes()
+    assert res.seeds_text() == (GOLDEN / f"{name}.w").read_bytes()
+    # the oracle's own linked list gives the same member order
+    heads = [[db.header(a) for a in sw] for sw in orc.swarm_lists()]
+    want = [l.split() for l in (GOLDEN / f"{name}.o").read_text().splitlines()]
+    assert heads == want
+
+
+def test_network_matches_reference(case):
+    name, db, orc = case
+    pairs = orc.links()
+    rp = np.zeros(db.n + 1, dtype=np.uint64)
+    np.add.at(rp, pairs[:, 0].astype(np.int64) + 1, 1)
+    rp = np.cumsum(rp).astype(np.uint64)
+    assert network_text(db, rp, pairs[:, 1]) == (GOLDEN / f"{name}.j").read_bytes()
+
+
+def test_no_cluster_breaking(case):
+    name, db, _ = case
+    orc = Oracle(db)
+    orc.network(no_cluster_breaking=True)
+    orc.cluster()
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent)
+    assert res.swarms_text() == (GOLDEN / f"{name}.n.o").read_bytes()
+
+
+@pytest.mark.parametrize("boundary,suffix", [(3, "f"), (10, "f.b10")])
+def test_fastidious_matches_reference(case, boundary, suffix):
+    name, db, _ = case
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    orc.fastidious(boundary=boundary)
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent, graft_cand=orc.graft_cand, boundary=boundary)
+    assert res.swarms_text() == (GOLDEN / f"{name}.{suffix}.o").read_bytes()
+    if suffix == "f":
+        assert res.stats_text() == (GOLDEN / f"{name}.f.s").read_bytes()
+        assert res.structure_text() == (GOLDEN / f"{name}.f.i").read_bytes()
+    heads = [[db.header(a) for a in sw] for sw in orc.swarm_lists()]
+    want = [l.split() for l in (GOLDEN / f"{name}.{suffix}.o").read_text().splitlines()]
+    assert heads == want
+
+
+def test_usearch_and_mothur(built):
+    db = HostDb(GOLDEN / "usearch_300.fasta", usearch_abundance=True)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent)
+    assert res.swarms_text() == (GOLDEN / "usearch_300.o").read_bytes()
+    assert res.stats_text() == (GOLDEN / "usearch_300.s").read_bytes()
+    assert res.structure_text() == (GOLDEN / "usearch_300.i").read_bytes()
+    assert res.seeds_text() == (GOLDEN / "usearch_300.w").read_bytes()
+    assert res.swarms_text(mothur=True) == (GOLDEN / "usearch_300.r.o").read_bytes()
+
+
+def test_duplicate_sequences_detected(built):
+    db = HostDb(text=b">a_3\nACGTACGT\n>b_2\nACGTACGT\n>c_1\nACGTACGA\n")
+    assert Oracle(db).network() is None     # the reference aborts (src/algod1.cc:1141-1150)
+
+
+@pytest.mark.parametrize("text,msg", [
+    (b"ACGT\n", "Illegal header line in fasta file."),
+    (b">a_1\nACGN\n", "Illegal character 'N' in sequence on line 2."),
+    (b">a_1\n>b_1\nAC\n", "Empty sequence found on line 1."),
+    (b">a\nACGT\n", "Abundance annotations not found for 1 sequences, starting on line 1."),
+    (b">a_0\nACGT\n", "Illegal abundance value on line 1:"),
+    (b">a_1\nACGT\n>a_2\nACGA\n", "Duplicated sequence identifier: a"),
+    (b">_1\nACGT\n", "Empty sequence identifier."),
+])
+def test_fasta_errors(built, text, msg):
+    with pytest.raises(ValueError) as e:
+        HostDb(text=text)
+    assert msg in str(e.value)
+    if helpers.have_ref():      # the reference prints the same message (src/db.cc)
+        import tempfile, os
+        with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
+            f.write(text)
+        r = helpers.run_ref(f.name)
+        os.unlink(f.name)
+        assert r["rc"] == 1 and msg.encode() in r["stderr"]
