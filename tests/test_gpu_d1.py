@@ -1,0 +1,176 @@
+"""GPU parity tests (-m gpu): the CUDA engine, called through the C ABI (include/swarm_b200.h),
+against the CPU oracle and the committed golden outputs of the reference binary.  Bit-exact."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN, Oracle
+from swarm_b200 import ENUM_FULL, ENUM_HALF, D1Result, Engine, EngineError, HostDb
+from swarm_b200.ffi import network_text
+
+pytestmark = pytest.mark.gpu
+CASES = ["handmade", "c1_1k_150", "tie_1500_60", "short_600_20", "w32_400", "w64_400", "w65_300"]
+
+
+def bases_of(db, i):
+    w = db.words[i * db.stride:(i + 1) * db.stride]
+    L = int(db.len[i])
+    p = np.arange(L)
+    return ((w[p >> 5] >> ((p & 31).astype(np.uint64) << np.uint64(1))) & np.uint64(3)).astype(np.int64)
+
+
+def cpu_variants(seq, Z):
+    """the reference's canonical microvariant set (src/variants.cc:184-249) with hashes from table Z"""
+    L = len(seq)
+
+    def H(s):
+        h = np.uint64(0)
+        for p, b in enumerate(s):
+            h ^= Z[p, b]
+        return int(h)
+    out = {}
+    for p in range(L):
+        for b in range(4):
+            if b != seq[p]:
+                s = list(seq); s[p] = b
+                out[(0 << 30) | (b << 28) | p] = H(s)
+    for p in range(L):
+        if p == 0 or seq[p] != seq[p - 1]:
+            out[(1 << 30) | p] = H(list(seq[:p]) + list(seq[p + 1:]))
+    for p in range(L + 1):
+        for b in range(4):
+            if p == 0 or b != seq[p - 1]:
+                out[(2 << 30) | (b << 28) | p] = H(list(seq[:p]) + [b] + list(seq[p:]))
+    return out
+
+
+@pytest.mark.parametrize("name", ["handmade", "short_600_20", "w32_400", "w65_300", "c1_1k_150"])
+def test_variant_enumeration_matches_cpu(built, name):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    eng = Engine(0)
+    eng.load(db)
+    rng = np.random.default_rng(1)
+    seeds = sorted(set([0, db.n - 1] + list(rng.integers(0, db.n, 6))))
+    if name == "handmade":
+        seeds = list(range(db.n))
+    for s in seeds:
+        h, c, Z = eng.debug_variants(s, ENUM_FULL)
+        seq = bases_of(db, s)
+        want = cpu_variants(seq, Z)
+        got = dict(zip(c.tolist(), h.tolist()))
+        assert len(got) == len(c), "duplicate variant codes"
+        assert got == want, (name, s)
+        h2, c2, _ = eng.debug_variants(s, ENUM_HALF)
+        half = dict(zip(c2.tolist(), h2.tolist()))
+        want_half = {k: v for k, v in want.items()
+                     if (k >> 30) == 1 or ((k >> 30) == 0 and ((k >> 28) & 3) > seq[k & 0x0FFFFFFF])}
+        assert half == want_half, (name, s)
+    eng.close()
+
+
+def run_engine(db, mode, ncb=False, **opt):
+    eng = Engine(0, enum_mode=mode, collect_stats=1, **opt)
+    eng.load(db)
+    eng.d1_index()
+    eng.d1_network(no_cluster_breaking=ncb)
+    links = eng.d1_export_links()
+    links = links[np.lexsort((links[:, 1], links[:, 0]))]
+    sw, gen, par = eng.d1_cluster()
+    rp, col = eng.d1_get_network()
+    stats = eng.stats()
+    eng.close()
+    return links, sw, gen, par, rp, col, stats
+
+
+@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF])
+@pytest.mark.parametrize("name", CASES)
+def test_golden_cases(built, name, mode):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    links, sw, gen, par, rp, col, stats = run_engine(db, mode)
+    assert np.array_equal(links, orc.links()), "directed link set differs from the oracle"
+    assert np.array_equal(sw, orc.swarm_of)
+    assert np.array_equal(gen, orc.generation)
+    assert np.array_equal(par, orc.parent)
+    res = D1Result(db, sw, gen, par)
+    assert res.swarms_text() == (GOLDEN / f"{name}.o").read_bytes()
+    assert res.stats_text() == (GOLDEN / f"{name}.s").read_bytes()
+    assert res.structure_text() == (GOLDEN / f"{name}.i").read_bytes()
+    assert network_text(db, rp, col) == (GOLDEN / f"{name}.j").read_bytes()
+    if mode == ENUM_FULL:   # the full enumeration probes exactly the reference's variant count
+        assert stats["variants"] == int(orc.net_stats[0])
+
+
+@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF])
+@pytest.mark.parametrize("name", ["handmade", "tie_1500_60", "c1_1k_150"])
+def test_no_cluster_breaking(built, name, mode):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    links, sw, gen, par, *_ = run_engine(db, mode, ncb=True)
+    res = D1Result(db, sw, gen, par)
+    assert res.swarms_text() == (GOLDEN / f"{name}.n.o").read_bytes()
+
+
+def test_duplicates_rejected(built):
+    db = HostDb(text=b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>c_1\nACGTACGA\n")
+    eng = Engine(0)
+    eng.load(db)
+    with pytest.raises(EngineError) as e:
+        eng.d1_index()
+    assert e.value.status == 3
+    eng.close()
+
+
+@pytest.mark.parametrize("n,L,seed,mode_ab", [(60000, 150, 42, 0), (40000, 80, 9, 1), (30000, 400, 5, 0), (20000, 31, 4, 1)])
+def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
+    fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
+    db = HostDb(fa)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    for mode in (ENUM_FULL, ENUM_HALF):
+        links, sw, gen, par, *_ = run_engine(db, mode)
+        assert np.array_equal(links, orc.links())
+        assert np.array_equal(sw, orc.swarm_of)
+        assert np.array_equal(gen, orc.generation)
+        assert np.array_equal(par, orc.parent)
+
+
+def test_filter_sizes_and_sharding_give_identical_links(built, tmp_path):
+    fa = helpers.make_fasta(tmp_path / "s.fa", 50000, 150, 77, 0)
+    db = HostDb(fa)
+    base, *_ = run_engine(db, ENUM_HALF)
+    for bps in (2, 4):
+        links, *_ = run_engine(db, ENUM_HALF, bloom_bytes_per_slot=bps)
+        assert np.array_equal(links, base)
+    parts = []
+    for r in range(3):
+        links, *_ = run_engine(db, ENUM_HALF, shard_rank=r, shard_world=3)
+        parts.append(links)
+    allp = np.concatenate(parts)
+    allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]
+    assert np.array_equal(allp, base)
+
+
+def test_large_set_properties(built, tmp_path):
+    """size-independent checks at a size the oracle would take minutes for: FULL == HALF, clustering is
+    a fixed point (every link stays inside one swarm or points from a smaller label), seeds are minima."""
+    fa = helpers.make_fasta(tmp_path / "big.fa", 1000000, 150, 11, 0)
+    db = HostDb(fa)
+    lf, swf, genf, parf, *_ = run_engine(db, ENUM_FULL)
+    lh, swh, genh, parh, *_ = run_engine(db, ENUM_HALF)
+    assert np.array_equal(lf, lh) and np.array_equal(swf, swh) and np.array_equal(genf, genh) and np.array_equal(parf, parh)
+    src, dst = lf[:, 0].astype(np.int64), lf[:, 1].astype(np.int64)
+    assert np.all(db.abundance[src] >= db.abundance[dst])
+    assert np.all(swf[src] >= swf[dst]) or True
+    assert np.all(swf[dst] <= swf[src])              # min-label fixed point over directed links
+    assert np.all(swf <= np.arange(db.n))            # a seed is the smallest id of its swarm
+    roots = swf == np.arange(db.n)
+    assert np.all(genf[roots] == 0) and np.all(parf[roots] == 0xFFFFFFFF)
+    nz = ~roots
+    assert np.all(genf[parf[nz].astype(np.int64)] + 1 == genf[nz]) and np.all(swf[parf[nz].astype(np.int64)] == swf[nz])
+    if helpers.have_ref():
+        r = helpers.run_ref(fa, outputs=("o",), threads=8)
+        res = D1Result(db, swf, genf, parf)
+        assert res.swarms_text() == r["o"]
