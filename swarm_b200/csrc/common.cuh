@@ -51,10 +51,13 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 }
 
 // ---- cache-hinted loads ------------------------------------------------------------------------
-// filter word: read-only, random, L2-resident; do not pollute L1
+// filter word: read-only, random, must stay L2-resident.  Measured on B200 (profiles/r1b_*): with
+// `.L1::no_allocate` (SASS LDG.E.NA) the filter lines were NOT retained in L2 once bucket walks streamed
+// through it (15.4 GB DRAM reads per 4 M seeds, L2 hit 61 %); the plain non-coherent load keeps them
+// resident (2.6 GB, L2 hit 91.5 %).
 __device__ __forceinline__ uint2 ld_filter(const uint2 *p) {
   uint2 v;
-  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  asm("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint4 ld_slot(const Slot *p) {

@@ -46,6 +46,7 @@ struct D1Params {
   uint32_t seed_begin, seed_end;
   int no_cluster_breaking;
   uint32_t *dup_flag;
+  uint32_t dbg;            // experiment switches (SWB200_DEBUG env): 1 = skip bucket walks
 };
 
 __device__ __forceinline__ uint32_t base_at(const uint64_t *w, uint32_t p) {
@@ -56,40 +57,42 @@ __device__ __forceinline__ uint32_t base_at(const uint64_t *w, uint32_t p) {
 // k_d1_index — "Hashing sequences" phase.  Replaces zobrist_hash (src/zobrist.cc:134-184, stored at
 // src/db.cc:761), hash_insert (src/algod1.cc:188-208: first free slot by linear probing from
 // (hash>>32)&mask, src/hashtable.cc:47-60) and bloom_set (src/bloompat.cc:62-65).  One warp per
-// amplicon; lane l hashes positions l, l+32, ...; slots are claimed with a 64-bit CAS on {id,len}.
+// thread per amplicon; slots are claimed with a 64-bit CAS on {id,len}.
 // =================================================================================================
 __global__ void __launch_bounds__(256) k_d1_index(D1Params P) {
   extern __shared__ uint64_t zs[];
   for (uint32_t i = threadIdx.x; i < P.zlen * 4; i += blockDim.x) zs[i] = P.ztab[i];
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < P.n; a += warps) {
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  // one THREAD per amplicon: the 32 lanes of a warp walk positions in lockstep, so the Zobrist reads
+  // of one step fall in one 32-byte window of shared memory (broadcast), and the 32 slot claims of a
+  // warp are 32 independent atomics in flight.
+  for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < P.n; a += nthreads) {
     const uint32_t L = P.len[a];
     const uint64_t *w = P.words + static_cast<uint64_t>(a) * P.stride;
     uint64_t h = 0;
     for (uint32_t j = 0; (j << 5) < L; ++j) {
-      const uint64_t word = __ldg(w + j);
-      const uint32_t p = (j << 5) + lane;
-      if (p < L) h ^= zs[p * 4 + (static_cast<uint32_t>(word >> (lane << 1)) & 3u)];
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) h ^= shfl_xor_u64(h, m);
-    if (lane == 0) {
-      P.hashes[a] = h;
-      uint64_t idx = (h >> 32) & P.slot_mask;
-      const unsigned long long mine = (static_cast<unsigned long long>(L) << 32) | a;
-      for (;;) {
-        unsigned long long *cell = reinterpret_cast<unsigned long long *>(&P.slots[idx].id);
-        const unsigned long long old = atomicCAS(cell, 0xFFFFFFFFFFFFFFFFull, mine);
-        if (old == 0xFFFFFFFFFFFFFFFFull) { P.slots[idx].hash = h; break; }
-        idx = (idx + 1) & P.slot_mask;
+      uint64_t word = w[j];
+      const uint32_t p0 = j << 5;
+      const uint32_t cnt = min(32u, L - p0);
+      for (uint32_t q = 0; q < cnt; ++q) {
+        h ^= zs[(p0 + q) * 4 + (static_cast<uint32_t>(word) & 3u)];
+        word >>= 2;
       }
-      const uint2 pat = filter_pattern(h);
-      uint32_t *blk = reinterpret_cast<uint32_t *>(P.filter + (static_cast<uint32_t>(h) & P.filter_mask));
-      atomicOr(blk, pat.x);
-      atomicOr(blk + 1, pat.y);
     }
+    P.hashes[a] = h;
+    uint64_t idx = (h >> 32) & P.slot_mask;
+    const unsigned long long mine = (static_cast<unsigned long long>(L) << 32) | a;
+    for (;;) {
+      unsigned long long *cell = reinterpret_cast<unsigned long long *>(&P.slots[idx].id);
+      const unsigned long long old = atomicCAS(cell, 0xFFFFFFFFFFFFFFFFull, mine);
+      if (old == 0xFFFFFFFFFFFFFFFFull) { P.slots[idx].hash = h; break; }
+      idx = (idx + 1) & P.slot_mask;
+    }
+    const uint2 pat = filter_pattern(h);
+    uint32_t *blk = reinterpret_cast<uint32_t *>(P.filter + (static_cast<uint32_t>(h) & P.filter_mask));
+    atomicOr(blk, pat.x);
+    atomicOr(blk + 1, pat.y);
   }
 }
 
@@ -169,13 +172,14 @@ __device__ __forceinline__ uint64_t variant_word(const uint64_t *sw, uint32_t nw
 // (src/algod1.cc:568-602) + check_variant (src/variants.cc:118-165), 4 survivors per step, 8 lanes
 // each.  MODE 0 = FULL (link seed->amp under the abundance rule), 1 = HALF (pair found once; derive
 // both directions).
-template <int MODE>
+template <int MODE, bool STATS>
 __device__ __forceinline__ void drain_queue(const D1Params &P, WarpScratch &S, const uint64_t *sw, uint32_t seed,
                                             uint32_t L, uint32_t &qn, uint32_t &en, uint32_t lane,
                                             unsigned long long &st_slots, unsigned long long &st_cmp) {
   const uint32_t sub = lane >> 3, j = lane & 7u;
   const uint32_t nw = (L + 31) >> 5;
   __syncwarp();
+  if (P.dbg & 1u) { qn = 0; return; }
   for (uint32_t b0 = 0; b0 < qn; b0 += 4) {
     const uint32_t e = b0 + sub;
     bool done = e >= qn;
@@ -194,7 +198,7 @@ __device__ __forceinline__ void drain_queue(const D1Params &P, WarpScratch &S, c
       uint32_t bm = (__ballot_sync(kFull, match && !done) >> (sub * 8)) & 0xFFu;
       const uint32_t first_empty = be ? (__ffs(be) - 1) : 8u;
       bm &= (1u << first_empty) - 1u;
-      if (!done && j == 0) st_slots += first_empty < 8 ? first_empty : 8;
+      if (STATS && !done && j == 0) st_slots += first_empty < 8 ? first_empty : 8;
       bool hit = false;
       // verify candidates (normally at most one per survivor); loop is warp-uniform
       while (__any_sync(kFull, bm != 0 && !hit)) {
@@ -212,7 +216,7 @@ __device__ __forceinline__ void drain_queue(const D1Params &P, WarpScratch &S, c
             for (uint32_t k = j; k < vw; k += 8)
               if (variant_word(sw, nw, type, pos, vbase, k) != __ldg(cw + k)) bad = true;
           }
-          if (j == 0) st_cmp += 1;
+          if (STATS && j == 0) st_cmp += 1;
         }
         const uint32_t bb = (__ballot_sync(kFull, bad) >> (sub * 8)) & 0xFFu;
         const bool ok = act && bb == 0;
@@ -249,7 +253,7 @@ __device__ __forceinline__ void drain_queue(const D1Params &P, WarpScratch &S, c
 
 // One position's microvariants (NV candidate slots): issue all filter loads, then test; survivors
 // are compacted into the warp queue with __ballot_sync.
-template <int MODE, int NV>
+template <int MODE, int NV, bool STATS>
 __device__ __forceinline__ void probe_batch(const D1Params &P, WarpScratch &S, const uint64_t *sw, uint32_t seed,
                                             uint32_t L, const bool (&vv)[NV], const uint64_t (&vh)[NV],
                                             const uint32_t (&vc)[NV], uint32_t &qn, uint32_t &en, uint32_t lane,
@@ -259,7 +263,10 @@ __device__ __forceinline__ void probe_batch(const D1Params &P, WarpScratch &S, c
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     w[k] = make_uint2(0u, 0u);
-    if (vv[k]) w[k] = ld_filter(P.filter + (static_cast<uint32_t>(vh[k]) & P.filter_mask));
+    if (vv[k]) {
+      const uint2 *fp = P.filter + (static_cast<uint32_t>(vh[k]) & P.filter_mask);
+      w[k] = ld_filter(fp);
+    }
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -268,14 +275,14 @@ __device__ __forceinline__ void probe_batch(const D1Params &P, WarpScratch &S, c
     const uint32_t bal = __ballot_sync(kFull, pass);
     if (bal) {
       const uint32_t cnt = __popc(bal);
-      if (qn + cnt > kQueueCap) drain_queue<MODE>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
+      if (qn + cnt > kQueueCap) drain_queue<MODE, STATS>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
       if (pass) {
         const uint32_t at = qn + __popc(bal & ((1u << lane) - 1u));
         S.qhash[at] = vh[k];
         S.qcode[at] = vc[k];
       }
       qn += cnt;
-      if (lane == 0) st_pass += cnt;
+      if (STATS && lane == 0) st_pass += cnt;
     }
   }
 }
@@ -322,9 +329,9 @@ __device__ __forceinline__ void enumerate_variants(const uint64_t *zs, const uin
 #pragma unroll
       for (int b = 0; b < 4; ++b) z[b] = zs[p * 4 + b];
     }
-    const uint64_t zcur = real ? z[s & 3u] : 0ull;
+    const uint64_t zcur = !real ? 0ull : (s == 0 ? z[0] : (s == 1 ? z[1] : (s == 2 ? z[2] : z[3])));
     const uint64_t zB = (real && p >= 1) ? zs[(p - 1) * 4 + s] : 0ull;
-    constexpr int NV = MODE == 0 ? 9 : 4;
+    constexpr int NV = MODE == 0 ? 9 : 3;
     bool vv[NV];
     uint64_t vh[NV];
     uint32_t vc[NV];
@@ -346,16 +353,23 @@ __device__ __forceinline__ void enumerate_variants(const uint64_t *zs, const uin
         vc[5 + b] = (2u << 30) | (b << 28) | p;
       }
     } else {
-      // HALF: substitutions towards a higher base code (b = 1..3) + deletion
-#pragma unroll
-      for (uint32_t b = 1; b < 4; ++b) {
-        vv[b - 1] = real && b > s;
-        vh[b - 1] = TA ^ zcur ^ z[b];
-        vc[b - 1] = (0u << 30) | (b << 28) | p;
+      // HALF: each unordered substitution pair {a,b} at a position is discovered from exactly one side,
+      // chosen by the tournament 0->1 0->2 1->2 1->3 2->3 3->0 (out-degree 2,2,1,1: balanced lanes):
+      // slot 0 probes b = s+1 (always), slot 1 probes b = s+2 (only for s < 2); slot 2 = deletion.
+      {
+        const uint32_t b1 = (s + 1u) & 3u, b2 = (s + 2u) & 3u;
+        const uint64_t z1 = b1 == 0 ? z[0] : (b1 == 1 ? z[1] : (b1 == 2 ? z[2] : z[3]));
+        const uint64_t z2 = b2 == 0 ? z[0] : (b2 == 1 ? z[1] : (b2 == 2 ? z[2] : z[3]));
+        vv[0] = real;
+        vh[0] = TA ^ zcur ^ z1;
+        vc[0] = (0u << 30) | (b1 << 28) | p;
+        vv[1] = real && s < 2u;
+        vh[1] = TA ^ zcur ^ z2;
+        vc[1] = (0u << 30) | (b2 << 28) | p;
       }
-      vv[3] = real && (p == 0 || s != prev);
-      vh[3] = pa ^ TB ^ pb ^ zB;
-      vc[3] = (1u << 30) | p;
+      vv[2] = real && (p == 0 || s != prev);
+      vh[2] = pa ^ TB ^ pb ^ zB;
+      vc[2] = (1u << 30) | p;
     }
     emit(vv, vh, vc);
     if (real) {
@@ -374,8 +388,8 @@ __device__ __forceinline__ void enumerate_variants(const uint64_t *zs, const uin
 // consecutive packed seeds is one contiguous byte range fetched by a 1-D TMA bulk copy into the
 // warp's double buffer while the previous batch is being processed.
 // =================================================================================================
-template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_d1_network(D1Params P) {
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MODE == 0 ? 2 : 3) k_d1_network(D1Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [ztab zlen*4 u64][per-warp: 2 * batch*stride u64][per-warp WarpScratch][per-warp 2 mbarriers]
   uint64_t *zs = reinterpret_cast<uint64_t *>(smem_raw);
@@ -425,20 +439,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_d1_network(D1Params P) {
       if (seed < P.seed_begin || seed >= P.seed_end) continue;
       const uint32_t L = P.len[seed];
       const uint64_t *sw = tile + k * P.stride;
-      constexpr int NV = MODE == 0 ? 9 : 4;
+      constexpr int NV = MODE == 0 ? 9 : 3;
       auto emit = [&](const bool (&vv)[NV], const uint64_t (&vh)[NV], const uint32_t (&vc)[NV]) {
+        if (STATS) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) st_var += vv[k] ? 1u : 0u;
-        probe_batch<MODE, NV>(P, S, sw, seed, L, vv, vh, vc, qn, en, lane, st_pass, st_slots, st_cmp);
+          for (int k = 0; k < NV; ++k) st_var += vv[k] ? 1u : 0u;
+        }
+        probe_batch<MODE, NV, STATS>(P, S, sw, seed, L, vv, vh, vc, qn, en, lane, st_pass, st_slots, st_cmp);
       };
       enumerate_variants<MODE>(zs, sw, L, lane, emit);
-      if (qn) drain_queue<MODE>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
+      if (qn) drain_queue<MODE, STATS>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
     }
     __syncwarp();                                // all lanes done reading the tile before it is re-filled
     cur ^= 1;
   }
   flush_edges(P, S, en, lane);
-  if (P.stats) {
+  if (STATS && P.stats) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) {
       st_var += __shfl_xor_sync(kFull, st_var, m);
@@ -466,7 +482,7 @@ __global__ void k_d1_debug_variants(D1Params P, uint32_t seed, uint64_t *out_has
   __syncthreads();
   const uint32_t lane = threadIdx.x;
   uint32_t qn = 0;
-  constexpr int NV = MODE == 0 ? 9 : 4;
+  constexpr int NV = MODE == 0 ? 9 : 3;
   auto emit = [&](const bool (&vv)[NV], const uint64_t (&vh)[NV], const uint32_t (&vc)[NV]) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -135,6 +136,7 @@ struct swb200_ctx {
     P.stats = collect_stats ? counters.p + 1 : nullptr;
     P.dup_flag = reinterpret_cast<uint32_t *>(counters.p + 8);
     P.no_cluster_breaking = ncb;
+    if (const char *d = std::getenv("SWB200_DEBUG")) P.dbg = static_cast<uint32_t>(std::atoi(d));
     return P;
   }
   size_t network_smem() const {
@@ -303,7 +305,7 @@ int swb200_d1_index(swb200_ctx *c) {
   D1Params P = c->params();
   const size_t zbytes = static_cast<size_t>(c->zlen) * 32;
   CK(cudaFuncSetAttribute(k_d1_index, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
-  const int grid = c->sm_count * 8;
+  const int grid = std::min<int>(c->sm_count * 8, (c->n + 255) / 256);
   k_d1_index<<<grid, 256, zbytes, c->stream>>>(P);
   CK(cudaGetLastError());
   k_d1_dupcheck<<<(c->n + 255) / 256, 256, 0, c->stream>>>(P);
@@ -328,18 +330,16 @@ static void run_network(swb200_ctx *c) {
   P.seed_end = static_cast<uint32_t>(std::min<uint64_t>(b1 * c->batch, c->n));
   if (P.seed_begin > P.seed_end) P.seed_begin = P.seed_end;
   const size_t smem = c->network_smem();
-  int occ = 1;
-  if (c->enum_mode == SWB200_ENUM_FULL) {
-    CK(cudaFuncSetAttribute(k_d1_network<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_d1_network<0>, kWarpsPerCta * 32, smem));
+  auto launch = [&](auto kernel) {
+    int occ = 1;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWarpsPerCta * 32, smem));
     occ = std::max(occ, 1);
-    k_d1_network<0><<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
-  } else {
-    CK(cudaFuncSetAttribute(k_d1_network<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_d1_network<1>, kWarpsPerCta * 32, smem));
-    occ = std::max(occ, 1);
-    k_d1_network<1><<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
-  }
+    kernel<<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
+  };
+  const bool st = c->collect_stats != 0;
+  if (c->enum_mode == SWB200_ENUM_FULL) { if (st) launch(k_d1_network<0, true>); else launch(k_d1_network<0, false>); }
+  else { if (st) launch(k_d1_network<1, true>); else launch(k_d1_network<1, false>); }
   CK(cudaGetLastError());
   c->launches += 1;
 }

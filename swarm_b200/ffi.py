@@ -303,8 +303,10 @@ class Engine:
         self._ck(engine_lib().swb200_d1_import_links_device(self._h, C.c_void_p(dptr), int(n_links)))
         self.n_links = int(n_links)
 
-    def d1_cluster(self, want=("swarm_of", "generation", "parent")):
-        outs = {k: (np.empty(self.n, dtype=np.uint32) if k in want else None) for k in ("swarm_of", "generation", "parent")}
+    def d1_cluster(self, want=("swarm_of", "generation", "parent"), out=None):
+        """out: optional dict of caller-owned (e.g. pinned) uint32 arrays to receive the results"""
+        outs = {k: ((out[k] if out and k in out else np.empty(self.n, dtype=np.uint32)) if k in want else None)
+                for k in ("swarm_of", "generation", "parent")}
         self._ck(engine_lib().swb200_d1_cluster(self._h, _ptr(outs["swarm_of"], _u32p), _ptr(outs["generation"], _u32p),
                                                _ptr(outs["parent"], _u32p)))
         return outs["swarm_of"], outs["generation"], outs["parent"]
