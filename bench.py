@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fastidious", action="store_true", help="BASELINE configs[2]: add the --fastidious graft search to every step")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -202,8 +203,9 @@ def main():
     pl[:] = db.len
     pa[:] = db.abundance
     res = {k: torch.empty(n, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32) for k in ("swarm_of", "generation", "parent")}
+    res_gc = torch.empty(n, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     h2d = pw.nbytes + pl.nbytes + pa.nbytes
-    d2h = 3 * 4 * n
+    d2h = (4 if args.fastidious else 3) * 4 * n
 
     eng = Engine(local, enum_mode=args.enum_mode, bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0,
                  shard_rank=rank, shard_world=world)
@@ -236,13 +238,18 @@ def main():
         eng.d1_network()
         gather_links()
         eng.d1_cluster(want=())
+        if args.fastidious:
+            eng.d1_fastidious(want=False)
 
     def e2e_step():
         eng.load_db(pw, db.stride, pl, pa)
         eng.d1_index()
         eng.d1_network()
         gather_links()
-        return eng.d1_cluster(out=res)
+        r = eng.d1_cluster(out=res)
+        if args.fastidious:
+            eng.d1_fastidious(out=res_gc)
+        return r
 
     def sync_all():
         torch.cuda.synchronize()
@@ -257,7 +264,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    phase = {1: [], 2: [], 3: []}
+    phase = {1: [], 2: [], 3: [], 4: []}
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -306,12 +313,13 @@ def main():
             "metric": METRIC, "value": n * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{n} x {args.length} bp synthetic amplicons (seed {args.seed}), d=1, BASELINE configs[1]",
+            "config": {"workload": f"{n} x {args.length} bp synthetic amplicons (seed {args.seed}), d=1" + (" --fastidious, BASELINE configs[2]" if args.fastidious else ", BASELINE configs[1]"),
                        "enum_mode": "half" if args.enum_mode == 1 else "full", "filter_bytes_per_slot": args.bloom_bytes,
                        "l2": "inputs larger than L2 (packed db + table + filter = %.0f MB)" % ((pw.nbytes + 16 * 1.68e7 + 1.68e7) / 1e6),
                        "parallelism": f"seeds sharded over {world} GPU(s); links all-gathered (NCCL); clustering replicated"},
             "phases_ms": {"index": 1e3 * sum(phase[1]) / len(phase[1]), "network": 1e3 * net_s,
-                          "cluster": 1e3 * sum(phase[3]) / len(phase[3])},
+                          "cluster": 1e3 * sum(phase[3]) / len(phase[3]),
+                          "fastidious": (1e3 * sum(phase[4]) / len(phase[4])) if args.fastidious else None},
             "e2e": {"value": n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * dt_e2e / args.steps},
             "gpu_launches": launches,

@@ -34,9 +34,10 @@ enum {
 enum {
   SWB200_ENUM_FULL = 0,  /* every seed probes all <= 7L+4 microvariants, exactly the reference's
                             enumeration (src/variants.cc:184-249) */
-  SWB200_ENUM_HALF = 1   /* each unordered neighbour pair is discovered once (substitutions towards a
-                            higher base code + deletions only); both directed links are derived from
-                            the abundances.  ~3x fewer probes. Default. */
+  SWB200_ENUM_HALF = 1   /* each unordered neighbour pair is discovered once: deletions from the longer
+                            sequence, substitutions from the side picked by the base tournament
+                            0->1 0->2 1->2 1->3 2->3 3->0; both directed links are then derived from
+                            the abundances.  ~3x fewer probes.  Default. */
 };
 
 typedef struct swb200_ctx swb200_ctx;   /* owns the CUDA device, stream, and all device buffers */
@@ -102,7 +103,7 @@ double swb200_last_device_seconds(swb200_ctx *ctx);
 double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
- * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create. */
+ * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches. */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 
 /* Test hook: enumerate the microvariants of amplicon `seed` on the device exactly as the network

@@ -77,7 +77,8 @@ int64_t orc_d1_fastidious(const orc_db *db, uint64_t boundary, uint32_t bloom_bi
                           const uint32_t *swarmid, uint32_t *next,
                           uint32_t *sw_seed, uint32_t *sw_last, uint32_t *sw_size, uint32_t *sw_singletons,
                           uint64_t *sw_mass, uint64_t *sw_sumlen, uint8_t *sw_attached,
-                          uint32_t *graft_cand, uint64_t *stats /* NULL or [4] */);
+                          uint32_t *graft_cand, uint32_t *graft_raw /* NULL or n: min heavy id before the attach loop */,
+                          uint64_t *stats /* NULL or [4] */);
 
 void orc_free(void *p);
 

@@ -398,7 +398,7 @@ int64_t orc_d1_fastidious(const orc_db *db, uint64_t boundary, uint32_t bloom_bi
                           const uint32_t *swarmid, uint32_t *next,
                           uint32_t *sw_seed, uint32_t *sw_last, uint32_t *sw_size, uint32_t *sw_singletons,
                           uint64_t *sw_mass, uint64_t *sw_sumlen, uint8_t *sw_attached,
-                          uint32_t *graft_cand, uint64_t *stats) {
+                          uint32_t *graft_cand, uint32_t *graft_raw, uint64_t *stats) {
   const uint32_t n = db->n;
   (void)sw_seed;
   for (uint32_t i = 0; i < n; i++) graft_cand[i] = ORC_NONE;
@@ -470,6 +470,7 @@ int64_t orc_d1_fastidious(const orc_db *db, uint64_t boundary, uint32_t bloom_bi
       }
     }
   }
+  if (graft_raw) memcpy(graft_raw, graft_cand, (size_t)n * sizeof(uint32_t));
   /* attach_candidates :274-336, attach :214-241 */
   uint32_t pairs = 0;
   for (uint32_t i = 0; i < n; i++) if (graft_cand[i] != ORC_NONE) pairs++;

@@ -3,6 +3,7 @@
 // There is NO CPU fallback in this library: every entry point runs CUDA kernels or fails.
 #include "../../include/swarm_b200.h"
 #include "d1_kernels.cuh"
+#include "d1_fastidious.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -96,6 +97,11 @@ struct swb200_ctx {
   DevBuf<uint32_t> label, generation, parent;
   DevBuf<unsigned long long> key;
   bool clustered = false;
+  // fastidious
+  DevBuf<unsigned long long> mass, t2;
+  DevBuf<uint32_t> light_ids, heavy_ids, graft;
+  uint32_t max_len = 0;
+  uint64_t fstats[4] = {0, 0, 0, 0};
   // pinned staging
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -195,6 +201,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
+  c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -475,10 +482,72 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   API_END()
 }
 
-int swb200_d1_fastidious(swb200_ctx *c, uint64_t, uint32_t *, uint64_t *, uint64_t *) {
-  if (!c) { g_err = "null context"; return SWB200_EINVAL; }
-  g_err = "d1_fastidious: not built yet";
-  return SWB200_EUNSUPPORTED;
+int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand, uint64_t *n_light, uint64_t *n_heavy) {
+  API_BEGIN(c)
+  if (!c->clustered) { g_err = "d1_fastidious: call swb200_d1_cluster first"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  c->mass.alloc(n); c->light_ids.alloc(n); c->heavy_ids.alloc(n); c->graft.alloc(n);
+  FastParams F{};
+  F.P = c->params();
+  F.label = c->label.p; F.mass = c->mass.p; F.boundary = boundary;
+  F.light_ids = c->light_ids.p; F.heavy_ids = c->heavy_ids.p;
+  F.counts = reinterpret_cast<uint32_t *>(c->counters.p + 10);
+  F.graft_cand = c->graft.p;
+  F.fstats = c->counters.p + 12;
+  const int vb = (n + 255) / 256;
+  c->tic();
+  CK(cudaMemsetAsync(c->mass.p, 0, static_cast<size_t>(n) * 8, c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 10, 0, 6 * 8, c->stream));
+  k_fast_mass<<<vb, 256, 0, c->stream>>>(c->label.p, c->abundance.p, c->mass.p, n);
+  k_fast_split<<<vb, 256, 0, c->stream>>>(F);
+  c->launches += 2;
+  uint32_t counts[2] = {0, 0};
+  CK(cudaMemcpyAsync(counts, F.counts, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (n_light) *n_light = counts[0];
+  if (n_heavy) *n_heavy = counts[1];
+  if (counts[0] != 0 && counts[1] != 0) {        // otherwise nothing to graft (src/algod1.cc:1330-1334)
+    // multimap sizing: <= 7L+4 variants per light amplicon, 2.5 slots per entry, 4 slots per bucket
+    const uint64_t per_amp = 7ull * (static_cast<uint64_t>(c->stride) * 32) + 4;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->t2.n * 8;
+    const uint64_t budget_slots = static_cast<uint64_t>(free_b * 0.85) / 8;
+    uint64_t chunk = counts[0];
+    if (static_cast<double>(chunk) * per_amp * 2.5 > static_cast<double>(budget_slots))
+      chunk = std::max<uint64_t>(1, static_cast<uint64_t>(budget_slots / (per_amp * 2.5)));
+    // exact variant count is <= 7*len+4 with the real lengths; use the mean bound when the set is one chunk
+    const uint64_t slots = std::max<uint64_t>(64, static_cast<uint64_t>(static_cast<double>(chunk) * per_amp * 2.5) / 4 * 4);
+    c->t2.alloc(slots);
+    F.t2 = c->t2.p;
+    F.n_buckets = slots / 4;
+    const size_t zb = static_cast<size_t>(c->zlen) * 32;
+    const size_t smem_l = zb + 8 * static_cast<size_t>(c->stride) * 8;
+    const size_t smem_h = smem_l + 8 * sizeof(FastScratch);
+    CK(cudaFuncSetAttribute(k_fast_light, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_l)));
+    CK(cudaFuncSetAttribute(k_fast_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_h)));
+    int occ_l = 1, occ_h = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, k_fast_light, 256, smem_l));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_h, k_fast_heavy, 256, smem_h));
+    for (uint64_t at = 0; at < counts[0]; at += chunk) {
+      CK(cudaMemsetAsync(c->t2.p, 0xFF, slots * 8, c->stream));
+      F.ids = c->light_ids.p + at;
+      F.n_ids = static_cast<uint32_t>(std::min<uint64_t>(chunk, counts[0] - at));
+      k_fast_light<<<c->sm_count * std::max(occ_l, 1), 256, smem_l, c->stream>>>(F);
+      F.ids = c->heavy_ids.p;
+      F.n_ids = counts[1];
+      k_fast_heavy<<<c->sm_count * std::max(occ_h, 1), 256, smem_h, c->stream>>>(F);
+      c->launches += 2;
+    }
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(c->fstats, c->counters.p + 12, 32, cudaMemcpyDeviceToHost, c->stream));
+  c->toc(4);
+  if (graft_cand) {
+    CK(cudaMemcpyAsync(graft_cand, c->graft.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  API_END()
 }
 
 double swb200_last_device_seconds(swb200_ctx *c) { return c ? c->last_s : 0.0; }
@@ -488,6 +557,7 @@ int swb200_get_stats(swb200_ctx *c, uint64_t *out, int n) {
   if (!c || !out) { g_err = "null argument"; return SWB200_EINVAL; }
   c->stats[5] = c->launches;
   for (int i = 0; i < n && i < 8; ++i) out[i] = c->stats[i];
+  for (int i = 8; i < n && i < 12; ++i) out[i] = c->fstats[i - 8];
   return SWB200_OK;
 }
 

@@ -311,8 +311,8 @@ class Engine:
                                                _ptr(outs["parent"], _u32p)))
         return outs["swarm_of"], outs["generation"], outs["parent"]
 
-    def d1_fastidious(self, boundary=3):
-        gc = np.empty(self.n, dtype=np.uint32)
+    def d1_fastidious(self, boundary=3, want=True, out=None):
+        gc = (out if out is not None else np.empty(self.n, dtype=np.uint32)) if want else None
         nl, nh = C.c_uint64(), C.c_uint64()
         self._ck(engine_lib().swb200_d1_fastidious(self._h, int(boundary), _ptr(gc, _u32p), C.byref(nl), C.byref(nh)))
         return gc, nl.value, nh.value
@@ -324,10 +324,12 @@ class Engine:
         return engine_lib().swb200_phase_device_seconds(self._h, int(phase))
 
     def stats(self):
-        out = np.zeros(8, dtype=np.uint64)
-        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 8))
+        out = np.zeros(12, dtype=np.uint64)
+        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 12))
         return {"variants": int(out[0]), "filter_pass": int(out[1]), "slots_visited": int(out[2]),
-                "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5])}
+                "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5]),
+                "fast_light_variants": int(out[8]), "fast_heavy_variants": int(out[9]),
+                "fast_tag_matches": int(out[10]), "fast_verified": int(out[11])}
 
     def debug_variants(self, seed: int, mode: int, cap: int = 1 << 16):
         h = np.zeros(cap, dtype=np.uint64)

@@ -54,7 +54,7 @@ def oracle_lib():
         L.orc_d1_cluster.argtypes = [C.POINTER(OrcDb), _u32p, _u32p, _u32p] + [_u32p] * 4 + [_u32p] * 5 + [_u64p] * 2
         L.orc_d1_cluster.restype = C.c_uint32
         L.orc_d1_fastidious.argtypes = [C.POINTER(OrcDb), C.c_uint64, C.c_uint32, C.c_uint32, _u32p, _u32p,
-                                        _u32p, _u32p, _u32p, _u32p, _u64p, _u64p, _u8p, _u32p, _u64p]
+                                        _u32p, _u32p, _u32p, _u32p, _u64p, _u64p, _u8p, _u32p, _u32p, _u64p]
         L.orc_d1_fastidious.restype = C.c_int64
         L.orc_free.argtypes = [C.c_void_p]
         _orc = L
@@ -119,11 +119,12 @@ class Oracle:
         n = self.db.n
         self.sw_attached = np.zeros(n, dtype=np.uint8)
         self.graft_cand = np.zeros(n, dtype=np.uint32)
+        self.graft_raw = np.zeros(n, dtype=np.uint32)
         st = np.zeros(4, dtype=np.uint64)
         g = L.orc_d1_fastidious(C.byref(self.c), int(boundary), int(bloom_bits), int(self.nswarms), _p(self.swarmid, _u32p),
                                 _p(self.next, _u32p), _p(self.sw_seed, _u32p), _p(self.sw_last, _u32p), _p(self.sw_size, _u32p),
                                 _p(self.sw_singletons, _u32p), _p(self.sw_mass, _u64p), _p(self.sw_sumlen, _u64p),
-                                _p(self.sw_attached, _u8p), _p(self.graft_cand, _u32p), _p(st, _u64p))
+                                _p(self.sw_attached, _u8p), _p(self.graft_cand, _u32p), _p(self.graft_raw, _u32p), _p(st, _u64p))
         self.fast_stats = st
         return g
 

@@ -176,3 +176,56 @@ def test_large_set_properties(built, tmp_path):
         r = helpers.run_ref(fa, outputs=("o",), threads=8)
         res = D1Result(db, swf, genf, parf)
         assert res.swarms_text() == r["o"]
+
+
+@pytest.mark.parametrize("boundary,suffix", [(3, "f"), (10, "f.b10")])
+@pytest.mark.parametrize("name", CASES)
+def test_fastidious_golden(built, name, boundary, suffix):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    grafts = orc.fastidious(boundary=boundary)
+    eng = Engine(0)
+    eng.load(db)
+    eng.d1_index()
+    eng.d1_network()
+    sw, gen, par = eng.d1_cluster()
+    gc, nl, nh = eng.d1_fastidious(boundary=boundary)
+    eng.close()
+    if grafts >= 0:
+        assert np.array_equal(gc, orc.graft_raw), "graft candidates differ from the oracle"
+    else:
+        assert np.all(gc == 0xFFFFFFFF)
+    res = D1Result(db, sw, gen, par, graft_cand=gc, boundary=boundary)
+    assert res.swarms_text() == (GOLDEN / f"{name}.{suffix}.o").read_bytes()
+    if suffix == "f":
+        assert res.stats_text() == (GOLDEN / f"{name}.f.s").read_bytes()
+        assert res.structure_text() == (GOLDEN / f"{name}.f.i").read_bytes()
+
+
+@pytest.mark.parametrize("n,L,seed,mode_ab,boundary", [(30000, 150, 21, 0, 3), (20000, 60, 22, 1, 4), (8000, 400, 23, 0, 3)])
+def test_fastidious_seeded_vs_oracle(built, tmp_path, n, L, seed, mode_ab, boundary):
+    fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
+    db = HostDb(fa)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    grafts = orc.fastidious(boundary=boundary)
+    eng = Engine(0)
+    eng.load(db)
+    eng.d1_index()
+    eng.d1_network()
+    sw, gen, par = eng.d1_cluster()
+    gc, nl, nh = eng.d1_fastidious(boundary=boundary)
+    st = eng.stats()
+    eng.close()
+    assert grafts > 0 and np.array_equal(gc, orc.graft_raw)
+    assert st["fast_light_variants"] == int(orc.fast_stats[0])      # same microvariant count as the reference's light pass
+    assert st["fast_heavy_variants"] == int(orc.fast_stats[1])
+    res_g = D1Result(db, sw, gen, par, graft_cand=gc, boundary=boundary)
+    res_o = D1Result(db, orc.swarm_of, orc.generation, orc.parent, graft_cand=orc.graft_cand, boundary=boundary)
+    assert res_g.swarms_text() == res_o.swarms_text() and res_g.grafts == grafts
+    if helpers.have_ref():
+        r = helpers.run_ref(fa, "-f", "-b", str(boundary), outputs=("o", "s", "i"), threads=1)
+        assert res_g.swarms_text() == r["o"] and res_g.stats_text() == r["s"] and res_g.structure_text() == r["i"]
