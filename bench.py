@@ -210,28 +210,10 @@ def main():
     eng = Engine(local, enum_mode=args.enum_mode, bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0,
                  shard_rank=rank, shard_world=world)
 
-    def gather_links():
-        if world == 1:
-            return
-        ptr, m = eng.d1_links_device()
+    from swarm_b200.multi import exchange_engine_links
 
-        class _Dev:
-            def __init__(self, p, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (p, False), "version": 3}
-        cnt = torch.tensor([m], dtype=torch.int64, device="cuda")
-        cnts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        cnts = [int(c.item()) for c in cnts]
-        mx = max(max(cnts), 1)
-        mine = torch.zeros(mx * 8, dtype=torch.uint8, device="cuda")
-        if m:
-            mine[: m * 8] = torch.as_tensor(_Dev(ptr, m * 8), device="cuda")
-        allb = torch.empty(world * mx * 8, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allb, mine)
-        parts = [allb[r * mx * 8: r * mx * 8 + cnts[r] * 8] for r in range(world)]
-        merged = torch.cat(parts).contiguous()
-        torch.cuda.synchronize()
-        eng.d1_import_links_device(merged.data_ptr(), sum(cnts))
+    def gather_links():
+        exchange_engine_links(eng)
 
     def device_step():
         eng.d1_index()
