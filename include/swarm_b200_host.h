@@ -52,6 +52,17 @@ int  swbh_write_structure(const swbh_db *db, const swbh_result *r, int usearch_a
 int  swbh_write_seeds(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
 int  swbh_write_network(const swbh_db *db, const uint64_t *row_ptr, const uint32_t *col,
                         int usearch_abundance, int64_t append_abundance, char **out, uint64_t *out_len);
+/* d>1 result assembly + writers (src/algo.cc:259-325 `-o/-r`, :608-674 `-s`, :470-484,:573-586 `-i`).
+ * pdiff[i] = differences between i and its parent; radius is accumulated here.  The swarm lists use
+ * the same order as d=1 (seed, then generations, ids ascending: src/algo.cc:205-256), so
+ * swbh_write_swarms() serves both. */
+int  swbh_dn_assemble(const swbh_db *db, const uint32_t *swarm_of, const uint32_t *generation,
+                      const uint32_t *parent, const uint32_t *pdiff, swbh_result **out);
+int  swbh_dn_write_stats(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_dn_write_structure(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+/* alignment scoring conversion (src/swarm.cc:466-483): penalties[3] = mismatch, gap open, gap extend */
+void swbh_scoring(int64_t match_reward, int64_t mismatch_penalty, int64_t gap_open, int64_t gap_extend, int64_t penalties[3]);
+
 void swbh_free(void *p);
 
 #ifdef __cplusplus

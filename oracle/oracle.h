@@ -80,6 +80,17 @@ int64_t orc_d1_fastidious(const orc_db *db, uint64_t boundary, uint32_t bloom_bi
                           uint32_t *graft_cand, uint32_t *graft_raw /* NULL or n: min heavy id before the attach loop */,
                           uint64_t *stats /* NULL or [4] */);
 
+/* --- d>1 (oracle_dn.c): q-grams src/qgram.cc:68-96,247-252; scoring src/swarm.cc:466-483; aligner
+ * src/nw.cc:40-191; greedy loop src/algo.cc:384-602 --- */
+void     orc_findqgrams(const uint64_t *seq, uint32_t len, uint8_t *vec /* 128 bytes */);
+uint64_t orc_qgram_diff(const uint8_t *a, const uint8_t *b);
+void     orc_scoring(int64_t match, int64_t mismatch, int64_t gapopen, int64_t gapextend, int64_t out[3]);
+uint64_t orc_nw_diffs(const uint64_t *dseq, uint32_t dlen, const uint64_t *qseq, uint32_t qlen,
+                      int64_t mismatch, int64_t gapopen, int64_t gapextend, uint64_t *alnlen);
+uint32_t orc_dn_cluster(const orc_db *db, uint32_t d, int no_cluster_breaking, const int64_t pen[3],
+                        uint32_t *order, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent,
+                        uint32_t *pdiff, uint32_t *radius, uint64_t *stats /* NULL or [3] */);
+
 void orc_free(void *p);
 
 #ifdef __cplusplus

@@ -113,6 +113,11 @@ def host_lib():
         L.swbh_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_seeds.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_network.argtypes = [vp, _u64p, _u32p, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
+        L.swbh_dn_assemble.argtypes = [vp, _u32p, _u32p, _u32p, _u32p, C.POINTER(vp)]
+        L.swbh_dn_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_dn_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_scoring.argtypes = [C.c_int64] * 4 + [C.POINTER(C.c_int64)]
+        L.swbh_scoring.restype = None
         L.swbh_free.argtypes = [vp]
         L.swbh_free.restype = None
         del cpp
@@ -218,6 +223,36 @@ class D1Result:
             self.close()
         except Exception:
             pass
+
+
+class DnResult(D1Result):
+    """d>1 flavour: same swarm lists; stats carry max radius, structure lines carry the differences."""
+
+    def __init__(self, db: HostDb, swarm_of, generation, parent, pdiff):
+        L = host_lib()
+        self.db = db
+        self._keep = [np.ascontiguousarray(a, dtype=np.uint32) for a in (swarm_of, generation, parent, pdiff)]
+        h = C.c_void_p()
+        rc = L.swbh_dn_assemble(db._h, *[_ptr(a, _u32p) for a in self._keep], C.byref(h))
+        if rc != 0:
+            raise ValueError(L.swbh_last_error().decode())
+        self._h = h
+        self.swarms = L.swbh_result_swarms(h)
+        self.grafts = 0
+        self.largest = L.swbh_result_largest(h)
+        self.maxgen = max(1, L.swbh_result_maxgen(h))
+
+    def stats_text(self) -> bytes:
+        return self._text(host_lib().swbh_dn_write_stats, self.db._h, self._h, self.db.opts[0])
+
+    def structure_text(self) -> bytes:
+        return self._text(host_lib().swbh_dn_write_structure, self.db._h, self._h, self.db.opts[0])
+
+
+def scoring(match=5, mismatch=4, gap_open=12, gap_extend=4):
+    out = (C.c_int64 * 3)()
+    host_lib().swbh_scoring(match, mismatch, gap_open, gap_extend, out)
+    return list(out)
 
 
 def network_text(db: HostDb, row_ptr, col) -> bytes:

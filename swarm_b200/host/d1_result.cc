@@ -26,7 +26,8 @@ struct swbh_db {
 struct swbh_result {
   uint32_t n = 0;
   std::vector<uint32_t> swarm_no;       // per amplicon: swarm number (by seed order)
-  std::vector<uint32_t> generation, parent, graft_cand;
+  std::vector<uint32_t> generation, parent, graft_cand, pdiff, radius;
+  std::vector<uint32_t> maxradius;       // per swarm (d>1)
   // per swarm (before grafting numbering)
   std::vector<uint32_t> seed, size, singletons, maxgen;
   std::vector<uint64_t> mass, sumlen;
@@ -264,6 +265,73 @@ int swbh_write_network(const swbh_db *dbh, const uint64_t *row_ptr, const uint32
     for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) {
       swb::append_id(s, dbh->db, i, o); s += '\t';
       swb::append_id(s, dbh->db, col[k], o); s += '\n';
+    }
+  return give(s, out, out_len);
+}
+
+
+// ---- d>1 -----------------------------------------------------------------------------------------
+void swbh_scoring(int64_t m, int64_t p, int64_t g, int64_t e, int64_t pen[3]) {   // src/swarm.cc:466-483
+  int64_t mis = 2 * m + 2 * p, go = 2 * g, ge = m + 2 * e;
+  auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+  const int64_t f = gcd(gcd(mis, go), ge);
+  pen[0] = mis / f; pen[1] = go / f; pen[2] = ge / f;
+}
+
+int swbh_dn_assemble(const swbh_db *dbh, const uint32_t *swarm_of, const uint32_t *generation, const uint32_t *parent,
+                     const uint32_t *pdiff, swbh_result **out) {
+  swbh_result *r = nullptr;
+  if (swbh_d1_assemble(dbh, swarm_of, generation, parent, nullptr, 0, &r) != 0) return 1;
+  const uint32_t n = r->n;
+  r->pdiff.assign(pdiff, pdiff + n);
+  r->radius.assign(n, 0);
+  r->maxradius.assign(r->seed.size(), 0);
+  // members are stored generation by generation, so a parent's radius is final before its children's
+  for (uint32_t sw = 0; sw < r->seed.size(); ++sw)
+    for (uint64_t k = 0; k < r->own_size[sw]; ++k) {
+      const uint32_t a = r->members[r->first[sw] + k];
+      if (parent[a] != 0xFFFFFFFFu) r->radius[a] = r->radius[parent[a]] + pdiff[a];   // src/algo.cc:493,569
+      r->maxradius[sw] = std::max(r->maxradius[sw], r->radius[a]);
+    }
+  *out = r;
+  return 0;
+}
+
+// -s at d>1: src/algo.cc:660-674 — maxgen starts at 1 (:401), last column = max radius
+int swbh_dn_write_stats(const swbh_db *dbh, const swbh_result *r, int usearch, char **out, uint64_t *out_len) {
+  swb::DbOptions o; o.usearch_abundance = usearch != 0;
+  std::string s;
+  for (uint32_t sw = 0; sw < r->seed.size(); ++sw) {
+    s += std::to_string(r->size[sw]) + "\t" + std::to_string(r->mass[sw]) + "\t";
+    swb::append_id_noabundance(s, dbh->db, r->seed[sw], o);
+    s += "\t" + std::to_string(dbh->db.abundance[r->seed[sw]]) + "\t" + std::to_string(r->singletons[sw]) + "\t" +
+         std::to_string(std::max<uint32_t>(1, r->maxgen[sw])) + "\t" + std::to_string(r->maxradius[sw]) + "\n";
+  }
+  return give(s, out, out_len);
+}
+
+// -i at d>1: src/algo.cc:470-484, :573-586 — one line per accepted link, in discovery order: swarm by
+// swarm, (sub)seeds in list order, each one's hits in pool order (ascending id)
+int swbh_dn_write_structure(const swbh_db *dbh, const swbh_result *r, int usearch, char **out, uint64_t *out_len) {
+  swb::DbOptions o; o.usearch_abundance = usearch != 0;
+  const uint32_t n = r->n;
+  // children of every amplicon, ascending id
+  std::vector<uint64_t> cstart(static_cast<size_t>(n) + 1, 0);
+  for (uint32_t a = 0; a < n; ++a) if (r->parent[a] != 0xFFFFFFFFu) cstart[r->parent[a] + 1]++;
+  for (uint32_t a = 0; a < n; ++a) cstart[a + 1] += cstart[a];
+  std::vector<uint32_t> child(cstart[n]);
+  { std::vector<uint64_t> cur(cstart.begin(), cstart.end() - 1);
+    for (uint32_t a = 0; a < n; ++a) if (r->parent[a] != 0xFFFFFFFFu) child[cur[r->parent[a]]++] = a; }
+  std::string s;
+  for (uint32_t sw = 0; sw < r->seed.size(); ++sw)
+    for (uint64_t k = 0; k < r->own_size[sw]; ++k) {
+      const uint32_t par = r->members[r->first[sw] + k];
+      for (uint64_t c = cstart[par]; c < cstart[par + 1]; ++c) {
+        const uint32_t a = child[c];
+        swb::append_id_noabundance(s, dbh->db, par, o); s += '\t';
+        swb::append_id_noabundance(s, dbh->db, a, o);
+        s += "\t" + std::to_string(r->pdiff[a]) + "\t" + std::to_string(sw + 1) + "\t" + std::to_string(r->generation[a]) + "\n";
+      }
     }
   return give(s, out, out_len);
 }

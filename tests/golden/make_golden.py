@@ -86,6 +86,20 @@ def main():
         r = helpers.run_ref(fa, "-f", "-b", "10", outputs=("o",), threads=1)
         (HERE / f"{name}.f.b10.o").write_bytes(r["o"])
         print(name, "ok")
+    # d > 1 (the reference runs its SIMD aligners here): swarms, stats, structure
+    for name, flags, tag in [("handmade", ["-d", "2"], "d2"), ("c1_1k_150", ["-d", "2"], "d2"), ("short_600_20", ["-d", "2"], "d2"),
+                             ("short_600_20", ["-d", "3"], "d3"), ("tie_1500_60", ["-d", "2"], "d2"), ("tie_1500_60", ["-d", "2", "-n"], "d2n"),
+                             ("w65_300", ["-d", "3"], "d3"), ("w64_400", ["-d", "4"], "d4"),
+                             ("w32_400", ["-d", "2", "-m", "3", "-p", "2", "-g", "5", "-e", "3"], "d2pen")]:
+        r = helpers.run_ref(HERE / f"{name}.fasta", *flags, outputs=("o", "s", "i"), threads=2)
+        assert r["rc"] == 0, r["stderr"]
+        for k in "osi":
+            (HERE / f"{name}.{tag}.{k}").write_bytes(r[k])
+    helpers.make_fasta(HERE / "l400_250.fasta", 250, 400, 12, 0, 0.3)
+    r = helpers.run_ref(HERE / "l400_250.fasta", "-d", "2", outputs=("o", "s", "i"), threads=2)
+    for k in "osi":
+        (HERE / f"l400_250.d2.{k}").write_bytes(r[k])
+    print("d>1 ok")
     # usearch-style headers (-z) + mothur (-r): derived from c1 by rewriting headers
     src = (HERE / "c1_1k_150.fasta").read_bytes().splitlines()
     out = []

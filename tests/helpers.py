@@ -56,6 +56,14 @@ def oracle_lib():
         L.orc_d1_fastidious.argtypes = [C.POINTER(OrcDb), C.c_uint64, C.c_uint32, C.c_uint32, _u32p, _u32p,
                                         _u32p, _u32p, _u32p, _u32p, _u64p, _u64p, _u8p, _u32p, _u32p, _u64p]
         L.orc_d1_fastidious.restype = C.c_int64
+        L.orc_findqgrams.argtypes = [_u64p, C.c_uint32, _u8p]
+        L.orc_qgram_diff.argtypes = [_u8p, _u8p]
+        L.orc_qgram_diff.restype = C.c_uint64
+        L.orc_scoring.argtypes = [C.c_int64] * 4 + [C.POINTER(C.c_int64)]
+        L.orc_nw_diffs.argtypes = [_u64p, C.c_uint32, _u64p, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, _u64p]
+        L.orc_nw_diffs.restype = C.c_uint64
+        L.orc_dn_cluster.argtypes = [C.POINTER(OrcDb), C.c_uint32, C.c_int, C.POINTER(C.c_int64)] + [_u32p] * 6 + [_u64p]
+        L.orc_dn_cluster.restype = C.c_uint32
         L.orc_free.argtypes = [C.c_void_p]
         _orc = L
     return _orc
@@ -127,6 +135,33 @@ class Oracle:
                                 _p(self.sw_attached, _u8p), _p(self.graft_cand, _u32p), _p(self.graft_raw, _u32p), _p(st, _u64p))
         self.fast_stats = st
         return g
+
+    def scoring(self, m=5, p=4, g=12, e=4):
+        out = (C.c_int64 * 3)()
+        oracle_lib().orc_scoring(m, p, g, e, out)
+        return list(out)
+
+    def nw_diffs(self, q, t, pen):
+        """differences of the reference's optimal alignment, query amplicon q vs target amplicon t"""
+        L = oracle_lib()
+        s = self.db.stride
+        qs = np.ascontiguousarray(self.words[q * s:(q + 1) * s])
+        ts = np.ascontiguousarray(self.words[t * s:(t + 1) * s])
+        return L.orc_nw_diffs(_p(ts, _u64p), int(self.len[t]), _p(qs, _u64p), int(self.len[q]), pen[0], pen[1], pen[2], None)
+
+    def dn_cluster(self, d, no_cluster_breaking=False, pen=None):
+        L = oracle_lib()
+        n = self.db.n
+        pen = pen or self.scoring()
+        cp = (C.c_int64 * 3)(*pen)
+        a32 = lambda: np.zeros(n, dtype=np.uint32)
+        self.order, self.swarm_of, self.generation, self.parent, self.pdiff, self.radius = a32(), a32(), a32(), a32(), a32(), a32()
+        st = np.zeros(3, dtype=np.uint64)
+        self.nswarms = L.orc_dn_cluster(C.byref(self.c), int(d), int(no_cluster_breaking), cp, _p(self.order, _u32p),
+                                        _p(self.swarm_of, _u32p), _p(self.generation, _u32p), _p(self.parent, _u32p),
+                                        _p(self.pdiff, _u32p), _p(self.radius, _u32p), _p(st, _u64p))
+        self.dn_stats = st
+        return self.swarm_of, self.generation, self.parent, self.pdiff
 
     def swarm_lists(self):
         """final member lists (list order) of the non-attached swarms, following `next`"""
