@@ -97,13 +97,24 @@ int  swb200_d1_cluster(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation
 int  swb200_d1_fastidious(swb200_ctx *ctx, uint64_t boundary, uint32_t *graft_cand,
                           uint64_t *n_light_amplicons, uint64_t *n_heavy_amplicons);
 
+/* d>1: replaces algo_run's clustering (src/algo.cc:329-708): db_qgrams_init/findqgrams
+ * (src/qgram.cc:68-96), the q-gram prefilter (qgram_diff, src/qgram.cc:247-252), search_do -> search8 /
+ * search16 + backtrack (src/scan.cc:221-256, src/search16.cc:207-230, src/utils/backtrack.h:51-138) and
+ * the greedy loop (src/algo.cc:384-602).  penalties = converted mismatch, gap-open, gap-extend costs
+ * (src/swarm.cc:466-483; defaults 18, 24, 13).  Outputs as swb200_d1_cluster plus pdiff[i] = number of
+ * differences between i and its parent (the -i file's third column).  Needs only swb200_load_db.
+ * Duplicate sequences must be rejected by the host at d>1 (src/db.cc:763-796). */
+int  swb200_dn_cluster(swb200_ctx *ctx, uint32_t d, int no_cluster_breaking, const int64_t penalties[3],
+                       uint32_t *swarm_of, uint32_t *generation, uint32_t *parent, uint32_t *pdiff);
+
 /* Device time (CUDA events on the engine's stream) of the last call, and accumulated per phase.
- * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 5 csr */
+ * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 6 d>1 (all of swb200_dn_cluster) */
 double swb200_last_device_seconds(swb200_ctx *ctx);
 double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
- * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches. */
+ * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
+ * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links. */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 
 /* Test hook: enumerate the microvariants of amplicon `seed` on the device exactly as the network

@@ -4,6 +4,7 @@
 #include "../../include/swarm_b200.h"
 #include "d1_kernels.cuh"
 #include "d1_fastidious.cuh"
+#include "dn_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -102,6 +103,10 @@ struct swb200_ctx {
   DevBuf<uint32_t> light_ids, heavy_ids, graft;
   uint32_t max_len = 0;
   uint64_t fstats[4] = {0, 0, 0, 0};
+  // d>1
+  DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
+  DevBuf<uint2> tasks;
+  uint64_t dnstats[4] = {0, 0, 0, 0};
   // pinned staging
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -202,6 +207,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
+  c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -286,6 +292,12 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   if (static_cast<size_t>(c->zlen) * 32 > 160 * 1024) {
     g_err = "sequences longer than 5,000 nt are not supported by the on-chip Zobrist table";
     return SWB200_EUNSUPPORTED;
+  }
+  {
+    CK(cudaMemsetAsync(c->counters.p + 15, 0, 8, c->stream));
+    k_max_u32<<<c->sm_count * 2, 256, 0, c->stream>>>(c->len.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 15));
+    CK(cudaMemcpyAsync(&c->max_len, c->counters.p + 15, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->launches++;
   }
   c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
   uint64_t sm = 0x5eedb200c0ffeeULL;
@@ -438,9 +450,7 @@ int swb200_d1_get_network(swb200_ctx *c, uint64_t *row_ptr, uint32_t *col) {
   API_END()
 }
 
-int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
-  API_BEGIN(c)
-  if (!c->have_network) { g_err = "d1_cluster: call swb200_d1_network first"; return SWB200_EINVAL; }
+static void run_cluster(swb200_ctx *c) {
   const uint32_t n = c->n;
   const uint64_t m = c->n_edges;
   c->label.alloc(n); c->generation.alloc(n); c->parent.alloc(n); c->key.alloc(n);
@@ -448,7 +458,6 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
-  c->tic();
   k_label_init<<<vb, 256, 0, c->stream>>>(c->label.p, n);
   c->launches++;
   for (int round = 0; m > 0 && round < 1 << 20; ++round) {
@@ -473,11 +482,99 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   k_bfs_unpack<<<vb, 256, 0, c->stream>>>(c->key.p, c->generation.p, c->parent.p, n);
   c->launches++;
   CK(cudaGetLastError());
+}
+
+int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
+  API_BEGIN(c)
+  if (!c->have_network) { g_err = "d1_cluster: call swb200_d1_network first"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  c->tic();
+  run_cluster(c);
   c->toc(3);
   c->clustered = true;
   if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (parent) CK(cudaMemcpyAsync(parent, c->parent.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const int64_t penalties[3], uint32_t *swarm_of,
+                      uint32_t *generation, uint32_t *parent, uint32_t *pdiff) {
+  API_BEGIN(c)
+  if (c->n == 0 || !penalties || d < 2) { g_err = "dn_cluster: needs a database, penalties and d >= 2"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  const int64_t mis = penalties[0], go = penalties[1], ge = penalties[2];
+  if (mis <= 0 || go < 0 || ge <= 0) { g_err = "dn_cluster: bad penalties"; return SWB200_EINVAL; }
+  const int64_t B = static_cast<int64_t>(d) * std::max(mis, go + ge);
+  const int64_t w64 = B >= go + ge ? (B - go) / ge : 0;
+  if (w64 > 15 || B > (1 << 24)) {
+    g_err = "dn_cluster: band half-width " + std::to_string(w64) + " > 15 (d too large for this scoring system) is not supported yet";
+    return SWB200_EUNSUPPORTED;
+  }
+  DnParams P{};
+  P.words = c->words.p; P.len = c->len.p; P.abundance = c->abundance.p;
+  P.n = n; P.stride = c->stride; P.d = d; P.ncb = no_cluster_breaking ? 1 : 0;
+  P.mismatch = static_cast<int32_t>(mis); P.gapopen = static_cast<int32_t>(go); P.gapextend = static_cast<int32_t>(ge);
+  P.bound = static_cast<int32_t>(B); P.w = static_cast<uint32_t>(w64); P.max_popc = 10 * d;
+  P.max_len = c->max_len;
+  c->qgrams.alloc(static_cast<size_t>(n) * 32);
+  P.qgrams = c->qgrams.p;
+  P.task_count = c->counters.p; P.edge_count = c->counters.p + 1; P.stats = c->counters.p + 2;
+  c->tic();
+  CK(cudaMemsetAsync(c->counters.p, 0, 8 * 8, c->stream));
+  k_dn_qgrams<<<c->sm_count * 8, 256, 0, c->stream>>>(c->words.p, c->len.p, c->stride, n, c->qgrams.p);
+  c->launches++;
+  if (c->tasks.n == 0) c->tasks.alloc(std::max<size_t>(static_cast<size_t>(n) * 16, 1u << 20));
+  unsigned long long ntasks = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    P.tasks = c->tasks.p; P.task_cap = c->tasks.n;
+    CK(cudaMemsetAsync(c->counters.p, 0, 8, c->stream));
+    k_dn_filter<<<(n + 255) / 256, 256, 0, c->stream>>>(P, 0, (n + kDnTileQ - 1) / kDnTileQ);
+    c->launches++;
+    CK(cudaMemcpyAsync(&ntasks, c->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (ntasks <= c->tasks.n) break;
+    c->tasks.alloc(ntasks + ntasks / 8);
+  }
+  c->edges.alloc(std::max<uint64_t>(ntasks, 1));
+  c->ediff.alloc(std::max<uint64_t>(ntasks, 1));
+  P.edges = c->edges.p; P.ediff = c->ediff.p; P.edge_cap = c->edges.n;
+  if (ntasks) {
+    const uint32_t nb = 2 * P.w + 1;
+    P.dir_words = (nb + 7) / 8;
+    const uint64_t per_thread = static_cast<uint64_t>(std::max<uint32_t>(c->max_len, 1)) * P.dir_words * 4;
+    uint64_t threads = static_cast<uint64_t>(c->sm_count) * 16 * 128;
+    while (threads > 128 * static_cast<uint64_t>(c->sm_count) && threads * per_thread > (4ull << 30)) threads /= 2;
+    threads = std::min<uint64_t>(threads, (ntasks + 127) / 128 * 128);
+    c->dirs.alloc(threads * per_thread / 4);
+    P.dirs = c->dirs.p;
+    const int grid = static_cast<int>(threads / 128);
+    if (P.w <= 4) k_dn_align<4><<<grid, 128, 0, c->stream>>>(P, 0, ntasks);
+    else if (P.w <= 8) k_dn_align<8><<<grid, 128, 0, c->stream>>>(P, 0, ntasks);
+    else k_dn_align<16><<<grid, 128, 0, c->stream>>>(P, 0, ntasks);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  unsigned long long host[5];
+  CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_edges = host[1];
+  c->dnstats[0] = host[2]; c->dnstats[1] = host[3]; c->dnstats[2] = host[4]; c->dnstats[3] = c->n_edges;
+  c->have_network = true;
+  run_cluster(c);
+  c->pdiff.alloc(n);
+  CK(cudaMemsetAsync(c->pdiff.p, 0, static_cast<size_t>(n) * 4, c->stream));
+  if (c->n_edges) {
+    k_dn_pdiff<<<c->sm_count * 4, 256, 0, c->stream>>>(c->edges.p, c->ediff.p, c->n_edges, c->parent.p, c->pdiff.p);
+    c->launches++;
+  }
+  c->toc(6);
+  c->clustered = true;
+  if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (parent) CK(cudaMemcpyAsync(parent, c->parent.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (pdiff) CK(cudaMemcpyAsync(pdiff, c->pdiff.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   API_END()
 }
@@ -558,6 +655,7 @@ int swb200_get_stats(swb200_ctx *c, uint64_t *out, int n) {
   c->stats[5] = c->launches;
   for (int i = 0; i < n && i < 8; ++i) out[i] = c->stats[i];
   for (int i = 8; i < n && i < 12; ++i) out[i] = c->fstats[i - 8];
+  for (int i = 12; i < n && i < 16; ++i) out[i] = c->dnstats[i - 12];
   return SWB200_OK;
 }
 

@@ -60,6 +60,7 @@ def engine_lib():
         L.swb200_d1_import_links_device.argtypes = [vp, vp, C.c_uint64]
         L.swb200_d1_cluster.argtypes = [vp, _u32p, _u32p, _u32p]
         L.swb200_d1_fastidious.argtypes = [vp, C.c_uint64, _u32p, _u64p, _u64p]
+        L.swb200_dn_cluster.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(C.c_int64), _u32p, _u32p, _u32p, _u32p]
         L.swb200_last_device_seconds.argtypes = [vp]
         L.swb200_last_device_seconds.restype = C.c_double
         L.swb200_phase_device_seconds.argtypes = [vp, C.c_int]
@@ -352,6 +353,13 @@ class Engine:
         self._ck(engine_lib().swb200_d1_fastidious(self._h, int(boundary), _ptr(gc, _u32p), C.byref(nl), C.byref(nh)))
         return gc, nl.value, nh.value
 
+    def dn_cluster(self, d, no_cluster_breaking=False, penalties=(18, 24, 13)):
+        outs = [np.empty(self.n, dtype=np.uint32) for _ in range(4)]
+        pen = (C.c_int64 * 3)(*penalties)
+        self._ck(engine_lib().swb200_dn_cluster(self._h, int(d), int(bool(no_cluster_breaking)), pen,
+                                               *[_ptr(a, _u32p) for a in outs]))
+        return tuple(outs)
+
     def last_device_seconds(self) -> float:
         return engine_lib().swb200_last_device_seconds(self._h)
 
@@ -359,12 +367,14 @@ class Engine:
         return engine_lib().swb200_phase_device_seconds(self._h, int(phase))
 
     def stats(self):
-        out = np.zeros(12, dtype=np.uint64)
-        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 12))
+        out = np.zeros(16, dtype=np.uint64)
+        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 16))
         return {"variants": int(out[0]), "filter_pass": int(out[1]), "slots_visited": int(out[2]),
                 "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5]),
                 "fast_light_variants": int(out[8]), "fast_heavy_variants": int(out[9]),
-                "fast_tag_matches": int(out[10]), "fast_verified": int(out[11])}
+                "fast_tag_matches": int(out[10]), "fast_verified": int(out[11]),
+                "dn_qgram_comparisons": int(out[12]), "dn_alignments": int(out[13]), "dn_pruned": int(out[14]),
+                "dn_links": int(out[15])}
 
     def debug_variants(self, seed: int, mode: int, cap: int = 1 << 16):
         h = np.zeros(cap, dtype=np.uint64)

@@ -5,7 +5,7 @@ import pytest
 
 import helpers
 from helpers import GOLDEN, Oracle
-from swarm_b200 import ENUM_FULL, ENUM_HALF, D1Result, Engine, EngineError, HostDb
+from swarm_b200 import ENUM_FULL, ENUM_HALF, D1Result, DnResult, Engine, EngineError, HostDb, scoring
 from swarm_b200.ffi import network_text
 
 pytestmark = pytest.mark.gpu
@@ -229,3 +229,45 @@ def test_fastidious_seeded_vs_oracle(built, tmp_path, n, L, seed, mode_ab, bound
     if helpers.have_ref():
         r = helpers.run_ref(fa, "-f", "-b", str(boundary), outputs=("o", "s", "i"), threads=1)
         assert res_g.swarms_text() == r["o"] and res_g.stats_text() == r["s"] and res_g.structure_text() == r["i"]
+
+
+DN_CASES = [("handmade", 2, False, None, "d2"), ("c1_1k_150", 2, False, None, "d2"), ("short_600_20", 2, False, None, "d2"),
+            ("short_600_20", 3, False, None, "d3"), ("tie_1500_60", 2, False, None, "d2"), ("tie_1500_60", 2, True, None, "d2n"),
+            ("w65_300", 3, False, None, "d3"), ("w64_400", 4, False, None, "d4"), ("w32_400", 2, False, (3, 2, 5, 3), "d2pen"),
+            ("l400_250", 2, False, None, "d2")]
+
+
+@pytest.mark.parametrize("name,d,ncb,pen,tag", DN_CASES)
+def test_dn_golden(built, name, d, ncb, pen, tag):
+    db = HostDb(GOLDEN / f"{name}.fasta", check_dup_sequences=True)
+    p = scoring(*pen) if pen else scoring()
+    orc = Oracle(db)
+    osw, ogen, opar, opd = orc.dn_cluster(d, no_cluster_breaking=ncb, pen=p)
+    eng = Engine(0)
+    eng.load(db)
+    sw, gen, par, pd = eng.dn_cluster(d, no_cluster_breaking=ncb, penalties=p)
+    eng.close()
+    assert np.array_equal(sw, osw) and np.array_equal(gen, ogen) and np.array_equal(par, opar) and np.array_equal(pd, opd)
+    res = DnResult(db, sw, gen, par, pd)
+    assert res.swarms_text() == (GOLDEN / f"{name}.{tag}.o").read_bytes()
+    assert res.stats_text() == (GOLDEN / f"{name}.{tag}.s").read_bytes()
+    assert res.structure_text() == (GOLDEN / f"{name}.{tag}.i").read_bytes()
+
+
+@pytest.mark.parametrize("n,L,seed,mode_ab,d", [(4000, 100, 31, 0, 2), (3000, 60, 32, 1, 3), (2500, 400, 33, 0, 2), (2000, 150, 34, 1, 5)])
+def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab, d):
+    fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
+    db = HostDb(fa, check_dup_sequences=True)
+    orc = Oracle(db)
+    osw, ogen, opar, opd = orc.dn_cluster(d)
+    eng = Engine(0)
+    eng.load(db)
+    sw, gen, par, pd = eng.dn_cluster(d)
+    st = eng.stats()
+    eng.close()
+    assert np.array_equal(sw, osw) and np.array_equal(gen, ogen) and np.array_equal(par, opar) and np.array_equal(pd, opd)
+    assert st["dn_links"] >= int(orc.dn_stats[2])      # all directed links vs the greedy loop's accepted ones
+    if helpers.have_ref():
+        r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
+        res = DnResult(db, sw, gen, par, pd)
+        assert res.swarms_text() == r["o"] and res.stats_text() == r["s"] and res.structure_text() == r["i"]
