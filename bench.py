@@ -307,7 +307,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_d1_network", "bytes_per_amplicon_counted": b1_counted,
+                         "traffic": None, "kernel": "k_d1_network_half" if args.enum_mode == 1 else "k_d1_network<FULL>", "bytes_per_amplicon_counted": b1_counted,
                          "bytes_per_amplicon_survey_formula_full_enumeration": b1_survey,
                          "achieved_if_counted_as_full_enumeration": seeds * b1_survey / net_s / 1e9,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},

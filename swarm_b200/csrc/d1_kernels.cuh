@@ -129,7 +129,8 @@ struct WarpScratch {
   uint2 edges[kEdgeCap];
 };
 
-__device__ __forceinline__ void flush_edges(const D1Params &P, WarpScratch &S, uint32_t &en, uint32_t lane) {
+template <typename SCR>
+__device__ __forceinline__ void flush_edges(const D1Params &P, SCR &S, uint32_t &en, uint32_t lane) {
   if (en == 0) return;
   unsigned long long base = 0;
   if (lane == 0) base = atomicAdd(P.edge_count, static_cast<unsigned long long>(en));
@@ -172,8 +173,8 @@ __device__ __forceinline__ uint64_t variant_word(const uint64_t *sw, uint32_t nw
 // (src/algod1.cc:568-602) + check_variant (src/variants.cc:118-165), 4 survivors per step, 8 lanes
 // each.  MODE 0 = FULL (link seed->amp under the abundance rule), 1 = HALF (pair found once; derive
 // both directions).
-template <int MODE, bool STATS>
-__device__ __forceinline__ void drain_queue(const D1Params &P, WarpScratch &S, const uint64_t *sw, uint32_t seed,
+template <int MODE, bool STATS, typename SCR>
+__device__ __forceinline__ void drain_queue(const D1Params &P, SCR &S, const uint64_t *sw, uint32_t seed,
                                             uint32_t L, uint32_t &qn, uint32_t &en, uint32_t lane,
                                             unsigned long long &st_slots, unsigned long long &st_cmp) {
   const uint32_t sub = lane >> 3, j = lane & 7u;
@@ -275,7 +276,7 @@ __device__ __forceinline__ void probe_batch(const D1Params &P, WarpScratch &S, c
     const uint32_t bal = __ballot_sync(kFull, pass);
     if (bal) {
       const uint32_t cnt = __popc(bal);
-      if (qn + cnt > kQueueCap) drain_queue<MODE, STATS>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
+      if (qn + cnt > kQueueCap) drain_queue<MODE, STATS, WarpScratch>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
       if (pass) {
         const uint32_t at = qn + __popc(bal & ((1u << lane) - 1u));
         S.qhash[at] = vh[k];
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MODE == 0 ? 2 : 3) k_d1_net
         probe_batch<MODE, NV, STATS>(P, S, sw, seed, L, vv, vh, vc, qn, en, lane, st_pass, st_slots, st_cmp);
       };
       enumerate_variants<MODE>(zs, sw, L, lane, emit);
-      if (qn) drain_queue<MODE, STATS>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
+      if (qn) drain_queue<MODE, STATS, WarpScratch>(P, S, sw, seed, L, qn, en, lane, st_slots, st_cmp);
     }
     __syncwarp();                                // all lanes done reading the tile before it is re-filled
     cur ^= 1;

@@ -3,6 +3,7 @@
 // There is NO CPU fallback in this library: every entry point runs CUDA kernels or fails.
 #include "../../include/swarm_b200.h"
 #include "d1_kernels.cuh"
+#include "d1_network_v2.cuh"
 #include "d1_fastidious.cuh"
 #include "dn_kernels.cuh"
 
@@ -78,6 +79,7 @@ struct swb200_ctx {
   int bloom_bytes_per_slot = 1;
   int collect_stats = 0;
   int shard_rank = 0, shard_world = 1;
+  int net_kernel = 0;   // 0 auto, 1 = k_d1_network (v1), 2 = k_d1_network_half (v2, HALF only)
   // database
   uint32_t n = 0, n_padded = 0, stride = 0, longest = 0, batch = 2, zlen = 0;
   DevBuf<uint64_t> words, abundance, ztab, hashes;
@@ -221,6 +223,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   if (k == "enum_mode" && (v == SWB200_ENUM_FULL || v == SWB200_ENUM_HALF)) c->enum_mode = static_cast<int>(v);
   else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
   else if (k == "collect_stats") c->collect_stats = v != 0;
+  else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -348,8 +351,7 @@ static void run_network(swb200_ctx *c) {
   P.seed_begin = static_cast<uint32_t>(b0 * c->batch);
   P.seed_end = static_cast<uint32_t>(std::min<uint64_t>(b1 * c->batch, c->n));
   if (P.seed_begin > P.seed_end) P.seed_begin = P.seed_end;
-  const size_t smem = c->network_smem();
-  auto launch = [&](auto kernel) {
+  auto launch = [&](auto kernel, size_t smem) {
     int occ = 1;
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWarpsPerCta * 32, smem));
@@ -357,8 +359,14 @@ static void run_network(swb200_ctx *c) {
     kernel<<<c->sm_count * occ, kWarpsPerCta * 32, smem, c->stream>>>(P);
   };
   const bool st = c->collect_stats != 0;
-  if (c->enum_mode == SWB200_ENUM_FULL) { if (st) launch(k_d1_network<0, true>); else launch(k_d1_network<0, false>); }
-  else { if (st) launch(k_d1_network<1, true>); else launch(k_d1_network<1, false>); }
+  const size_t smem1 = c->network_smem();
+  const size_t smem2 = static_cast<size_t>(c->zlen) * kTStride + static_cast<size_t>(kWarpsPerCta) * 2 * c->batch * c->stride * 8 +
+                       static_cast<size_t>(kWarpsPerCta) * sizeof(WarpScratch2) + kWarpsPerCta * 2 * 8;
+  const bool v2_ok = c->enum_mode == SWB200_ENUM_HALF && static_cast<size_t>(c->zlen) * kTStride <= 60 * 1024 && c->max_len <= 990;
+  const bool use_v2 = v2_ok && c->net_kernel != 1;
+  if (use_v2) { if (st) launch(k_d1_network_half<true>, smem2); else launch(k_d1_network_half<false>, smem2); }
+  else if (c->enum_mode == SWB200_ENUM_FULL) { if (st) launch(k_d1_network<0, true>, smem1); else launch(k_d1_network<0, false>, smem1); }
+  else { if (st) launch(k_d1_network<1, true>, smem1); else launch(k_d1_network<1, false>, smem1); }
   CK(cudaGetLastError());
   c->launches += 1;
 }

@@ -114,6 +114,17 @@ def test_no_cluster_breaking(built, name, mode):
     assert res.swarms_text() == (GOLDEN / f"{name}.n.o").read_bytes()
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_lean_half_kernel_matches_first_kernel(built, name):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    orc.network()
+    l1, *_r1, s1 = run_engine(db, ENUM_HALF, net_kernel=1)
+    l2, *_r2, s2 = run_engine(db, ENUM_HALF, net_kernel=2)
+    assert np.array_equal(l1, l2) and np.array_equal(l2, orc.links())
+    assert s1["variants"] == s2["variants"] and s1["filter_pass"] == s2["filter_pass"]
+
+
 def test_duplicates_rejected(built):
     db = HostDb(text=b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>c_1\nACGTACGA\n")
     eng = Engine(0)
@@ -131,8 +142,8 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for mode in (ENUM_FULL, ENUM_HALF):
-        links, sw, gen, par, *_ = run_engine(db, mode)
+    for mode, opt in ((ENUM_FULL, {}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2})):
+        links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
         assert np.array_equal(gen, orc.generation)
@@ -161,7 +172,9 @@ def test_large_set_properties(built, tmp_path):
     fa = helpers.make_fasta(tmp_path / "big.fa", 1000000, 150, 11, 0)
     db = HostDb(fa)
     lf, swf, genf, parf, *_ = run_engine(db, ENUM_FULL)
-    lh, swh, genh, parh, *_ = run_engine(db, ENUM_HALF)
+    lh, swh, genh, parh, *_ = run_engine(db, ENUM_HALF, net_kernel=2)
+    l1, *_ = run_engine(db, ENUM_HALF, net_kernel=1)
+    assert np.array_equal(l1, lh)
     assert np.array_equal(lf, lh) and np.array_equal(swf, swh) and np.array_equal(genf, genh) and np.array_equal(parf, parh)
     src, dst = lf[:, 0].astype(np.int64), lf[:, 1].astype(np.int64)
     assert np.all(db.abundance[src] >= db.abundance[dst])
