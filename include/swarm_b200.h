@@ -50,6 +50,7 @@ const char *swb200_last_error(void);
 /* Tunables (call before swb200_d1_index).  key: "enum_mode" (SWB200_ENUM_*), "bloom_bytes_per_slot"
  * (1,2,4,8: filter size = table slots * this; reference uses 1, src/algod1.cc:1127),
  * "collect_stats" (0/1), "net_kernel" (0 auto, 1 first-generation kernel, 2 lean HALF kernel),
+ * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
  * "shard_rank"/"shard_world" (seeds [rank*n/world, (rank+1)*n/world) are
  * this context's share of the network build). */
 int  swb200_set_option(swb200_ctx *ctx, const char *key, int64_t value);

@@ -24,12 +24,13 @@
 
 namespace swb {
 
-__global__ void k_max_u32(const uint32_t *v, uint32_t n, uint32_t *out) {
-  uint32_t m = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+// out[0] = max, out[1] = ~min (both start at 0)
+__global__ void k_minmax_u32(const uint32_t *v, uint32_t n, uint32_t *out) {
+  uint32_t m = 0, w = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { m = max(m, v[i]); w = max(w, ~v[i]); }
 #pragma unroll
-  for (int k = 16; k >= 1; k >>= 1) m = max(m, __shfl_xor_sync(kFull, m, k));
-  if ((threadIdx.x & 31u) == 0) atomicMax(out, m);
+  for (int k = 16; k >= 1; k >>= 1) { m = max(m, __shfl_xor_sync(kFull, m, k)); w = max(w, __shfl_xor_sync(kFull, w, k)); }
+  if ((threadIdx.x & 31u) == 0) { atomicMax(out, m); atomicMax(out + 1, w); }
 }
 
 // ---- q-gram parity vectors (a10) ------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include "d1_kernels.cuh"
 #include "d1_network_v2.cuh"
 #include "d1_fastidious.cuh"
+#include "d1_fastidious_join.cuh"
 #include "dn_kernels.cuh"
 
 #include <algorithm>
@@ -103,7 +104,11 @@ struct swb200_ctx {
   // fastidious
   DevBuf<unsigned long long> mass, t2;
   DevBuf<uint32_t> light_ids, heavy_ids, graft;
-  uint32_t max_len = 0;
+  uint32_t max_len = 0, min_len = 0;
+  uint32_t minmax[2] = {0, 0};
+  int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
+  DevBuf<uint8_t> is_light;
+  DevBuf<uint2> cands;
   uint64_t fstats[4] = {0, 0, 0, 0};
   // d>1
   DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
@@ -209,6 +214,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
+  c->is_light.release(); c->cands.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -224,6 +230,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
   else if (k == "collect_stats") c->collect_stats = v != 0;
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
+  else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -298,8 +305,8 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   }
   {
     CK(cudaMemsetAsync(c->counters.p + 15, 0, 8, c->stream));
-    k_max_u32<<<c->sm_count * 2, 256, 0, c->stream>>>(c->len.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 15));
-    CK(cudaMemcpyAsync(&c->max_len, c->counters.p + 15, 4, cudaMemcpyDeviceToHost, c->stream));
+    k_minmax_u32<<<c->sm_count * 2, 256, 0, c->stream>>>(c->len.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 15));
+    CK(cudaMemcpyAsync(c->minmax, c->counters.p + 15, 8, cudaMemcpyDeviceToHost, c->stream));
     c->launches++;
   }
   c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
@@ -308,6 +315,8 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   c->ztab.alloc(c->h_ztab.size());
   CK(cudaMemcpyAsync(c->ztab.p, c->h_ztab.data(), c->h_ztab.size() * 8, cudaMemcpyHostToDevice, c->stream));
   c->toc(0);
+  c->max_len = c->minmax[0];
+  c->min_len = ~c->minmax[1];
   API_END()
 }
 
@@ -591,6 +600,67 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
   API_BEGIN(c)
   if (!c->clustered) { g_err = "d1_fastidious: call swb200_d1_cluster first"; return SWB200_EINVAL; }
   const uint32_t n = c->n;
+  const uint32_t Kj = std::min<uint32_t>(64, c->min_len / 3);
+  if (c->fast_kernel != 1 && Kj >= 8) {
+    // ---- pigeonhole join (d1_fastidious_join.cuh) ----
+    c->mass.alloc(n); c->graft.alloc(n); c->is_light.alloc(n);
+    uint32_t *counts_d = reinterpret_cast<uint32_t *>(c->counters.p + 10);
+    const int vb = (n + 255) / 256;
+    c->tic();
+    CK(cudaMemsetAsync(c->mass.p, 0, static_cast<size_t>(n) * 8, c->stream));
+    CK(cudaMemsetAsync(c->counters.p + 10, 0, 6 * 8, c->stream));
+    k_fast_mass<<<vb, 256, 0, c->stream>>>(c->label.p, c->abundance.p, c->mass.p, n);
+    k_fj_flags<<<vb, 256, 0, c->stream>>>(c->label.p, c->mass.p, boundary, n, c->is_light.p, c->graft.p, counts_d);
+    c->launches += 2;
+    uint32_t counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(counts, counts_d, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_light) *n_light = counts[0];
+    if (n_heavy) *n_heavy = counts[1];
+    if (counts[0] != 0 && counts[1] != 0) {
+      JoinParams J{};
+      J.words = c->words.p; J.len = c->len.p; J.n = n; J.stride = c->stride; J.K = Kj;
+      J.is_light = c->is_light.p; J.graft_cand = c->graft.p; J.fstats = c->counters.p + 12;
+      const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(counts[0]) * 3 * 5 / 2 + 3) / 4 * 4);
+      c->t2.alloc(slots);
+      J.table = c->t2.p; J.n_buckets = slots / 4;
+      CK(cudaMemsetAsync(c->t2.p, 0xFF, slots * 8, c->stream));
+      k_fj_insert<<<vb, 256, 0, c->stream>>>(J);
+      c->launches++;
+      if (c->cands.n == 0) c->cands.alloc(std::max<size_t>(static_cast<size_t>(n) * 4, 1u << 20));
+      J.cand_count = c->counters.p + 11;
+      uint32_t chunk = std::max<uint32_t>(1, (n + 15) / 16);
+      for (uint32_t a0 = 0; a0 < n;) {
+        const uint32_t a1 = static_cast<uint32_t>(std::min<uint64_t>(n, static_cast<uint64_t>(a0) + chunk));
+        J.cands = c->cands.p; J.cand_cap = c->cands.n;
+        CK(cudaMemsetAsync(c->counters.p + 11, 0, 8, c->stream));
+        const uint64_t threads = static_cast<uint64_t>(a1 - a0) * 7;
+        k_fj_candidates<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(J, a0, a1);
+        c->launches++;
+        unsigned long long m = 0;
+        CK(cudaMemcpyAsync(&m, c->counters.p + 11, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (m > c->cands.n) {                       // candidate list overflow: retry this range with a smaller chunk / larger buffer
+          if (chunk > 1024) { chunk /= 2; continue; }
+          c->cands.alloc(m + m / 8);
+          continue;
+        }
+        if (m) {
+          k_fj_verify<<<static_cast<unsigned>((m + 255) / 256), 256, 0, c->stream>>>(J, m);
+          c->launches++;
+        }
+        a0 = a1;
+      }
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(c->fstats, c->counters.p + 12, 32, cudaMemcpyDeviceToHost, c->stream));
+    c->toc(4);
+    if (graft_cand) {
+      CK(cudaMemcpyAsync(graft_cand, c->graft.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    return SWB200_OK;
+  }
   c->mass.alloc(n); c->light_ids.alloc(n); c->heavy_ids.alloc(n); c->graft.alloc(n);
   FastParams F{};
   F.P = c->params();

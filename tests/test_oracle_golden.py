@@ -134,3 +134,57 @@ def test_fasta_errors(built, text, msg):
         r = helpers.run_ref(f.name)
         os.unlink(f.name)
         assert r["rc"] == 1 and msg.encode() in r["stderr"]
+
+
+def _ed_le2(a, b):
+    """banded Levenshtein: True iff 1 <= ed(a, b) <= 2"""
+    la, lb = len(a), len(b)
+    if abs(la - lb) > 2:
+        return False
+    prev = {c: c + 1 for c in range(-1, min(lb, 2))}
+    for r in range(la):
+        cur = {}
+        if r - 2 <= -1:
+            cur[-1] = r + 1
+        for c in range(max(0, r - 2), min(lb, r + 3)):
+            best = 99
+            if c - 1 in prev:
+                best = prev[c - 1] + (a[r] != b[c])
+            if c in prev:
+                best = min(best, prev[c] + 1)
+            if c - 1 in cur:
+                best = min(best, cur[c - 1] + 1)
+            cur[c] = best
+        if min(cur.values()) > 2:
+            return False
+        prev = cur
+    d = prev.get(lb - 1, 99)
+    return 1 <= d <= 2
+
+
+@pytest.mark.parametrize("name", ["handmade", "short_600_20", "w32_400"])
+def test_fastidious_is_edit_distance_two(built, name):
+    """the closed form the GPU join uses: graft_cand[l] = min heavy h with 1 <= ed(h,l) <= 2 equals the
+    reference's two-level microvariant scheme (oracle restatement of src/algod1.cc:374-552)"""
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    if orc.fastidious(boundary=3) < 0:
+        pytest.skip("only light or only heavy swarms")
+    seqs = []
+    for i in range(db.n):
+        w = db.words[i * db.stride:(i + 1) * db.stride]
+        p = np.arange(int(db.len[i]))
+        seqs.append(((w[p >> 5] >> ((p & 31).astype(np.uint64) << np.uint64(1))) & np.uint64(3)).astype(np.int8).tolist())
+    mass = orc.sw_mass_before if hasattr(orc, "sw_mass_before") else None
+    o2 = Oracle(db); o2.network(); o2.cluster()
+    light = o2.sw_mass[o2.swarmid] < 3
+    want = np.full(db.n, 0xFFFFFFFF, dtype=np.uint32)
+    heavy_ids = np.nonzero(~light)[0]
+    for l in np.nonzero(light)[0]:
+        for h in heavy_ids:
+            if _ed_le2(seqs[h], seqs[l]):
+                want[l] = h
+                break
+    assert np.array_equal(want, orc.graft_raw)
