@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--amplicons", type=int, default=10_000_000)
     ap.add_argument("--length", type=int, default=150)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--enum-mode", type=int, default=1)
+    ap.add_argument("--enum-mode", type=int, default=2, help="0 full microvariant enumeration, 1 half, 2 pigeonhole join (default)")
     ap.add_argument("--bloom-bytes", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--cpu-threads", type=int, default=0)
@@ -288,7 +288,12 @@ def main():
         seeds = max(1, (n + world - 1) // world)
         P_ = 8 * ((args.length + 31) // 32)
         V, s_, c_, e_ = st["variants"] / seeds, st["slots_visited"] / seeds, st["exact_compares"] / seeds, st["links"] / seeds
-        b1_counted = P_ + 16 + 8 * V + 16 * s_ + (P_ + 8) * c_ + 8 * e_
+        if args.enum_mode == 2:
+            # JOIN: own sequence + 2 piece entries written/read (8 B slots visited) + candidate list (8 B written + read)
+            # + both packed sequences and abundances per exact comparison + links written
+            b1_counted = P_ + 16 + 8 * s_ + 16 * (st["filter_pass"] / seeds) + (2 * P_ + 16) * c_ + 8 * e_
+        else:
+            b1_counted = P_ + 16 + 8 * V + 16 * s_ + (P_ + 8) * c_ + 8 * e_
         b1_survey = 8400.0 if args.length == 150 else (P_ + 16 + 8 * (7 * args.length + 4))
         achieved = seeds * b1_counted / net_s / 1e9
         line = {
@@ -296,7 +301,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"{n} x {args.length} bp synthetic amplicons (seed {args.seed}), d=1" + (" --fastidious, BASELINE configs[2]" if args.fastidious else ", BASELINE configs[1]"),
-                       "enum_mode": "half" if args.enum_mode == 1 else "full", "filter_bytes_per_slot": args.bloom_bytes,
+                       "enum_mode": {0: "full", 1: "half", 2: "join"}[args.enum_mode], "filter_bytes_per_slot": args.bloom_bytes,
                        "l2": "inputs larger than L2 (packed db + table + filter = %.0f MB)" % ((pw.nbytes + 16 * 1.68e7 + 1.68e7) / 1e6),
                        "parallelism": f"seeds sharded over {world} GPU(s); links all-gathered (NCCL); clustering replicated"},
             "phases_ms": {"index": 1e3 * sum(phase[1]) / len(phase[1]), "network": 1e3 * net_s,
@@ -307,7 +312,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_d1_network_half" if args.enum_mode == 1 else "k_d1_network<FULL>", "bytes_per_amplicon_counted": b1_counted,
+                         "traffic": None, "kernel": {0: "k_d1_network<FULL>", 1: "k_d1_network_half", 2: "k_join_network"}[args.enum_mode], "bytes_per_amplicon_counted": b1_counted,
                          "bytes_per_amplicon_survey_formula_full_enumeration": b1_survey,
                          "achieved_if_counted_as_full_enumeration": seeds * b1_survey / net_s / 1e9,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},

@@ -34,10 +34,15 @@ enum {
 enum {
   SWB200_ENUM_FULL = 0,  /* every seed probes all <= 7L+4 microvariants, exactly the reference's
                             enumeration (src/variants.cc:184-249) */
-  SWB200_ENUM_HALF = 1   /* each unordered neighbour pair is discovered once: deletions from the longer
+  SWB200_ENUM_HALF = 1,  /* each unordered neighbour pair is discovered once: deletions from the longer
                             sequence, substitutions from the side picked by the base tournament
                             0->1 0->2 1->2 1->3 2->3 3->0; both directed links are then derived from
-                            the abundances.  ~3x fewer probes.  Default. */
+                            the abundances.  ~3x fewer probes. */
+  SWB200_ENUM_JOIN = 2   /* no microvariant enumeration: ed(u,v)=1 pairs share their first or last K
+                            nucleotides, so two K-mer entries + two lookups per amplicon and an exact
+                            packed-word comparison per candidate find the same links.  Needs the
+                            shortest sequence to be >= 16 nt (falls back to HALF otherwise).  In this
+                            mode duplicates are reported by swb200_d1_network.  Default. */
 };
 
 typedef struct swb200_ctx swb200_ctx;   /* owns the CUDA device, stream, and all device buffers */

@@ -99,4 +99,34 @@ __device__ __forceinline__ uint2 filter_pattern(uint64_t h) {
   return m;
 }
 
+// per-warp staging of output pairs in shared memory: one global atomicAdd per ~100 pairs instead of
+// one per warp step (a single hot counter serialises at ~0.5 G atomics/s: 2.5 M atomics cost 5 ms)
+constexpr int kStageCap = 160;
+struct PairStage { uint2 buf[kStageCap]; };
+
+__device__ __forceinline__ void stage_flush(PairStage &S, uint32_t &cnt, uint2 *out, unsigned long long *counter, uint64_t cap,
+                                            uint32_t lane) {
+  if (cnt == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(counter, static_cast<unsigned long long>(cnt));
+  base = shfl_u64(base, 0);
+  for (uint32_t i = lane; i < cnt; i += 32)
+    if (base + i < cap) out[base + i] = S.buf[i];
+  __syncwarp();
+  cnt = 0;
+}
+// every lane contributes `mine` (0..2) pairs; warp-uniform bookkeeping, no global atomics
+__device__ __forceinline__ void stage_push(PairStage &S, uint32_t &cnt, uint32_t mine, uint2 p0, uint2 p1, uint2 *out,
+                                           unsigned long long *counter, uint64_t cap, uint32_t lane) {
+  const uint32_t b1 = __ballot_sync(kFull, mine >= 1), b2 = __ballot_sync(kFull, mine >= 2);
+  const uint32_t total = __popc(b1) + __popc(b2);
+  if (total == 0) return;
+  if (cnt + total > kStageCap) stage_flush(S, cnt, out, counter, cap, lane);
+  const uint32_t lt = (1u << lane) - 1u;
+  if (mine >= 1) S.buf[cnt + __popc(b1 & lt)] = p0;
+  if (mine >= 2) S.buf[cnt + __popc(b1) + __popc(b2 & lt)] = p1;
+  __syncwarp();
+  cnt += total;
+}
+
 }  // namespace swb

@@ -95,50 +95,86 @@ __global__ void __launch_bounds__(256) k_fj_insert(JoinParams J) {
   if (J.fstats) atomicAdd(&J.fstats[0], 3ull);
 }
 
-// heavy pass, step 1: 7 lookups per heavy amplicon of [a_begin, a_end) -> candidate (heavy, light) pairs
+// heavy pass, step 1: 7 lookups per heavy amplicon of [a_begin, a_end) -> candidate (heavy, light) pairs.
+// Warp-synchronous bucket walk; candidates are staged per warp in shared memory (one global atomic per
+// ~100 pairs).
 __global__ void __launch_bounds__(256) k_fj_candidates(JoinParams J, uint32_t a_begin, uint32_t a_end) {
-  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const uint32_t a = a_begin + static_cast<uint32_t>(t / 7);
-  const uint32_t q = static_cast<uint32_t>(t % 7);
-  if (a >= a_end || J.is_light[a]) return;
-  const uint64_t *w = J.words + static_cast<uint64_t>(a) * J.stride;
-  const uint32_t L = J.len[a], K = J.K;
-  uint32_t piece, off;
-  if (q == 0) { piece = 0; off = 0; }
-  else if (q == 1) { piece = 2; off = L - K; }
-  else {
-    piece = 1;
-    const int o = static_cast<int>(K) + static_cast<int>(q) - 4;         // K-2 .. K+2
-    if (o < 0 || static_cast<uint32_t>(o) + K > L) return;
-    off = static_cast<uint32_t>(o);
-  }
-  const uint64_t h = piece_hash(w, J.stride, off, K, piece);
-  const uint32_t tag = static_cast<uint32_t>(h);
-  uint64_t b = __umul64hi(h, J.n_buckets);
-  unsigned long long lookups = 1, found = 0;
-  for (;;) {
-    const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(J.table + b * 4);
-    const ulonglong2 x = bp[0], y = bp[1];
-    const unsigned long long sv[4] = {x.x, x.y, y.x, y.y};
-    bool full = true;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (sv[s] == kT2Empty) { full = false; break; }
-      if (static_cast<uint32_t>(sv[s] >> 32) == tag) {
-        const uint32_t l = static_cast<uint32_t>(sv[s]);
-        const uint32_t Ll = J.len[l];
-        const uint32_t dl = Ll > L ? Ll - L : L - Ll;
-        if (dl <= 2 && J.graft_cand[l] > a) {
-          const unsigned long long at = atomicAdd(J.cand_count, 1ull);
-          if (at < J.cand_cap) J.cands[at] = make_uint2(a, l);
-          found++;
-        }
+  __shared__ PairStage stage[8];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  PairStage &S = stage[warp];
+  uint32_t scnt = 0;
+  const uint64_t total = static_cast<uint64_t>(a_end - a_begin) * 7;
+  const uint64_t nthreads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t rounds = (total + nthreads - 1) / nthreads;
+  unsigned long long lookups = 0, found = 0;
+  const uint32_t K = J.K;
+  for (uint64_t r = 0; r < rounds; ++r) {
+    const uint64_t t = r * nthreads + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t a = a_begin + static_cast<uint32_t>(t / 7);
+    const uint32_t q = static_cast<uint32_t>(t % 7);
+    bool walking = t < total && !J.is_light[a];
+    uint32_t L = 0, tag = 0;
+    uint64_t b = 0;
+    if (walking) {
+      const uint64_t *w = J.words + static_cast<uint64_t>(a) * J.stride;
+      L = J.len[a];
+      uint32_t piece = 0, off = 0;
+      if (q == 0) { piece = 0; off = 0; }
+      else if (q == 1) { piece = 2; off = L - K; }
+      else {
+        piece = 1;
+        const int o = static_cast<int>(K) + static_cast<int>(q) - 4;       // K-2 .. K+2
+        if (o < 0 || static_cast<uint32_t>(o) + K > L) walking = false;
+        off = static_cast<uint32_t>(o < 0 ? 0 : o);
+      }
+      if (walking) {
+        const uint64_t h = piece_hash(w, J.stride, off, K, piece);
+        tag = static_cast<uint32_t>(h);
+        b = __umul64hi(h, J.n_buckets);
+        lookups++;
       }
     }
-    if (!full) break;
-    if (++b == J.n_buckets) b = 0;
+    while (__any_sync(kFull, walking)) {
+      unsigned long long sv[4] = {kT2Empty, kT2Empty, kT2Empty, kT2Empty};
+      if (walking) {
+        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(J.table + b * 4);
+        const ulonglong2 x = bp[0], y = bp[1];
+        sv[0] = x.x; sv[1] = x.y; sv[2] = y.x; sv[3] = y.y;
+      }
+      bool full = walking;
+      uint32_t cv[4] = {0, 0, 0, 0};
+      uint32_t nc = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (full) {
+          if (sv[s] == kT2Empty) full = false;
+          else if (static_cast<uint32_t>(sv[s] >> 32) == tag) {
+            const uint32_t l = static_cast<uint32_t>(sv[s]);
+            const uint32_t Ll = J.len[l];
+            const uint32_t dl = Ll > L ? Ll - L : L - Ll;
+            if (dl <= 2 && J.graft_cand[l] > a) {
+              if (nc == 0) cv[0] = l; else if (nc == 1) cv[1] = l; else if (nc == 2) cv[2] = l; else cv[3] = l;
+              ++nc;
+            }
+          }
+        }
+      }
+      found += nc;
+      stage_push(S, scnt, min(nc, 2u), make_uint2(a, cv[0]), make_uint2(a, cv[1]), J.cands, J.cand_count, J.cand_cap, lane);
+      if (__any_sync(kFull, nc > 2))
+        stage_push(S, scnt, nc > 2 ? nc - 2 : 0u, make_uint2(a, cv[2]), make_uint2(a, cv[3]), J.cands, J.cand_count, J.cand_cap, lane);
+      if (walking) {
+        if (!full) walking = false;
+        else if (++b == J.n_buckets) b = 0;
+      }
+    }
   }
-  if (J.fstats) { atomicAdd(&J.fstats[1], lookups); if (found) atomicAdd(&J.fstats[2], found); }
+  stage_flush(S, scnt, J.cands, J.cand_count, J.cand_cap, lane);
+  if (J.fstats) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { lookups += __shfl_xor_sync(kFull, lookups, m); found += __shfl_xor_sync(kFull, found, m); }
+    if (lane == 0) { atomicAdd(&J.fstats[1], lookups); if (found) atomicAdd(&J.fstats[2], found); }
+  }
 }
 
 // heavy pass, step 2: exact decision ed(h, l) <= 2 with a banded (±2) unit-cost DP, one pair per thread.
@@ -194,10 +230,7 @@ __global__ void __launch_bounds__(256) k_fj_verify(JoinParams J, uint64_t m) {
   int dist = 99;
 #pragma unroll
   for (int k = 0; k < 5; ++k) if (k == kend) dist = prev[k];
-  if (dist <= 2) {
-    atomicMin(&J.graft_cand[l], a);
-    if (J.fstats) atomicAdd(&J.fstats[3], 1ull);
-  }
+  if (dist <= 2) atomicMin(&J.graft_cand[l], a);
 }
 
 }  // namespace swb

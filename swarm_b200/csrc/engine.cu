@@ -6,6 +6,7 @@
 #include "d1_network_v2.cuh"
 #include "d1_fastidious.cuh"
 #include "d1_fastidious_join.cuh"
+#include "d1_join.cuh"
 #include "dn_kernels.cuh"
 
 #include <algorithm>
@@ -76,7 +77,7 @@ struct swb200_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // options
-  int enum_mode = SWB200_ENUM_HALF;
+  int enum_mode = SWB200_ENUM_JOIN;
   int bloom_bytes_per_slot = 1;
   int collect_stats = 0;
   int shard_rank = 0, shard_world = 1;
@@ -109,6 +110,10 @@ struct swb200_ctx {
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
   DevBuf<uint2> cands;
+  DevBuf<unsigned long long> jtab;   // K-mer multimap of the JOIN network
+  uint64_t jtab_buckets = 0;
+  uint32_t jK = 0;
+  bool join_active = false;
   uint64_t fstats[4] = {0, 0, 0, 0};
   // d>1
   DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
@@ -214,7 +219,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
-  c->is_light.release(); c->cands.release();
+  c->is_light.release(); c->cands.release(); c->jtab.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -226,7 +231,7 @@ void swb200_destroy(swb200_ctx *c) {
 int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   if (!c || !key) { g_err = "null argument"; return SWB200_EINVAL; }
   const std::string k(key);
-  if (k == "enum_mode" && (v == SWB200_ENUM_FULL || v == SWB200_ENUM_HALF)) c->enum_mode = static_cast<int>(v);
+  if (k == "enum_mode" && (v == SWB200_ENUM_FULL || v == SWB200_ENUM_HALF || v == SWB200_ENUM_JOIN)) c->enum_mode = static_cast<int>(v);
   else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
   else if (k == "collect_stats") c->collect_stats = v != 0;
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
@@ -323,6 +328,28 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
 int swb200_d1_index(swb200_ctx *c) {
   API_BEGIN(c)
   if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
+  c->join_active = false;
+  c->jK = std::min<uint32_t>(64, c->min_len / 2);
+  if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8) {
+    // JOIN: the index is a multimap of two K-mer pieces per amplicon (d1_join.cuh); no Zobrist table, no filter
+    const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(c->n) * 2 * 5 / 2 + 3) / 4 * 4);
+    c->jtab.alloc(slots);
+    c->jtab_buckets = slots / 4;
+    c->tic();
+    CK(cudaMemsetAsync(c->jtab.p, 0xFF, slots * 8, c->stream));
+    CK(cudaMemsetAsync(c->counters.p, 0, 16 * 8, c->stream));
+    NetJoinParams J{};
+    J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
+    J.table = c->jtab.p; J.n_buckets = c->jtab_buckets;
+    k_join_index<<<static_cast<unsigned>((static_cast<uint64_t>(c->n) * 2 + 255) / 256), 256, 0, c->stream>>>(J);
+    CK(cudaGetLastError());
+    c->launches += 1;
+    c->toc(1);
+    c->indexed = true;
+    c->join_active = true;
+    c->have_network = c->clustered = false;
+    return SWB200_OK;
+  }
   c->n_slots = table_slots(c->n);
   c->n_filter_blocks = std::max<uint64_t>(1, c->n_slots * c->bloom_bytes_per_slot / 8);
   if (c->n_filter_blocks > (1ull << 32)) c->n_filter_blocks = 1ull << 32;
@@ -371,7 +398,7 @@ static void run_network(swb200_ctx *c) {
   const size_t smem1 = c->network_smem();
   const size_t smem2 = static_cast<size_t>(c->zlen) * kTStride + static_cast<size_t>(kWarpsPerCta) * 2 * c->batch * c->stride * 8 +
                        static_cast<size_t>(kWarpsPerCta) * sizeof(WarpScratch2) + kWarpsPerCta * 2 * 8;
-  const bool v2_ok = c->enum_mode == SWB200_ENUM_HALF && static_cast<size_t>(c->zlen) * kTStride <= 60 * 1024 && c->max_len <= 990;
+  const bool v2_ok = c->enum_mode != SWB200_ENUM_FULL && static_cast<size_t>(c->zlen) * kTStride <= 60 * 1024 && c->max_len <= 990;
   const bool use_v2 = v2_ok && c->net_kernel != 1;
   if (use_v2) { if (st) launch(k_d1_network_half<true>, smem2); else launch(k_d1_network_half<false>, smem2); }
   else if (c->enum_mode == SWB200_ENUM_FULL) { if (st) launch(k_d1_network<0, true>, smem1); else launch(k_d1_network<0, false>, smem1); }
@@ -387,7 +414,37 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
   if (c->edges.n == 0) c->edges.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 4, 1u << 16));
   c->tic();
   for (int attempt = 0; attempt < 2; ++attempt) {
-    CK(cudaMemsetAsync(c->counters.p, 0, 8 * 8, c->stream));
+    CK(cudaMemsetAsync(c->counters.p, 0, 10 * 8, c->stream));
+    if (c->join_active) {
+      NetJoinParams J{};
+      J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
+      J.table = c->jtab.p; J.n_buckets = c->jtab_buckets;
+      J.edges = c->edges.p; J.edge_count = c->counters.p; J.edge_cap = c->edges.n;
+      J.ncb = c->ncb; J.dup_flag = reinterpret_cast<uint32_t *>(c->counters.p + 8);
+      J.stats = c->collect_stats ? c->counters.p + 1 : nullptr;
+      const uint64_t per = (static_cast<uint64_t>(c->n) + c->shard_world - 1) / c->shard_world;
+      J.seed_begin = static_cast<uint32_t>(std::min<uint64_t>(per * c->shard_rank, c->n));
+      J.seed_end = static_cast<uint32_t>(std::min<uint64_t>(J.seed_begin + per, c->n));
+      const uint64_t threads = static_cast<uint64_t>(J.seed_end - J.seed_begin) * 2;
+      if (c->cands.n < static_cast<size_t>(c->n) * 6) c->cands.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 6, 1u << 20));
+      unsigned long long ncand = 0;
+      for (int tries = 0; tries < 2 && threads; ++tries) {
+        J.cands = c->cands.p; J.cand_cap = c->cands.n; J.cand_count = c->counters.p + 9;
+        CK(cudaMemsetAsync(c->counters.p + 9, 0, 8, c->stream));
+        if (tries) CK(cudaMemsetAsync(c->counters.p + 1, 0, 4 * 8, c->stream));
+        k_join_candidates<<<static_cast<unsigned>(std::min<uint64_t>((threads + 255) / 256, static_cast<uint64_t>(c->sm_count) * 8)), 256, 0, c->stream>>>(J);
+        c->launches += 1;
+        CK(cudaMemcpyAsync(&ncand, c->counters.p + 9, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (ncand <= c->cands.n) break;
+        c->cands.alloc(ncand + ncand / 8);
+      }
+      if (ncand) {
+        k_join_verify<<<static_cast<unsigned>(std::min<uint64_t>((ncand + 255) / 256, static_cast<uint64_t>(c->sm_count) * 8)), 256, 0, c->stream>>>(J, ncand);
+        c->launches += 1;
+      }
+      CK(cudaGetLastError());
+    } else
     run_network(c);
     unsigned long long host[5];
     CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
@@ -395,6 +452,11 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
     c->n_edges = host[0];
     for (int i = 0; i < 4; ++i) c->stats[i] = host[1 + i];
     c->stats[4] = c->n_edges;
+    if (c->join_active) {
+      uint32_t dup = 0;
+      CK(cudaMemcpy(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost));
+      if (dup) { c->toc(2); g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
+    }
     if (c->n_edges <= c->edges.n) break;
     c->edges.alloc(c->n_edges + c->n_edges / 8);    // link list overflowed: grow and redo (dense data)
   }
@@ -635,7 +697,7 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
         J.cands = c->cands.p; J.cand_cap = c->cands.n;
         CK(cudaMemsetAsync(c->counters.p + 11, 0, 8, c->stream));
         const uint64_t threads = static_cast<uint64_t>(a1 - a0) * 7;
-        k_fj_candidates<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, c->stream>>>(J, a0, a1);
+        k_fj_candidates<<<static_cast<unsigned>(std::min<uint64_t>((threads + 255) / 256, static_cast<uint64_t>(c->sm_count) * 8)), 256, 0, c->stream>>>(J, a0, a1);
         c->launches++;
         unsigned long long m = 0;
         CK(cudaMemcpyAsync(&m, c->counters.p + 11, 8, cudaMemcpyDeviceToHost, c->stream));

@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-ENUM_FULL, ENUM_HALF = 0, 1
+ENUM_FULL, ENUM_HALF, ENUM_JOIN = 0, 1, 2
 NONE = 0xFFFFFFFF
 _STATUS = {1: "CUDA error", 2: "invalid argument", 3: "duplicate sequences", 4: "out of memory", 5: "unsupported"}
 

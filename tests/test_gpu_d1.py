@@ -5,7 +5,7 @@ import pytest
 
 import helpers
 from helpers import GOLDEN, Oracle
-from swarm_b200 import ENUM_FULL, ENUM_HALF, D1Result, DnResult, Engine, EngineError, HostDb, scoring
+from swarm_b200 import ENUM_FULL, ENUM_HALF, ENUM_JOIN, D1Result, DnResult, Engine, EngineError, HostDb, scoring
 from swarm_b200.ffi import network_text
 
 pytestmark = pytest.mark.gpu
@@ -84,7 +84,7 @@ def run_engine(db, mode, ncb=False, **opt):
     return links, sw, gen, par, rp, col, stats
 
 
-@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF])
+@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF, ENUM_JOIN])
 @pytest.mark.parametrize("name", CASES)
 def test_golden_cases(built, name, mode):
     db = HostDb(GOLDEN / f"{name}.fasta")
@@ -101,11 +101,13 @@ def test_golden_cases(built, name, mode):
     assert res.stats_text() == (GOLDEN / f"{name}.s").read_bytes()
     assert res.structure_text() == (GOLDEN / f"{name}.i").read_bytes()
     assert network_text(db, rp, col) == (GOLDEN / f"{name}.j").read_bytes()
+    if mode == ENUM_JOIN and db.len.min() >= 16:
+        assert stats["variants"] == 2 * db.n             # two lookups per amplicon, no enumeration
     if mode == ENUM_FULL:   # the full enumeration probes exactly the reference's variant count
         assert stats["variants"] == int(orc.net_stats[0])
 
 
-@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF])
+@pytest.mark.parametrize("mode", [ENUM_FULL, ENUM_HALF, ENUM_JOIN])
 @pytest.mark.parametrize("name", ["handmade", "tie_1500_60", "c1_1k_150"])
 def test_no_cluster_breaking(built, name, mode):
     db = HostDb(GOLDEN / f"{name}.fasta")
@@ -127,10 +129,18 @@ def test_lean_half_kernel_matches_first_kernel(built, name):
 
 def test_duplicates_rejected(built):
     db = HostDb(text=b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>c_1\nACGTACGA\n")
-    eng = Engine(0)
+    eng = Engine(0, enum_mode=ENUM_HALF)
     eng.load(db)
     with pytest.raises(EngineError) as e:
         eng.d1_index()
+    assert e.value.status == 3
+    eng.close()
+    db = HostDb(text=b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>c_1\nACGTACGAGGGGGGGGGTTTTT\n")
+    eng = Engine(0, enum_mode=ENUM_JOIN)       # JOIN reports duplicates from the network phase (ed = 0 candidates)
+    eng.load(db)
+    eng.d1_index()
+    with pytest.raises(EngineError) as e:
+        eng.d1_network()
     assert e.value.status == 3
     eng.close()
 
@@ -142,7 +152,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for mode, opt in ((ENUM_FULL, {}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2})):
+    for mode, opt in ((ENUM_FULL, {}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
@@ -175,6 +185,8 @@ def test_large_set_properties(built, tmp_path):
     lh, swh, genh, parh, *_ = run_engine(db, ENUM_HALF, net_kernel=2)
     l1, *_ = run_engine(db, ENUM_HALF, net_kernel=1)
     assert np.array_equal(l1, lh)
+    lj, swj, genj, parj, *_ = run_engine(db, ENUM_JOIN)
+    assert np.array_equal(lj, lh) and np.array_equal(swj, swh)
     assert np.array_equal(lf, lh) and np.array_equal(swf, swh) and np.array_equal(genf, genh) and np.array_equal(parf, parh)
     src, dst = lf[:, 0].astype(np.int64), lf[:, 1].astype(np.int64)
     assert np.all(db.abundance[src] >= db.abundance[dst])
