@@ -20,7 +20,7 @@
 // flags along the backtrack equal the full-matrix ones.  If the banded score exceeds B the pair is
 // rejected (the true optimum then exceeds B as well).
 #pragma once
-#include "d1_kernels.cuh"
+#include "d1_join.cuh"
 
 namespace swb {
 
@@ -293,6 +293,143 @@ __global__ void __launch_bounds__(128) k_dn_align(DnParams P, uint64_t task0, ui
   if (P.stats) {
     if (done_cnt) atomicAdd(&P.stats[1], done_cnt);
     if (pruned) atomicAdd(&P.stats[2], pruned);
+  }
+}
+
+// ---- candidate generation by pigeonhole join (preferred; the all-pairs k_dn_filter is the fallback) --------
+// <= d differences leave at least one of d+1 disjoint pieces of t untouched: P_j = t[jK,(j+1)K) for j < d and
+// the suffix piece t[Lt-K, Lt), K = min(64, minlen/(d+1)).  Every amplicon stores its d+1 piece hashes; every
+// amplicon a looks up: its prefix piece, its suffix piece, and for the middle pieces j = 1..d-1 the K-mers at
+// offsets jK+δ, |δ| <= d.  A hit v > a (each unordered pair from its smaller id) that also passes the length
+// and q-gram tests (src/qgram.cc:247-252) becomes alignment task (a -> v), plus (v -> a) when the abundances
+// tie or with -n.  A pair reachable through several pieces is de-duplicated with a small hash set.
+struct DnJoinParams {
+  unsigned long long *table;
+  uint64_t n_buckets;
+  uint32_t K;
+  unsigned long long *seen;      // open-addressing set of (a<<32|v)
+  uint64_t seen_mask;
+};
+
+__global__ void __launch_bounds__(256) k_dn_index_pieces(DnParams P, DnJoinParams Q) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t np = P.d + 1;
+  const uint32_t a = static_cast<uint32_t>(t / np), piece = static_cast<uint32_t>(t % np);
+  if (a >= P.n) return;
+  const uint64_t *w = P.words + static_cast<uint64_t>(a) * P.stride;
+  const uint32_t L = P.len[a];
+  const uint32_t off = piece == P.d ? L - Q.K : piece * Q.K;
+  const uint64_t h = piece_hash(w, P.stride, off, Q.K, piece);
+  const unsigned long long val = (h << 32) | a;
+  uint64_t b = __umul64hi(h, Q.n_buckets);
+  for (;;) {
+    unsigned long long *slot = Q.table + b * 4;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      if (slot[s] == kT2Empty && atomicCAS(&slot[s], kT2Empty, val) == kT2Empty) return;
+    if (++b == Q.n_buckets) b = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_dn_candidates_join(DnParams P, DnJoinParams Q) {
+  __shared__ PairStage stage[8];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  PairStage &S = stage[warp];
+  uint32_t scnt = 0;
+  const uint32_t d = P.d, K = Q.K;
+  const uint32_t nq = 2 + (d - 1) * (2 * d + 1);
+  const uint64_t total = static_cast<uint64_t>(P.n) * nq;
+  const uint64_t nthreads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t rounds = (total + nthreads - 1) / nthreads;
+  unsigned long long cmp = 0;
+  for (uint64_t r = 0; r < rounds; ++r) {
+    const uint64_t t = r * nthreads + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t a = static_cast<uint32_t>(t / nq), q = static_cast<uint32_t>(t % nq);
+    bool walking = t < total;
+    uint32_t L = 0, tag = 0;
+    uint64_t b = 0, aab = 0;
+    if (walking) {
+      const uint64_t *w = P.words + static_cast<uint64_t>(a) * P.stride;
+      L = P.len[a];
+      aab = P.abundance[a];
+      uint32_t piece, off;
+      if (q == 0) { piece = 0; off = 0; }
+      else if (q == 1) { piece = d; off = L - K; }
+      else {
+        const uint32_t m = q - 2;
+        piece = 1 + m / (2 * d + 1);
+        const int o = static_cast<int>(piece * K) + static_cast<int>(m % (2 * d + 1)) - static_cast<int>(d);
+        if (o < 0 || static_cast<uint32_t>(o) + K > L) walking = false;
+        off = static_cast<uint32_t>(o < 0 ? 0 : o);
+      }
+      if (walking) {
+        const uint64_t h = piece_hash(w, P.stride, off, K, piece);
+        tag = static_cast<uint32_t>(h);
+        b = __umul64hi(h, Q.n_buckets);
+      }
+    }
+    while (__any_sync(kFull, walking)) {
+      unsigned long long sv[4] = {kT2Empty, kT2Empty, kT2Empty, kT2Empty};
+      if (walking) {
+        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(Q.table + b * 4);
+        const ulonglong2 x = bp[0], y = bp[1];
+        sv[0] = x.x; sv[1] = x.y; sv[2] = y.x; sv[3] = y.y;
+      }
+      bool full = walking;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t mine = 0;
+        uint2 t1 = make_uint2(0, 0), t2 = make_uint2(0, 0);
+        if (full) {
+          if (sv[s] == kT2Empty) full = false;
+          else if (static_cast<uint32_t>(sv[s] >> 32) == tag) {
+            const uint32_t v = static_cast<uint32_t>(sv[s]);
+            if (v > a) {
+              const uint32_t Lv = P.len[v];
+              const uint32_t dl = Lv > L ? Lv - L : L - Lv;
+              bool cand = dl <= P.w;
+              if (cand) {                                             // first time this pair is seen?
+                const unsigned long long key = (static_cast<unsigned long long>(a) << 32) | v;
+                uint64_t i = (key * 0x9E3779B97F4A7C15ull) >> 20 & Q.seen_mask;
+                for (int probe = 0; probe < 64; ++probe) {
+                  const unsigned long long old = atomicCAS(&Q.seen[i], kT2Empty, key);
+                  if (old == kT2Empty) break;                         // inserted: new pair
+                  if (old == key) { cand = false; break; }            // duplicate
+                  i = (i + 1) & Q.seen_mask;
+                }
+              }
+              if (cand) {                                             // q-gram lower bound
+                cmp++;
+                const uint4 *qa = reinterpret_cast<const uint4 *>(P.qgrams + static_cast<uint64_t>(a) * 32);
+                const uint4 *qv = reinterpret_cast<const uint4 *>(P.qgrams + static_cast<uint64_t>(v) * 32);
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const uint4 x = qa[k], y = qv[k];
+                  c += __popc(x.x ^ y.x) + __popc(x.y ^ y.y) + __popc(x.z ^ y.z) + __popc(x.w ^ y.w);
+                }
+                cand = c <= P.max_popc;
+              }
+              if (cand) {
+                t1 = make_uint2(a, v); mine = 1;
+                if (P.ncb || P.abundance[v] == aab) { t2 = make_uint2(v, a); mine = 2; }
+              }
+            }
+          }
+        }
+        stage_push(S, scnt, mine, t1, t2, P.tasks, P.task_count, P.task_cap, lane);
+      }
+      if (walking) {
+        if (!full) walking = false;
+        else if (++b == Q.n_buckets) b = 0;
+      }
+    }
+  }
+  stage_flush(S, scnt, P.tasks, P.task_count, P.task_cap, lane);
+  if (P.stats) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) cmp += __shfl_xor_sync(kFull, cmp, m);
+    if (lane == 0 && cmp) atomicAdd(&P.stats[0], cmp);
   }
 }
 

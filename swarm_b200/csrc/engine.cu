@@ -107,6 +107,7 @@ struct swb200_ctx {
   DevBuf<uint32_t> light_ids, heavy_ids, graft;
   uint32_t max_len = 0, min_len = 0;
   uint32_t minmax[2] = {0, 0};
+  int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
   DevBuf<uint2> cands;
@@ -236,6 +237,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "collect_stats") c->collect_stats = v != 0;
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
+  else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -606,10 +608,32 @@ int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const 
   c->launches++;
   if (c->tasks.n == 0) c->tasks.alloc(std::max<size_t>(static_cast<size_t>(n) * 16, 1u << 20));
   unsigned long long ntasks = 0;
+  const uint32_t Kp = std::min<uint32_t>(64, c->min_len / (d + 1));
+  const bool use_join = Kp >= 8 && c->dn_filter != 1;
+  DnJoinParams Q{};
+  if (use_join) {
+    const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(n) * (d + 1) * 5 / 2 + 3) / 4 * 4);
+    c->jtab.alloc(slots);
+    c->join_active = false;                       // the d=1 join table is overwritten
+    c->indexed = false;
+    Q.table = c->jtab.p; Q.n_buckets = slots / 4; Q.K = Kp;
+    uint64_t seen = 1;
+    while (seen < static_cast<uint64_t>(n) * 16) seen <<= 1;
+    c->t2.alloc(seen);
+    Q.seen = c->t2.p; Q.seen_mask = seen - 1;
+    CK(cudaMemsetAsync(c->jtab.p, 0xFF, slots * 8, c->stream));
+    k_dn_index_pieces<<<static_cast<unsigned>((static_cast<uint64_t>(n) * (d + 1) + 255) / 256), 256, 0, c->stream>>>(P, Q);
+    c->launches++;
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     P.tasks = c->tasks.p; P.task_cap = c->tasks.n;
     CK(cudaMemsetAsync(c->counters.p, 0, 8, c->stream));
-    k_dn_filter<<<(n + 255) / 256, 256, 0, c->stream>>>(P, 0, (n + kDnTileQ - 1) / kDnTileQ);
+    if (use_join) {
+      CK(cudaMemsetAsync(c->t2.p, 0xFF, (Q.seen_mask + 1) * 8, c->stream));
+      k_dn_candidates_join<<<c->sm_count * 8, 256, 0, c->stream>>>(P, Q);
+    } else {
+      k_dn_filter<<<(n + 255) / 256, 256, 0, c->stream>>>(P, 0, (n + kDnTileQ - 1) / kDnTileQ);
+    }
     c->launches++;
     CK(cudaMemcpyAsync(&ntasks, c->counters.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -267,13 +267,14 @@ DN_CASES = [("handmade", 2, False, None, "d2"), ("c1_1k_150", 2, False, None, "d
             ("l400_250", 2, False, None, "d2")]
 
 
+@pytest.mark.parametrize("dn_filter", [0, 1])
 @pytest.mark.parametrize("name,d,ncb,pen,tag", DN_CASES)
-def test_dn_golden(built, name, d, ncb, pen, tag):
+def test_dn_golden(built, name, d, ncb, pen, tag, dn_filter):
     db = HostDb(GOLDEN / f"{name}.fasta", check_dup_sequences=True)
     p = scoring(*pen) if pen else scoring()
     orc = Oracle(db)
     osw, ogen, opar, opd = orc.dn_cluster(d, no_cluster_breaking=ncb, pen=p)
-    eng = Engine(0)
+    eng = Engine(0, dn_filter=dn_filter)
     eng.load(db)
     sw, gen, par, pd = eng.dn_cluster(d, no_cluster_breaking=ncb, penalties=p)
     eng.close()
@@ -284,13 +285,14 @@ def test_dn_golden(built, name, d, ncb, pen, tag):
     assert res.structure_text() == (GOLDEN / f"{name}.{tag}.i").read_bytes()
 
 
+@pytest.mark.parametrize("dn_filter", [0, 1])
 @pytest.mark.parametrize("n,L,seed,mode_ab,d", [(4000, 100, 31, 0, 2), (3000, 60, 32, 1, 3), (2500, 400, 33, 0, 2), (2000, 150, 34, 1, 5)])
-def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab, d):
+def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab, d, dn_filter):
     fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
     db = HostDb(fa, check_dup_sequences=True)
     orc = Oracle(db)
     osw, ogen, opar, opd = orc.dn_cluster(d)
-    eng = Engine(0)
+    eng = Engine(0, dn_filter=dn_filter)
     eng.load(db)
     sw, gen, par, pd = eng.dn_cluster(d)
     st = eng.stats()
