@@ -185,6 +185,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        if not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION/INFO prints to stdout; the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n_total = args.amplicons
@@ -303,7 +305,8 @@ def main():
             "config": {"workload": f"{n} x {args.length} bp synthetic amplicons (seed {args.seed}), d=1" + (" --fastidious, BASELINE configs[2]" if args.fastidious else ", BASELINE configs[1]"),
                        "enum_mode": {0: "full", 1: "half", 2: "join"}[args.enum_mode], "filter_bytes_per_slot": args.bloom_bytes,
                        "l2": "inputs larger than L2 (packed db + table + filter = %.0f MB)" % ((pw.nbytes + 16 * 1.68e7 + 1.68e7) / 1e6),
-                       "parallelism": f"seeds sharded over {world} GPU(s); links all-gathered (NCCL); clustering replicated"},
+                       "parallelism": (f"K-mer table sharded by hash range over {world} GPUs; links all-gathered (NCCL all-gather over NVLink); clustering replicated"
+                                       if world > 1 else "single GPU")},
             "phases_ms": {"index": 1e3 * sum(phase[1]) / len(phase[1]), "network": 1e3 * net_s,
                           "cluster": 1e3 * sum(phase[3]) / len(phase[3]),
                           "fastidious": (1e3 * sum(phase[4]) / len(phase[4])) if args.fastidious else None},

@@ -56,8 +56,11 @@ const char *swb200_last_error(void);
  * (1,2,4,8: filter size = table slots * this; reference uses 1, src/algod1.cc:1127),
  * "collect_stats" (0/1), "net_kernel" (0 auto, 1 first-generation kernel, 2 lean HALF kernel),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "shard_rank"/"shard_world" (seeds [rank*n/world, (rank+1)*n/world) are
- * this context's share of the network build). */
+ * "cluster_kernel" (0 fused label+generation relaxation, 1 label propagation then BFS), "dn_filter" (0 auto,
+ * 1 all-pairs q-gram filter),
+ * "shard_rank"/"shard_world" (this context's share of the network build, SURVEY.md §8e: in JOIN mode the
+ * K-mer table is sharded by hash range — every rank scans all lookups but builds and walks only its own
+ * bucket range; in the enumeration modes the seeds [rank*n/world, (rank+1)*n/world) are sharded). */
 int  swb200_set_option(swb200_ctx *ctx, const char *key, int64_t value);
 
 /* Replaces db_getsequence/len/abundance/count (src/db.h:35-53, src/db.cc:806-906) as the engine's

@@ -19,8 +19,9 @@ struct NetJoinParams {
   const uint32_t *len;
   const uint64_t *abundance;
   uint32_t n, stride, K;
-  unsigned long long *table;       // tag32 | id32, 4-slot buckets
-  uint64_t n_buckets;
+  unsigned long long *table;       // tag32 | id32, 4-slot buckets; this rank holds buckets [b_lo, b_hi) at table[(b-b_lo)*4]
+  uint64_t n_buckets;              // global bucket count (the hash -> bucket map is the same on every rank)
+  uint64_t b_lo, b_hi;             // multi-GPU: the K-mer table is sharded by bucket range (hash range)
   uint2 *edges;
   unsigned long long *edge_count;
   uint64_t edge_cap;
@@ -42,12 +43,13 @@ __global__ void __launch_bounds__(256) k_join_index(NetJoinParams J) {
   const uint64_t h = piece_hash(w, J.stride, piece ? L - J.K : 0u, J.K, piece);
   const unsigned long long val = (h << 32) | a;
   uint64_t b = __umul64hi(h, J.n_buckets);
+  if (b < J.b_lo || b >= J.b_hi) return;            // another rank owns this hash range
   for (;;) {
-    unsigned long long *slot = J.table + b * 4;
+    unsigned long long *slot = J.table + (b - J.b_lo) * 4;
 #pragma unroll
     for (int s = 0; s < 4; ++s)
       if (slot[s] == kT2Empty && atomicCAS(&slot[s], kT2Empty, val) == kT2Empty) return;
-    if (++b == J.n_buckets) b = 0;
+    if (++b == J.b_hi) b = J.b_lo;                  // linear probing wraps inside the shard
   }
 }
 
@@ -116,12 +118,12 @@ __global__ void __launch_bounds__(256) k_join_candidates(NetJoinParams J) {
     const uint64_t h = in ? piece_hash(w, J.stride, piece ? L - K : 0u, K, piece) : 0ull;
     const uint32_t tag = static_cast<uint32_t>(h);
     uint64_t b = __umul64hi(h, J.n_buckets);
-    bool walking = in;
-    if (in) st_l++;
+    bool walking = in && b >= J.b_lo && b < J.b_hi;   // only the owner of the hash range walks it
+    if (walking) st_l++;
     while (__any_sync(kFull, walking)) {
       unsigned long long sv[4] = {kT2Empty, kT2Empty, kT2Empty, kT2Empty};
       if (walking) {
-        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(J.table + b * 4);
+        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(J.table + (b - J.b_lo) * 4);
         const ulonglong2 x = bp[0], y = bp[1];
         sv[0] = x.x; sv[1] = x.y; sv[2] = y.x; sv[3] = y.y;
       }
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) k_join_candidates(NetJoinParams J) {
       }
       if (walking) {
         if (!full) walking = false;
-        else if (++b == J.n_buckets) b = 0;
+        else if (++b == J.b_hi) b = J.b_lo;
       }
     }
   }

@@ -551,6 +551,37 @@ __global__ void k_bfs_relax(const uint2 *edges, uint64_t m, const uint32_t *labe
   }
   if (__any_sync(kFull, ch) && (threadIdx.x & 31) == 0) *changed = 1;
 }
+// ---- fused formulation (default): ONE relaxation on key = label<<32 | generation.
+// key[v] = min over links u->v of key[u]+1 (lexicographic: the smallest reaching id wins; among
+// predecessors carrying that id, the smallest depth), iterated to the fixed point with 64-bit atomicMin;
+// then parent[v] = min { u : u->v, key[u]+1 == key[v] }.  Same result as k_label_* + k_bfs_* in half the
+// passes over the link list.
+__global__ void k_key_init(unsigned long long *key, uint32_t *parent, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { key[i] = static_cast<unsigned long long>(i) << 32; parent[i] = kNone; }
+}
+__global__ void k_key_relax(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *changed) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  bool ch = false;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < m; e += stride) {
+    const uint2 ed = edges[e];
+    const unsigned long long cand = key[ed.x] + 1ull;
+    if (cand < key[ed.y]) { atomicMin(&key[ed.y], cand); ch = true; }
+  }
+  if (__any_sync(kFull, ch) && (threadIdx.x & 31) == 0) *changed = 1;
+}
+__global__ void k_key_parent(const uint2 *edges, uint64_t m, const unsigned long long *key, uint32_t *parent) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < m; e += stride) {
+    const uint2 ed = edges[e];
+    if (key[ed.x] + 1ull == key[ed.y]) atomicMin(&parent[ed.y], ed.x);
+  }
+}
+__global__ void k_key_unpack(const unsigned long long *key, uint32_t *label, uint32_t *generation, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { label[i] = static_cast<uint32_t>(key[i] >> 32); generation[i] = static_cast<uint32_t>(key[i]); }
+}
+
 __global__ void k_bfs_unpack(const unsigned long long *key, uint32_t *generation, uint32_t *parent, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

@@ -107,12 +107,13 @@ struct swb200_ctx {
   DevBuf<uint32_t> light_ids, heavy_ids, graft;
   uint32_t max_len = 0, min_len = 0;
   uint32_t minmax[2] = {0, 0};
+  int cluster_kernel = 0; // 0/2 fused key relaxation, 1 = label propagation + BFS (first generation)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
   DevBuf<uint2> cands;
   DevBuf<unsigned long long> jtab;   // K-mer multimap of the JOIN network
-  uint64_t jtab_buckets = 0;
+  uint64_t jtab_buckets = 0, jb_lo = 0, jb_hi = 0;
   uint32_t jK = 0;
   bool join_active = false;
   uint64_t fstats[4] = {0, 0, 0, 0};
@@ -238,6 +239,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
+  else if (k == "cluster_kernel" && v >= 0 && v <= 2) c->cluster_kernel = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -335,14 +337,19 @@ int swb200_d1_index(swb200_ctx *c) {
   if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8) {
     // JOIN: the index is a multimap of two K-mer pieces per amplicon (d1_join.cuh); no Zobrist table, no filter
     const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(c->n) * 2 * 5 / 2 + 3) / 4 * 4);
-    c->jtab.alloc(slots);
     c->jtab_buckets = slots / 4;
+    // multi-GPU: this rank owns the bucket (hash) range [b_lo, b_hi) of the table
+    const uint64_t per = (c->jtab_buckets + c->shard_world - 1) / c->shard_world;
+    c->jb_lo = std::min<uint64_t>(per * c->shard_rank, c->jtab_buckets);
+    c->jb_hi = std::min<uint64_t>(c->jb_lo + per, c->jtab_buckets);
+    const uint64_t my_slots = std::max<uint64_t>(4, (c->jb_hi - c->jb_lo) * 4);
+    c->jtab.alloc(my_slots);
     c->tic();
-    CK(cudaMemsetAsync(c->jtab.p, 0xFF, slots * 8, c->stream));
+    CK(cudaMemsetAsync(c->jtab.p, 0xFF, my_slots * 8, c->stream));
     CK(cudaMemsetAsync(c->counters.p, 0, 16 * 8, c->stream));
     NetJoinParams J{};
     J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
-    J.table = c->jtab.p; J.n_buckets = c->jtab_buckets;
+    J.table = c->jtab.p; J.n_buckets = c->jtab_buckets; J.b_lo = c->jb_lo; J.b_hi = c->jb_hi;
     k_join_index<<<static_cast<unsigned>((static_cast<uint64_t>(c->n) * 2 + 255) / 256), 256, 0, c->stream>>>(J);
     CK(cudaGetLastError());
     c->launches += 1;
@@ -420,13 +427,12 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
     if (c->join_active) {
       NetJoinParams J{};
       J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
-      J.table = c->jtab.p; J.n_buckets = c->jtab_buckets;
+      J.table = c->jtab.p; J.n_buckets = c->jtab_buckets; J.b_lo = c->jb_lo; J.b_hi = c->jb_hi;
       J.edges = c->edges.p; J.edge_count = c->counters.p; J.edge_cap = c->edges.n;
       J.ncb = c->ncb; J.dup_flag = reinterpret_cast<uint32_t *>(c->counters.p + 8);
       J.stats = c->collect_stats ? c->counters.p + 1 : nullptr;
-      const uint64_t per = (static_cast<uint64_t>(c->n) + c->shard_world - 1) / c->shard_world;
-      J.seed_begin = static_cast<uint32_t>(std::min<uint64_t>(per * c->shard_rank, c->n));
-      J.seed_end = static_cast<uint32_t>(std::min<uint64_t>(J.seed_begin + per, c->n));
+      J.seed_begin = 0;                 // every rank scans all lookups and walks only its own hash range
+      J.seed_end = c->n;
       const uint64_t threads = static_cast<uint64_t>(J.seed_end - J.seed_begin) * 2;
       if (c->cands.n < static_cast<size_t>(c->n) * 6) c->cands.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 6, 1u << 20));
       unsigned long long ncand = 0;
@@ -539,6 +545,24 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
+  if (c->cluster_kernel != 1) {
+    // fused label+generation relaxation (d1_kernels.cuh: k_key_*)
+    k_key_init<<<vb, 256, 0, c->stream>>>(c->key.p, c->parent.p, n);
+    c->launches++;
+    for (int round = 0; m > 0 && round < 1 << 20; ++round) {
+      CK(cudaMemsetAsync(changed, 0, 4, c->stream));
+      k_key_relax<<<std::max(eb, 1), 256, 0, c->stream>>>(c->edges.p, m, c->key.p, changed);
+      c->launches++;
+      CK(cudaMemcpyAsync(h_changed, changed, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (*h_changed == 0) break;
+    }
+    if (m > 0) { k_key_parent<<<std::max(eb, 1), 256, 0, c->stream>>>(c->edges.p, m, c->key.p, c->parent.p); c->launches++; }
+    k_key_unpack<<<vb, 256, 0, c->stream>>>(c->key.p, c->label.p, c->generation.p, n);
+    c->launches++;
+    CK(cudaGetLastError());
+    return;
+  }
   k_label_init<<<vb, 256, 0, c->stream>>>(c->label.p, n);
   c->launches++;
   for (int round = 0; m > 0 && round < 1 << 20; ++round) {

@@ -152,7 +152,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for mode, opt in ((ENUM_FULL, {}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
+    for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
@@ -167,13 +167,14 @@ def test_filter_sizes_and_sharding_give_identical_links(built, tmp_path):
     for bps in (2, 4):
         links, *_ = run_engine(db, ENUM_HALF, bloom_bytes_per_slot=bps)
         assert np.array_equal(links, base)
-    parts = []
-    for r in range(3):
-        links, *_ = run_engine(db, ENUM_HALF, shard_rank=r, shard_world=3)
-        parts.append(links)
-    allp = np.concatenate(parts)
-    allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]
-    assert np.array_equal(allp, base)
+    for mode in (ENUM_HALF, ENUM_JOIN):      # seed shards (enumeration) / hash-range shards of the K-mer table (join)
+        parts = []
+        for r in range(3):
+            links, *_ = run_engine(db, mode, shard_rank=r, shard_world=3)
+            parts.append(links)
+        allp = np.concatenate(parts)
+        allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]
+        assert np.array_equal(allp, base)
 
 
 def test_large_set_properties(built, tmp_path):
@@ -181,7 +182,7 @@ def test_large_set_properties(built, tmp_path):
     a fixed point (every link stays inside one swarm or points from a smaller label), seeds are minima."""
     fa = helpers.make_fasta(tmp_path / "big.fa", 1000000, 150, 11, 0)
     db = HostDb(fa)
-    lf, swf, genf, parf, *_ = run_engine(db, ENUM_FULL)
+    lf, swf, genf, parf, *_ = run_engine(db, ENUM_FULL, cluster_kernel=1)
     lh, swh, genh, parh, *_ = run_engine(db, ENUM_HALF, net_kernel=2)
     l1, *_ = run_engine(db, ENUM_HALF, net_kernel=1)
     assert np.array_equal(l1, lh)
@@ -303,3 +304,58 @@ def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab,
         r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
         res = DnResult(db, sw, gen, par, pd)
         assert res.swarms_text() == r["o"] and res.stats_text() == r["s"] and res.structure_text() == r["i"]
+
+
+def _engine_vs_oracle(db, **opt):
+    orc = Oracle(db)
+    assert orc.network() is not None
+    orc.cluster()
+    links, sw, gen, par, *_ = run_engine(db, opt.pop("mode", ENUM_JOIN), **opt)
+    assert np.array_equal(links, orc.links())
+    assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
+
+
+def test_edge_cases(built):
+    # a single amplicon; two unrelated singletons; a pure chain of equal abundances; one-nucleotide sequences
+    for text in (b">a_1\nACGTACGTACGTACGTACGTAGCTAGCTAGGATC\n",
+                 b">a_2\nACGTACGTACGTACGTACGTAGCTAGCTAGGATC\n>b_1\nTTTTTTTTTTTTTTTTTTTTTTGGGGGGGGGGGGG\n",
+                 b">a_1\nAAAAAAAAAAAAAAAAAAAA\n>b_1\nAAAAAAAAAAAAAAAAAAAC\n>c_1\nAAAAAAAAAAAAAAAAAACC\n>d_1\nAAAAAAAAAAAAAAAAACCC\n>e_1\nAAAAAAAAAAAAAAAACCCC\n",
+                 b">a_5\nA\n>b_4\nC\n>c_3\nAC\n>d_2\nACG\n>e_1\nG\n"):
+        db = HostDb(text=text)
+        for mode in (ENUM_FULL, ENUM_HALF, ENUM_JOIN):
+            _engine_vs_oracle(db, mode=mode)
+
+
+def test_long_sequences_use_the_general_kernels(built, tmp_path):
+    # > 990 nt: the lean HALF kernel and its fused table do not apply; JOIN pieces are capped at 64 nt
+    fa = helpers.make_fasta(tmp_path / "long.fa", 1500, 1100, 3, 0)
+    db = HostDb(fa)
+    assert db.longest > 1000
+    for mode in (ENUM_HALF, ENUM_JOIN, ENUM_FULL):
+        _engine_vs_oracle(db, mode=mode)
+    orc = Oracle(db); orc.network(); orc.cluster()
+    if orc.fastidious(boundary=3) >= 0:
+        for fk in (1, 2):
+            eng = Engine(0, fast_kernel=fk)
+            eng.load(db); eng.d1_index(); eng.d1_network(); eng.d1_cluster()
+            gc, *_ = eng.d1_fastidious(boundary=3)
+            eng.close()
+            assert np.array_equal(gc, orc.graft_raw)
+
+
+def test_mixed_lengths(built, tmp_path):
+    # lengths from 30 to 300 in one database: piece length K is set by the shortest sequence
+    parts = []
+    for i, L in enumerate((30, 75, 150, 300)):
+        p = helpers.make_fasta(tmp_path / f"p{i}.fa", 800, L, 50 + i, i % 2)
+        parts.append(open(p, "rb").read().replace(b">s", b">l%d_" % L))
+    db = HostDb(text=b"".join(parts))
+    for mode in (ENUM_HALF, ENUM_JOIN):
+        _engine_vs_oracle(db, mode=mode)
+    orc = Oracle(db); orc.network(); orc.cluster(); g = orc.fastidious(boundary=3)
+    eng = Engine(0)
+    eng.load(db); eng.d1_index(); eng.d1_network(); eng.d1_cluster()
+    gc, *_ = eng.d1_fastidious(boundary=3)
+    eng.close()
+    if g >= 0:
+        assert np.array_equal(gc, orc.graft_raw)
