@@ -9,10 +9,11 @@ NVCCFLAGS  = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -X
              -Xptxas -v --expt-relaxed-constexpr
 ENGINE_SRC = swarm_b200/csrc/engine.cu
 ENGINE_DEP = $(wildcard swarm_b200/csrc/*.cuh) include/swarm_b200.h
-HOST_SRC   = $(wildcard swarm_b200/host/*.cc)
+HOST_SRC   = $(filter-out swarm_b200/host/main.cc, $(wildcard swarm_b200/host/*.cc))
 HOST_DEP   = $(wildcard swarm_b200/host/*.h) include/swarm_b200_host.h
 
-all: engine host tools oracle
+all: engine host tools oracle cli
+cli: bin/swarm_b200
 engine: swarm_b200/libswarm_b200.so
 host: swarm_b200/libswarm_b200_host.so
 tools: tools/libgen_amplicons.so
@@ -24,6 +25,11 @@ swarm_b200/libswarm_b200.so: $(ENGINE_SRC) $(ENGINE_DEP)
 swarm_b200/libswarm_b200_host.so: $(HOST_SRC) $(HOST_DEP)
 	$(CXX) -O2 -g -std=c++17 -fPIC -shared -Wall -Wextra -Iinclude -o $@ $(HOST_SRC)
 
+# the drop-in command line: host layer compiled in, CUDA engine linked dynamically
+bin/swarm_b200: swarm_b200/host/main.cc $(HOST_SRC) $(HOST_DEP) swarm_b200/libswarm_b200.so
+	@mkdir -p bin
+	$(CXX) -O2 -g -std=c++17 -Wall -Wextra -Iinclude -o $@ swarm_b200/host/main.cc $(HOST_SRC) -Lswarm_b200 -lswarm_b200 -Wl,-rpath,'$$ORIGIN/../swarm_b200'
+
 tools/libgen_amplicons.so: tools/gen_amplicons.c
 	gcc -O2 -std=c11 -fPIC -shared -Wall -o $@ $< -lm
 
@@ -31,6 +37,6 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -f swarm_b200/*.so tools/*.so swarm_b200/csrc/ptxas.log
+	rm -rf swarm_b200/*.so tools/*.so swarm_b200/csrc/ptxas.log bin
 	$(MAKE) -C oracle clean
-.PHONY: all engine host tools oracle clean
+.PHONY: all engine host tools oracle cli clean

@@ -1,0 +1,302 @@
+// swarm_b200/host/main.cc — `swarm_b200`: drop-in command line for swarm's d >= 1 clustering on a B200.
+//
+// Host mirror of /root/reference src/swarm.cc (options :93-124, checks :486-630, dispatch :633-675) and
+// src/utils/open_and_close_files.cc:35-93, written from scratch: same options, same validation messages,
+// same output bytes (`-o -r -s -i -w -j`), same exit code (1 after "\nError: ..." on stderr,
+// src/utils/fatal.h:27,38-46).  The clustering itself is the CUDA engine behind include/swarm_b200.h.
+// Not provided: d = 0 dereplication (src/derep.cc) and the uclust writer `-u` (needs the scalar NW +
+// CIGAR of src/nw.cc): both end with an error message.  `-t`, `-x`, `-c`, `-y` are accepted and validated
+// but have nothing to configure (no CPU thread pool, no SSE dispatch, no Bloom filter to size).
+#include "../../include/swarm_b200.h"
+#include "../../include/swarm_b200_host.h"
+
+#include <getopt.h>
+#include <unistd.h>
+
+#include <array>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+[[noreturn]] void fatal(const std::string &msg) {
+  std::fprintf(stderr, "\nError: %s\n", msg.c_str());
+  std::exit(EXIT_FAILURE);
+}
+
+struct Params {
+  int64_t append_abundance = 0, boundary = 3, ceiling = 0, differences = 1, gap_ext = 4, gap_open = 12, match = 5,
+          mismatch = 4, threads = 1, bloom_bits = 16;
+  bool fastidious = false, help = false, ncb = false, mothur = false, version = false, disable_sse3 = false, usearch = false;
+  std::string internal_structure, network_file, log, output_file = "-", statistics_file, uclust_file, seeds, input = "-";
+  int64_t pen[3] = {18, 24, 13};
+};
+
+const option kLong[] = {
+    {"append-abundance", required_argument, nullptr, 'a'}, {"boundary", required_argument, nullptr, 'b'},
+    {"ceiling", required_argument, nullptr, 'c'}, {"differences", required_argument, nullptr, 'd'},
+    {"gap-extension-penalty", required_argument, nullptr, 'e'}, {"fastidious", no_argument, nullptr, 'f'},
+    {"gap-opening-penalty", required_argument, nullptr, 'g'}, {"help", no_argument, nullptr, 'h'},
+    {"internal-structure", required_argument, nullptr, 'i'}, {"log", required_argument, nullptr, 'l'},
+    {"network-file", required_argument, nullptr, 'j'}, {"match-reward", required_argument, nullptr, 'm'},
+    {"no-otu-breaking", no_argument, nullptr, 'n'}, {"output-file", required_argument, nullptr, 'o'},
+    {"mismatch-penalty", required_argument, nullptr, 'p'}, {"mothur", no_argument, nullptr, 'r'},
+    {"statistics-file", required_argument, nullptr, 's'}, {"threads", required_argument, nullptr, 't'},
+    {"uclust-file", required_argument, nullptr, 'u'}, {"version", no_argument, nullptr, 'v'},
+    {"seeds", required_argument, nullptr, 'w'}, {"disable-sse3", no_argument, nullptr, 'x'},
+    {"bloom-bits", required_argument, nullptr, 'y'}, {"usearch-abundance", no_argument, nullptr, 'z'},
+    {nullptr, 0, nullptr, 0}};
+
+const char *kHeader =
+    "swarm_b200 1.0 — B200 (sm_100a) engine, command-line compatible with Swarm 3.1.6\n"
+    "clustering method: Mahe F, Rognes T, Quince C, de Vargas C, Dunthorn M (2014, 2015, 2022), Swarm v1-v3\n\n";
+
+const char *kUsage =
+    "Usage: swarm_b200 [OPTIONS] [FASTAFILE]\n\n"
+    "General options:\n"
+    " -h, --help                          display this help and exit\n"
+    " -t, --threads INTEGER               accepted for compatibility (the GPU engine has no thread pool)\n"
+    " -v, --version                       display version information and exit\n\n"
+    "Clustering options:\n"
+    " -d, --differences INTEGER           resolution (1)\n"
+    " -n, --no-otu-breaking               never break clusters (not recommended!)\n\n"
+    "Fastidious options (only when d = 1):\n"
+    " -b, --boundary INTEGER              min mass of large clusters (3)\n"
+    " -c, --ceiling INTEGER               accepted for compatibility (no Bloom filter to size)\n"
+    " -f, --fastidious                    link nearby low-abundance swarms\n"
+    " -y, --bloom-bits INTEGER            accepted for compatibility\n\n"
+    "Input/output options:\n"
+    " -a, --append-abundance INTEGER      value to use when abundance is missing\n"
+    " -i, --internal-structure FILENAME   write internal cluster structure to file\n"
+    " -j, --network-file FILENAME         dump sequence network to file\n"
+    " -l, --log FILENAME                  log to file, not to stderr\n"
+    " -o, --output-file FILENAME          output result to file (stdout)\n"
+    " -r, --mothur                        output using mothur-like format\n"
+    " -s, --statistics-file FILENAME      dump cluster statistics to file\n"
+    " -w, --seeds FILENAME                write cluster representatives to FASTA file\n"
+    " -z, --usearch-abundance             abundance annotation in usearch style\n\n"
+    "Pairwise alignment advanced options (only when d > 1):\n"
+    " -m, --match-reward INTEGER          reward for nucleotide match (5)\n"
+    " -p, --mismatch-penalty INTEGER      penalty for nucleotide mismatch (4)\n"
+    " -g, --gap-opening-penalty INTEGER   gap open penalty (12)\n"
+    " -e, --gap-extension-penalty INTEGER gap extension penalty (4)\n\n";
+
+int64_t args_long(const char *str, const char *option) {   // src/swarm.cc:193-208
+  char *end = nullptr;
+  const int64_t v = std::strtol(str, &end, 10);
+  if (*end != '\0')
+    fatal(std::string("Invalid numeric argument for option ") + option +
+          ".\n\nFrequent causes are:\n - a missing space between an argument and the next option,\n"
+          " - a long option name not starting with a double dash\n   (swarm accepts '--help' or '-h', but not '-help')\n\n"
+          "Please see 'swarm --help' for more details.");
+  return v;
+}
+
+std::FILE *open_out(const std::string &name) {             // src/utils/input_output.cc:44-60: "-" = stdout via dup
+  if (name == "-") { const int fd = dup(STDOUT_FILENO); return fd < 0 ? nullptr : fdopen(fd, "w"); }
+  return std::fopen(name.c_str(), "w");
+}
+
+void write_all(std::FILE *f, char *text, uint64_t len) {
+  if (f && text) std::fwrite(text, 1, len, f);
+  swbh_free(text);
+}
+
+void engine_check(int status) {
+  if (status == SWB200_OK) return;
+  if (status == SWB200_EDUPLICATE)                          // same text as src/algod1.cc:1141-1150
+    fatal("some fasta entries have identical sequences.\nSwarm expects dereplicated fasta files.\n"
+          "Such files can be produced with swarm or vsearch:\n swarm -d 0 -w derep.fasta -o /dev/null input.fasta\nor\n"
+          " vsearch --derep_fulllength input.fasta --sizein --sizeout --output derep.fasta\n");
+  fatal(std::string("GPU engine: ") + swb200_last_error());
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Params P;
+  std::array<bool, 26> used{};
+  opterr = 1;
+  for (;;) {
+    int idx = 0;
+    const int c = getopt_long(argc, argv, "a:b:c:d:e:fg:hi:j:l:m:no:p:rs:t:u:vw:xy:z", kLong, &idx);
+    if (c == -1) break;
+    if (c >= 'a' && c <= 'z') {
+      if (used[static_cast<size_t>(c - 'a')]) {
+        const char *lname = "";
+        for (const option *o = kLong; o->name; ++o) if (o->val == c) { lname = o->name; break; }
+        fatal(std::string("Option -") + static_cast<char>(c) + " or --" + lname + " specified more than once.");
+      }
+      used[static_cast<size_t>(c - 'a')] = true;
+    }
+    switch (c) {
+      case 'a': P.append_abundance = args_long(optarg, "-a or --append-abundance"); break;
+      case 'b': P.boundary = args_long(optarg, "-b or --boundary"); break;
+      case 'c': P.ceiling = args_long(optarg, "-c or --ceiling"); break;
+      case 'd': P.differences = args_long(optarg, "-d or --differences"); break;
+      case 'e': P.gap_ext = args_long(optarg, "-e or --gap-extension-penalty"); break;
+      case 'f': P.fastidious = true; break;
+      case 'g': P.gap_open = args_long(optarg, "-g or --gap-opening-penalty"); break;
+      case 'h': P.help = true; break;
+      case 'i': P.internal_structure = optarg; break;
+      case 'j': P.network_file = optarg; break;
+      case 'l': P.log = optarg; break;
+      case 'm': P.match = args_long(optarg, "-m or --match-reward"); break;
+      case 'n': P.ncb = true; break;
+      case 'o': P.output_file = optarg; break;
+      case 'p': P.mismatch = args_long(optarg, "-p or --mismatch-penalty"); break;
+      case 'r': P.mothur = true; break;
+      case 's': P.statistics_file = optarg; break;
+      case 't': P.threads = args_long(optarg, "-t or --threads"); break;
+      case 'u': P.uclust_file = optarg; break;
+      case 'v': P.version = true; break;
+      case 'w': P.seeds = optarg; break;
+      case 'x': P.disable_sse3 = true; break;
+      case 'y': P.bloom_bits = args_long(optarg, "-y or --bloom-bits"); break;
+      case 'z': P.usearch = true; break;
+      default:
+        std::fputs(kHeader, stderr);
+        std::fputs(kUsage, stderr);
+        std::exit(EXIT_FAILURE);
+    }
+  }
+  if (optind < argc) P.input = argv[optind];
+  swbh_scoring(P.match, P.mismatch, P.gap_open, P.gap_ext, P.pen);
+
+  // args_check, src/swarm.cc:486-630 (same order, same messages)
+  if (P.threads < 1 || P.threads > 512) fatal("Illegal number of threads specified with -t or --threads, must be in the range 1 to 512.");
+  // the reference streams `uint8_max` (an unsigned char) into its message, so the upper bound is printed as
+  // the single byte 0xFF (src/swarm.cc:513-516 via src/utils/fatal.h); reproduced for byte-identical stderr
+  if (P.differences < 0 || P.differences > 255) fatal("Illegal number of differences specified with -d or --differences, must be in the range 0 to \xff.");
+  if (P.fastidious && P.differences != 1)
+    fatal("Fastidious mode (specified with -f or --fastidious) only works when the resolution (specified with -d or --differences) is 1.");
+  if (P.disable_sse3 && P.differences < 2)
+    fatal("Option --disable-sse3 or -x has no effect when d < 2 (SSE3 instructions are only used when d > 1).");
+  if (!P.fastidious) {
+    if (used['b' - 'a']) fatal("Option -b or --boundary specified without -f or --fastidious.");
+    if (used['c' - 'a']) fatal("Option -c or --ceiling specified without -f or --fastidious.");
+    if (used['y' - 'a']) fatal("Option -y or --bloom-bits specified without -f or --fastidious.");
+  }
+  if (P.differences < 2) {
+    if (used['m' - 'a']) fatal("Option -m or --match-reward specified when d < 2.");
+    if (used['p' - 'a']) fatal("Option -p or --mismatch-penalty specified when d < 2.");
+    if (used['g' - 'a']) fatal("Option -g or --gap-opening-penalty specified when d < 2.");
+    if (used['e' - 'a']) fatal("Option -e or --gap-extension-penalty specified when d < 2.");
+  }
+  if (P.gap_open < 0) fatal("Illegal gap opening penalty specified with -g or --gap-opening-penalty, must not be negative.");
+  if (P.gap_ext < 0) fatal("Illegal gap extension penalty specified with -e or --gap-extension-penalty, must not be negative.");
+  if (P.gap_open + P.gap_ext < 1) fatal("Illegal gap penalties specified, the sum of the gap open and the gap extension penalty must be at least 1.");
+  if (P.match < 1) fatal("Illegal match reward specified with -m or --match-reward, must be at least 1.");
+  if (P.mismatch < 1) fatal("Illegal mismatch penalty specified with -p or --mismatch-penalty, must be at least 1.");
+  if (P.boundary < 2) fatal("Illegal boundary specified with -b or --boundary, must be at least 2.");
+  if (used['c' - 'a'] && (P.ceiling < 40 || P.ceiling > (1 << 30)))
+    fatal("Illegal memory ceiling specified with -c or --ceiling, must be in the range 8 to 1,073,741,824 MB.");
+  if (P.bloom_bits < 2 || P.bloom_bits > 64) fatal("Illegal number of Bloom filter bits specified with -y or --bloom-bits, must be in the range 2 to 64.");
+  if (used['a' - 'a'] && P.append_abundance < 1) fatal("Illegal abundance value specified with -a or --append-abundance, must be at least 1.");
+  if (!P.network_file.empty() && P.differences != 1) fatal("A network file can only written when d = 1.");
+  if (P.version) { std::fputs(kHeader, stderr); return EXIT_SUCCESS; }
+  if (P.help) { std::fputs(kHeader, stderr); std::fputs(kUsage, stderr); return EXIT_SUCCESS; }
+  {
+    const int64_t sat16 = std::min<int64_t>(65535 / P.pen[0], (65535 - P.pen[1]) / P.pen[2]);
+    if (P.differences > sat16) fatal("Resolution (d) too high for the given scoring system.");
+    if (P.pen[0] > 255) fatal("Alignment scoring system yielded a mismatch penalty greater than 255, please use different parameter values.");
+  }
+  if (P.differences == 0) fatal("d = 0 (dereplication) is not provided by swarm_b200; use swarm -d 0 or vsearch --derep_fulllength.");
+  if (!P.uclust_file.empty()) fatal("the UCLUST writer (-u) is not provided by swarm_b200.");
+
+  // open_files, src/utils/open_and_close_files.cc:35-93
+  std::FILE *out = open_out(P.output_file);
+  if (!out) fatal("Unable to open output file for writing.");
+  std::FILE *logf = stderr;
+  if (!P.log.empty()) { logf = open_out(P.log); if (!logf) fatal("Unable to open log file for writing."); }
+  std::FILE *seedsf = nullptr, *statsf = nullptr, *structf = nullptr, *netf = nullptr;
+  if (!P.seeds.empty() && !(seedsf = open_out(P.seeds))) fatal("Unable to open seeds file for writing.");
+  if (!P.statistics_file.empty() && !(statsf = open_out(P.statistics_file))) fatal("Unable to open statistics file for writing.");
+  if (!P.internal_structure.empty() && !(structf = open_out(P.internal_structure))) fatal("Unable to open internal structure file for writing.");
+  if (!P.network_file.empty() && !(netf = open_out(P.network_file))) fatal("Unable to open network file for writing.");
+
+  // args_show, src/swarm.cc:211-257
+  std::fputs(kHeader, logf);
+  std::fprintf(logf, "Database file:     %s\nOutput file:       %s\n", P.input.c_str(), P.output_file.c_str());
+  if (!P.statistics_file.empty()) std::fprintf(logf, "Statistics file:   %s\n", P.statistics_file.c_str());
+  if (!P.internal_structure.empty()) std::fprintf(logf, "Int. struct. file  %s\n", P.internal_structure.c_str());
+  if (!P.network_file.empty()) std::fprintf(logf, "Network file       %s\n", P.network_file.c_str());
+  std::fprintf(logf, "Resolution (d):    %" PRId64 "\nThreads:           %" PRId64 "\n", P.differences, P.threads);
+  if (P.differences > 1) {
+    std::fprintf(logf, "Scores:            match: %" PRId64 ", mismatch: %" PRId64 "\n", P.match, P.mismatch);
+    std::fprintf(logf, "Gap penalties:     opening: %" PRId64 ", extension: %" PRId64 "\n", P.gap_open, P.gap_ext);
+    std::fprintf(logf, "Converted costs:   mismatch: %" PRId64 ", gap opening: %" PRId64 ", gap extension: %" PRId64 "\n", P.pen[0], P.pen[1], P.pen[2]);
+  }
+  std::fprintf(logf, "Break clusters:    %s\n", P.ncb ? "No" : "Yes");
+  if (P.fastidious) std::fprintf(logf, "Fastidious:        Yes, with boundary %" PRId64 "\n\n", P.boundary);
+  else std::fprintf(logf, "Fastidious:        No\n\n");
+
+  // db_read
+  swbh_db *db = nullptr;
+  if (swbh_db_read_fasta(P.input.c_str(), P.usearch ? 1 : 0, P.append_abundance, P.differences > 1 ? 1 : 0, &db) != 0)
+    fatal(swbh_last_error());
+  const uint32_t n = swbh_db_count(db);
+  std::fprintf(logf, "Database info:     %" PRIu64 " nt in %u sequences, longest %u nt\n", swbh_db_nucleotides(db), n, swbh_db_longest(db));
+
+  swbh_result *res = nullptr;
+  char *text = nullptr;
+  uint64_t len = 0;
+  if (n > 0) {
+    swb200_ctx *ctx = nullptr;
+    const char *dev = std::getenv("SWARM_B200_DEVICE");
+    engine_check(swb200_create(&ctx, dev ? std::atoi(dev) : 0));
+    engine_check(swb200_load_db(ctx, swbh_db_words(db), swbh_db_stride_words(db), swbh_db_lengths(db), swbh_db_abundances(db), n));
+    std::vector<uint32_t> swarm_of(n), generation(n), parent(n), extra(n, SWB200_NONE);
+    if (P.differences == 1) {
+      engine_check(swb200_d1_index(ctx));
+      uint64_t links = 0;
+      engine_check(swb200_d1_network(ctx, P.ncb ? 1 : 0, &links));
+      if (netf) {
+        std::vector<uint64_t> row_ptr(static_cast<size_t>(n) + 1);
+        std::vector<uint32_t> col(links ? links : 1);
+        engine_check(swb200_d1_get_network(ctx, row_ptr.data(), col.data()));
+        if (swbh_write_network(db, row_ptr.data(), col.data(), P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
+        write_all(netf, text, len);
+      }
+      engine_check(swb200_d1_cluster(ctx, swarm_of.data(), generation.data(), parent.data()));
+      bool grafting = false;
+      if (P.fastidious) {
+        uint64_t nl = 0, nh = 0;
+        engine_check(swb200_d1_fastidious(ctx, static_cast<uint64_t>(P.boundary), extra.data(), &nl, &nh));
+        grafting = nl != 0 && nh != 0;
+      }
+      if (swbh_d1_assemble(db, swarm_of.data(), generation.data(), parent.data(), grafting ? extra.data() : nullptr,
+                           static_cast<uint64_t>(P.boundary), &res) != 0) fatal(swbh_last_error());
+    } else {
+      engine_check(swb200_dn_cluster(ctx, static_cast<uint32_t>(P.differences), P.ncb ? 1 : 0, P.pen, swarm_of.data(), generation.data(),
+                                     parent.data(), extra.data()));
+      if (swbh_dn_assemble(db, swarm_of.data(), generation.data(), parent.data(), extra.data(), &res) != 0) fatal(swbh_last_error());
+    }
+    swb200_destroy(ctx);
+    if (swbh_write_swarms(db, res, P.mothur, P.differences, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
+    write_all(out, text, len);
+    if (seedsf) { if (swbh_write_seeds(db, res, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); }
+    if (structf) {
+      if ((P.differences == 1 ? swbh_write_structure(db, res, P.usearch, &text, &len) : swbh_dn_write_structure(db, res, P.usearch, &text, &len)) != 0)
+        fatal(swbh_last_error());
+      write_all(structf, text, len);
+    }
+    if (statsf) {
+      if ((P.differences == 1 ? swbh_write_stats(db, res, P.usearch, &text, &len) : swbh_dn_write_stats(db, res, P.usearch, &text, &len)) != 0)
+        fatal(swbh_last_error());
+      write_all(statsf, text, len);
+    }
+    // src/algod1.cc:1484-1487 / src/algo.cc:699-705
+    std::fprintf(logf, "\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\nMax generations:   %u\n", swbh_result_swarms(res), swbh_result_largest(res),
+                 P.differences == 1 ? swbh_result_maxgen(res) : std::max(1u, swbh_result_maxgen(res)));
+    swbh_result_free(res);
+  }
+  swbh_db_free(db);
+  for (std::FILE *f : {netf, structf, statsf, seedsf, out}) if (f) std::fclose(f);
+  if (logf != stderr) std::fclose(logf);
+  return EXIT_SUCCESS;
+}

@@ -34,7 +34,7 @@ def pytest_collection_modifyitems(config, items):
 def built():
     """Build every in-tree library once per session (no-op when up to date)."""
     import subprocess
-    subprocess.run(["make", "-s", "host", "tools", "oracle"], cwd=ROOT, check=True,
+    subprocess.run(["make", "-s", "host", "tools", "oracle", "cli"], cwd=ROOT, check=True,
                    stdout=subprocess.DEVNULL)
     if not (ROOT / "swarm_b200" / "libswarm_b200.so").exists():
         subprocess.run(["make", "-s", "engine"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)

@@ -1,0 +1,98 @@
+"""The drop-in command line bin/swarm_b200: option validation (CPU: identical messages and exit codes as
+the reference binary, src/swarm.cc:486-630) and end-to-end runs (GPU: byte-identical output files)."""
+import os
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import helpers
+from helpers import GOLDEN
+
+ROOT = Path(__file__).resolve().parent.parent
+CLI = ROOT / "bin" / "swarm_b200"
+FA = str(GOLDEN / "c1_1k_150.fasta")
+
+BAD = [
+    ["-t", "0"], ["-t", "513"], ["-d", "256"], ["-d", "-1"], ["-f", "-d", "2"], ["-x"], ["-b", "5"], ["-c", "100"], ["-y", "8"],
+    ["-m", "3"], ["-p", "3"], ["-g", "3"], ["-e", "3"], ["-d", "2", "-g", "-1"], ["-d", "2", "-e", "-1"], ["-d", "2", "-g", "0", "-e", "0"],
+    ["-d", "2", "-m", "0"], ["-d", "2", "-p", "0"], ["-f", "-b", "1"], ["-f", "-c", "10"], ["-f", "-y", "1"], ["-f", "-y", "65"],
+    ["-a", "0"], ["-d", "2", "-j", "/dev/null"], ["-t", "1x"], ["-d", "1", "-d", "1"], ["-o", "/nonexistent_dir/x"],
+    ["-d", "200", "-m", "1000", "-p", "1000"], ["-d", "2", "-m", "1000", "-p", "1000"],
+]
+
+
+@pytest.mark.parametrize("args", BAD, ids=[" ".join(a) for a in BAD])
+def test_option_validation_matches_reference(built, args):
+    if not helpers.have_ref():
+        pytest.skip("reference binary not built")
+    mine = subprocess.run([str(CLI)] + args + [FA], capture_output=True)
+    ref = subprocess.run([str(helpers.REF_BIN)] + args + [FA], capture_output=True)
+    assert ref.returncode == 1 and mine.returncode == 1
+    want = ref.stderr[ref.stderr.index(b"\nError:"):]        # the reference may print its banner first
+    assert mine.stderr[mine.stderr.index(b"\nError:"):] == want
+
+
+def test_help_and_version_exit_zero(built):
+    for flag in ("-h", "-v"):
+        p = subprocess.run([str(CLI), flag], capture_output=True)
+        assert p.returncode == 0 and b"swarm_b200" in p.stderr
+
+
+def test_unsupported_modes_fail_loudly(built):
+    assert subprocess.run([str(CLI), "-d", "0", FA], capture_output=True).returncode == 1
+    assert subprocess.run([str(CLI), "-u", "/dev/null", FA], capture_output=True).returncode == 1
+
+
+def _run(tmp, *flags, fasta=FA, outs=("o",)):
+    cmd = [str(CLI), "-l", str(tmp / "log")]
+    for k in outs:
+        cmd += ["-" + k, str(tmp / k)]
+    if "o" not in outs:
+        cmd += ["-o", os.devnull]
+    p = subprocess.run(cmd + list(flags) + [fasta], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    return {k: (tmp / k).read_bytes() for k in outs} | {"log": (tmp / "log").read_bytes()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["handmade", "c1_1k_150", "tie_1500_60", "short_600_20", "w65_300"])
+def test_cli_d1_outputs(built, tmp_path, name):
+    fa = str(GOLDEN / f"{name}.fasta")
+    r = _run(tmp_path, fasta=fa, outs=("o", "s", "i", "j", "w"))
+    for k in "osijw":
+        assert r[k] == (GOLDEN / f"{name}.{k}").read_bytes(), k
+    assert _run(tmp_path, "-n", fasta=fa)["o"] == (GOLDEN / f"{name}.n.o").read_bytes()
+    r = _run(tmp_path, "-f", fasta=fa, outs=("o", "s", "i"))
+    for k in "osi":
+        assert r[k] == (GOLDEN / f"{name}.f.{k}").read_bytes(), k
+    assert _run(tmp_path, "-f", "-b", "10", fasta=fa)["o"] == (GOLDEN / f"{name}.f.b10.o").read_bytes()
+
+
+@pytest.mark.gpu
+def test_cli_dn_usearch_mothur_stdin(built, tmp_path):
+    r = _run(tmp_path, "-d", "2", fasta=str(GOLDEN / "c1_1k_150.fasta"), outs=("o", "s", "i"))
+    for k in "osi":
+        assert r[k] == (GOLDEN / f"c1_1k_150.d2.{k}").read_bytes()
+    assert b"Number of swarms:" in r["log"] and b"Converted costs:   mismatch: 18, gap opening: 24, gap extension: 13" in r["log"]
+    r = _run(tmp_path, "-d", "2", "-m", "3", "-p", "2", "-g", "5", "-e", "3", fasta=str(GOLDEN / "w32_400.fasta"), outs=("o", "i"))
+    assert r["o"] == (GOLDEN / "w32_400.d2pen.o").read_bytes() and r["i"] == (GOLDEN / "w32_400.d2pen.i").read_bytes()
+    r = _run(tmp_path, "-z", fasta=str(GOLDEN / "usearch_300.fasta"), outs=("o", "s", "i", "w"))
+    for k in "osiw":
+        assert r[k] == (GOLDEN / f"usearch_300.{k}").read_bytes()
+    assert _run(tmp_path, "-z", "-r", fasta=str(GOLDEN / "usearch_300.fasta"))["o"] == (GOLDEN / "usearch_300.r.o").read_bytes()
+    # FASTA on stdin, swarms on stdout
+    p = subprocess.run([str(CLI), "-l", os.devnull], input=(GOLDEN / "handmade.fasta").read_bytes(), capture_output=True)
+    assert p.returncode == 0 and p.stdout == (GOLDEN / "handmade.o").read_bytes()
+
+
+@pytest.mark.gpu
+def test_cli_duplicate_sequences_message(built, tmp_path):
+    fa = tmp_path / "dup.fa"
+    fa.write_bytes(b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n")
+    mine = subprocess.run([str(CLI), "-o", os.devnull, str(fa)], capture_output=True)
+    assert mine.returncode == 1 and b"some fasta entries have identical sequences" in mine.stderr
+    if helpers.have_ref():
+        ref = subprocess.run([str(helpers.REF_BIN), "-o", os.devnull, str(fa)], capture_output=True)
+        assert ref.returncode == 1
+        assert mine.stderr[mine.stderr.index(b"\nError:"):] == ref.stderr[ref.stderr.index(b"\nError:"):]
