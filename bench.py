@@ -30,6 +30,10 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "amplicons clustered/s (device-timed) at d=1"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the network kernel(s) at 10 M x 150 bp, from the committed
+# ncu --set full captures: JOIN = k_join_candidates (2.954+0.320 GB) + k_join_verify (5.897+0.071 GB), profiles/r1h_*;
+# HALF (lean kernel) = 2.639+0.028 GB per 4 M seeds scaled to 10 M, profiles/r1d_*
+TRAFFIC = {"join": 9.242e9, "half": 6.67e9, "full": None}
 UNIT = "amplicons/s"
 
 
@@ -315,7 +319,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": {0: "k_d1_network<FULL>", 1: "k_d1_network_half", 2: "k_join_network"}[args.enum_mode], "bytes_per_amplicon_counted": b1_counted,
+                         "traffic": TRAFFIC.get({0: "full", 1: "half", 2: "join"}[args.enum_mode]) if (n == 10_000_000 and world == 1) else None,
+                         "traffic_source": "profiles/r1h_*_full_set_10M.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, network kernels)",
+                         "kernel": {0: "k_d1_network<FULL>", 1: "k_d1_network_half", 2: "k_join_candidates + k_join_verify (network phase)"}[args.enum_mode], "bytes_per_amplicon_counted": b1_counted,
                          "bytes_per_amplicon_survey_formula_full_enumeration": b1_survey,
                          "achieved_if_counted_as_full_enumeration": seeds * b1_survey / net_s / 1e9,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
