@@ -55,8 +55,10 @@ const char *swb200_last_error(void);
 /* Tunables (call before swb200_d1_index).  key: "enum_mode" (SWB200_ENUM_*), "bloom_bytes_per_slot"
  * (1,2,4,8: filter size = table slots * this; reference uses 1, src/algod1.cc:1127),
  * "collect_stats" (0/1), "net_kernel" (0 auto, 1 first-generation kernel, 2 lean HALF kernel),
+ * "join_kernel" (JOIN mode: 0 auto = radix-partitioned join in shared memory, d1_tilejoin.cuh; 1 = global hash
+ * multimap, d1_join.cuh — same links), "tile_cmax" (test hook: cap on the entries a tile may hold in shared memory),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "cluster_kernel" (0 fused label+generation relaxation, 1 label propagation then BFS), "dn_filter" (0 auto,
+ * "cluster_kernel" (0 fused label+generation relaxation in one persistent cooperative kernel, 2 the same with one launch per round, 1 label propagation then BFS), "dn_filter" (0 auto,
  * 1 all-pairs q-gram filter),
  * "shard_rank"/"shard_world" (this context's share of the network build, SURVEY.md §8e: in JOIN mode the
  * K-mer table is sharded by hash range — every rank scans all lookups but builds and walks only its own

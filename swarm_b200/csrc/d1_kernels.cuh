@@ -16,6 +16,7 @@
 //   * hash matches are verified exactly on the packed words (funnel-shift compare);
 //   * the packed seeds are staged into shared memory by per-warp double-buffered 1-D TMA bulk copies.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace swb {
@@ -580,6 +581,93 @@ __global__ void k_key_parent(const uint2 *edges, uint64_t m, const unsigned long
 __global__ void k_key_unpack(const unsigned long long *key, uint32_t *label, uint32_t *generation, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { label[i] = static_cast<uint32_t>(key[i] >> 32); generation[i] = static_cast<uint32_t>(key[i]); }
+}
+
+// ---- the same fused relaxation as ONE persistent cooperative kernel (default): init, every round, the parent
+// pass and the unpacking run back to back with grid-wide barriers in between, so a clustering costs one launch
+// and no host round trip (the host-looped variant above pays a launch + a D2H flag read per round, ~15 rounds).
+// flags[3] rotate: round r raises flags[r%3]; flags[(r+1)%3] is cleared during round r (its last readers
+// passed the barrier of round r-1).
+// A link u->v can only lower key[v] in round r if key[u] was lowered in round r-1, so every round tests one bit
+// of a "lowered last round" bitmap (n/8 bytes, L2-resident) before touching the two random 8-byte keys of the
+// link: after the first two rounds most links are skipped (the first cut relaxed every link in every round and
+// was bound by ~300 M random L2 sectors: 1.2 ms at 10 M amplicons).  bits = 3 rotating bitmaps of `nwords` words:
+// round r reads bits[r%3], sets bits[(r+1)%3], clears bits[(r+2)%3].
+constexpr int kClU = 8;
+__global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *parent,
+                                                            uint32_t *label, uint32_t *generation, uint32_t n,
+                                                            volatile uint32_t *flags, uint32_t *rounds_out, uint32_t *bits,
+                                                            uint32_t nwords) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (uint64_t v = tid; v < n; v += nth) { key[v] = static_cast<unsigned long long>(v) << 32; parent[v] = kNone; }
+  for (uint64_t w = tid; w < 3ull * nwords; w += nth) bits[w] = 0;
+  if (tid == 0) { flags[0] = 0; flags[1] = 0; flags[2] = 0; }
+  grid.sync();
+  uint32_t round = 0;
+  for (;; ++round) {
+    const uint32_t *rd = bits + static_cast<size_t>(round % 3) * nwords;
+    uint32_t *wr = bits + static_cast<size_t>((round + 1) % 3) * nwords;
+    uint32_t *cl = bits + static_cast<size_t>((round + 2) % 3) * nwords;
+    if (tid == 0) flags[(round + 1) % 3] = 0;
+    if (round) for (uint64_t w = tid; w < nwords; w += nth) cl[w] = 0;
+    int ch = 0;
+    // kClU links per thread and step, loads issued stage by stage (links, bitmap words, keys): the loop is a chain
+    // of dependent random reads, and one link at a time left each warp with a single request in flight
+    for (uint64_t base = tid; base < m; base += nth * kClU) {
+      uint2 ed[kClU];
+      bool act[kClU];
+#pragma unroll
+      for (int k = 0; k < kClU; ++k) {
+        const uint64_t e = base + static_cast<uint64_t>(k) * nth;
+        act[k] = e < m;
+        ed[k] = act[k] ? edges[e] : make_uint2(0u, 0u);
+      }
+      if (round) {
+        uint32_t w[kClU];
+#pragma unroll
+        for (int k = 0; k < kClU; ++k) w[k] = act[k] ? rd[ed[k].x >> 5] : 0u;
+#pragma unroll
+        for (int k = 0; k < kClU; ++k) act[k] = act[k] && ((w[k] >> (ed[k].x & 31u)) & 1u);
+      }
+      unsigned long long ks[kClU], kd[kClU];
+#pragma unroll
+      for (int k = 0; k < kClU; ++k) {
+        ks[k] = act[k] ? key[ed[k].x] : ~0ull;
+        kd[k] = act[k] ? key[ed[k].y] : 0ull;
+      }
+#pragma unroll
+      for (int k = 0; k < kClU; ++k) {
+        const unsigned long long cand = ks[k] + 1ull;
+        if (act[k] && cand < kd[k]) {
+          if (atomicMin(&key[ed[k].y], cand) > cand) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+        }
+      }
+    }
+    if (__syncthreads_or(ch) && threadIdx.x == 0) flags[round % 3] = 1;
+    grid.sync();
+    if (flags[round % 3] == 0) break;
+  }
+  for (uint64_t base = tid; base < m; base += nth * kClU) {
+    uint2 ed[kClU];
+    unsigned long long ks[kClU], kd[kClU];
+#pragma unroll
+    for (int k = 0; k < kClU; ++k) {
+      const uint64_t e = base + static_cast<uint64_t>(k) * nth;
+      ed[k] = e < m ? edges[e] : make_uint2(kNone, kNone);
+    }
+#pragma unroll
+    for (int k = 0; k < kClU; ++k) {
+      ks[k] = ed[k].x != kNone ? key[ed[k].x] : 0ull;
+      kd[k] = ed[k].x != kNone ? key[ed[k].y] : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kClU; ++k)
+      if (ed[k].x != kNone && ks[k] + 1ull == kd[k]) atomicMin(&parent[ed[k].y], ed[k].x);
+  }
+  for (uint64_t v = tid; v < n; v += nth) { label[v] = static_cast<uint32_t>(key[v] >> 32); generation[v] = static_cast<uint32_t>(key[v]); }
+  if (tid == 0 && rounds_out) *rounds_out = round + 1;
 }
 
 __global__ void k_bfs_unpack(const unsigned long long *key, uint32_t *generation, uint32_t *parent, uint32_t n) {

@@ -33,6 +33,13 @@ __global__ void k_minmax_u32(const uint32_t *v, uint32_t n, uint32_t *out) {
   if ((threadIdx.x & 31u) == 0) { atomicMax(out, m); atomicMax(out + 1, w); }
 }
 
+// *flag = 1 when some abundance is smaller than its successor's (the database is not sorted descending)
+__global__ void k_unsorted_u64(const uint64_t *v, uint32_t n, uint32_t *flag) {
+  bool bad = false;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) bad |= v[i] < v[i + 1];
+  if (__any_sync(kFull, bad) && (threadIdx.x & 31u) == 0) *flag = 1u;
+}
+
 // ---- q-gram parity vectors (a10) ------------------------------------------------------------------
 // one warp per amplicon; the 1024-bit vector lives in shared memory (32 x u32), bits toggled with
 // shared atomics, then written as one coalesced 128-byte row.

@@ -7,6 +7,7 @@
 #include "d1_fastidious.cuh"
 #include "d1_fastidious_join.cuh"
 #include "d1_join.cuh"
+#include "d1_tilejoin.cuh"
 #include "dn_kernels.cuh"
 
 #include <algorithm>
@@ -99,7 +100,7 @@ struct swb200_ctx {
   bool have_network = false;
   int ncb = 0;
   // clustering
-  DevBuf<uint32_t> label, generation, parent;
+  DevBuf<uint32_t> label, generation, parent, cl_bits;
   DevBuf<unsigned long long> key;
   bool clustered = false;
   // fastidious
@@ -107,7 +108,9 @@ struct swb200_ctx {
   DevBuf<uint32_t> light_ids, heavy_ids, graft;
   uint32_t max_len = 0, min_len = 0;
   uint32_t minmax[2] = {0, 0};
-  int cluster_kernel = 0; // 0/2 fused key relaxation, 1 = label propagation + BFS (first generation)
+  uint32_t unsorted = 0;
+  bool sorted_desc = false;          // abundances never increase with the id (the reference's order, src/db.cc:392-406)
+  int cluster_kernel = 0; // 0 fused key relaxation as one persistent cooperative kernel, 2 the same host-looped, 1 = label propagation + BFS
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
@@ -116,6 +119,15 @@ struct swb200_ctx {
   uint64_t jtab_buckets = 0, jb_lo = 0, jb_hi = 0;
   uint32_t jK = 0;
   bool join_active = false;
+  // partitioned (tile) join: d1_tilejoin.cuh
+  int join_kernel = 0;               // 0 auto (tile join when the rows fit shared memory), 1 = global hash multimap (d1_join.cuh)
+  bool tile_active = false;
+  DevBuf<uint32_t> tj_count, tj_cursor, tj_big;
+  DevBuf<unsigned long long> tj_off, tj_entries;
+  uint32_t tj_tiles = 0, tj_lo = 0, tj_hi = 0, tj_cmax = 0;
+  uint32_t tj_cmax_override = 0;     // test hook: pretend shared memory holds fewer entries (exercises k_tile_join_big)
+  unsigned long long tj_total = 0;
+  size_t tj_smem = 0;
   uint64_t fstats[4] = {0, 0, 0, 0};
   // d>1
   DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
@@ -205,7 +217,7 @@ int swb200_create(swb200_ctx **out, int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    c->counters.alloc(16);
+    c->counters.alloc(32);
   } catch (const CudaFail &f) {
     delete c;
     return f.code;
@@ -219,9 +231,10 @@ void swb200_destroy(swb200_ctx *c) {
   cudaSetDevice(c->device);
   c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
-  c->label.release(); c->generation.release(); c->parent.release(); c->key.release();
+  c->label.release(); c->generation.release(); c->parent.release(); c->key.release(); c->cl_bits.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
+  c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -237,6 +250,8 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
   else if (k == "collect_stats") c->collect_stats = v != 0;
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
+  else if (k == "join_kernel" && v >= 0 && v <= 1) c->join_kernel = static_cast<int>(v);
+  else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
   else if (k == "cluster_kernel" && v >= 0 && v <= 2) c->cluster_kernel = static_cast<int>(v);
@@ -316,7 +331,10 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
     CK(cudaMemsetAsync(c->counters.p + 15, 0, 8, c->stream));
     k_minmax_u32<<<c->sm_count * 2, 256, 0, c->stream>>>(c->len.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 15));
     CK(cudaMemcpyAsync(c->minmax, c->counters.p + 15, 8, cudaMemcpyDeviceToHost, c->stream));
-    c->launches++;
+    CK(cudaMemsetAsync(c->counters.p + 20, 0, 8, c->stream));
+    k_unsorted_u64<<<c->sm_count * 2, 256, 0, c->stream>>>(c->abundance.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 20));
+    CK(cudaMemcpyAsync(&c->unsorted, c->counters.p + 20, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->launches += 2;
   }
   c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
   uint64_t sm = 0x5eedb200c0ffeeULL;
@@ -326,14 +344,69 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   c->toc(0);
   c->max_len = c->minmax[0];
   c->min_len = ~c->minmax[1];
+  c->sorted_desc = c->unsorted == 0;
   API_END()
+}
+
+static TileJoinParams tile_params(swb200_ctx *c) {
+  TileJoinParams J{};
+  J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
+  J.n_tiles = c->tj_tiles; J.t_lo = c->tj_lo; J.t_hi = c->tj_hi; J.cmax = c->tj_cmax;
+  uint32_t idb = 12;
+  while (idb < 32 && (1ull << idb) < c->n) ++idb;
+  J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0;
+  J.tile_count = c->tj_count.p; J.tile_off = c->tj_off.p; J.tile_cursor = c->tj_cursor.p;
+  J.big_tiles = c->tj_big.p; J.big_count = reinterpret_cast<uint32_t *>(c->counters.p + 16);
+  J.entries = c->tj_entries.p;
+  J.edges = c->edges.p; J.edge_count = c->counters.p; J.edge_cap = c->edges.n;
+  J.ncb = c->ncb; J.dup_flag = reinterpret_cast<uint32_t *>(c->counters.p + 8);
+  J.stats = c->collect_stats ? c->counters.p + 1 : nullptr;
+  return J;
 }
 
 int swb200_d1_index(swb200_ctx *c) {
   API_BEGIN(c)
   if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
-  c->join_active = false;
+  c->join_active = c->tile_active = false;
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
+  if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8 && c->join_kernel != 1 && c->stride <= 32 && c->max_len < 8192) {
+    // JOIN, partitioned: two K-mer entries per amplicon appended to hash-range tiles (d1_tilejoin.cuh)
+    c->tj_cmax = c->stride <= 6 ? 768 : (c->stride <= 14 ? 384 : 192);
+    const uint64_t want_tiles = (static_cast<uint64_t>(c->n) * 2 + c->tj_cmax / 2 - 1) / (c->tj_cmax / 2);
+    c->tj_tiles = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(want_tiles, 0x7FFFFFFFull)));
+    const uint32_t per = (c->tj_tiles + c->shard_world - 1) / c->shard_world;
+    c->tj_lo = std::min<uint64_t>(static_cast<uint64_t>(per) * c->shard_rank, c->tj_tiles);
+    c->tj_hi = std::min<uint64_t>(static_cast<uint64_t>(c->tj_lo) + per, c->tj_tiles);
+    const uint32_t T = c->tj_hi - c->tj_lo;
+    if (c->tj_cmax_override >= 2) c->tj_cmax = std::min(c->tj_cmax, c->tj_cmax_override);
+    c->tj_smem = static_cast<size_t>(c->tj_cmax) * 8 + static_cast<size_t>(c->tj_cmax) * c->stride * 8 + kTjOutCap * 8 +
+                 (kTjBuckets + 2) * 4 + (static_cast<size_t>(c->tj_cmax) + 2) * 4;
+    c->tj_count.alloc(T + 1); c->tj_cursor.alloc(T + 1); c->tj_big.alloc(T + 1); c->tj_off.alloc(T + 2);
+    c->tic();
+    CK(cudaMemsetAsync(c->counters.p, 0, 17 * 8, c->stream));
+    CK(cudaMemsetAsync(c->tj_count.p, 0, static_cast<size_t>(T + 1) * 4, c->stream));
+    CK(cudaMemsetAsync(c->tj_cursor.p, 0, static_cast<size_t>(T + 1) * 4, c->stream));
+    TileJoinParams J = tile_params(c);
+    const unsigned pb = (c->n + 255) / 256;
+    unsigned long long total = 0;
+    if (T) {
+      k_tile_partition<true><<<pb, 256, 0, c->stream>>>(J);
+      k_tile_scan<<<1, 1024, 0, c->stream>>>(J);
+      CK(cudaMemcpyAsync(&total, c->tj_off.p + T, 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      c->tj_total = total;
+      c->tj_entries.alloc(std::max<unsigned long long>(total, 1));
+      J.entries = c->tj_entries.p;
+      k_tile_partition<false><<<pb, 256, 0, c->stream>>>(J);
+      CK(cudaGetLastError());
+      c->launches += 3;
+    }
+    c->toc(1);
+    c->indexed = true;
+    c->join_active = c->tile_active = true;
+    c->have_network = c->clustered = false;
+    return SWB200_OK;
+  }
   if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8) {
     // JOIN: the index is a multimap of two K-mer pieces per amplicon (d1_join.cuh); no Zobrist table, no filter
     const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(c->n) * 2 * 5 / 2 + 3) / 4 * 4);
@@ -424,7 +497,23 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
   c->tic();
   for (int attempt = 0; attempt < 2; ++attempt) {
     CK(cudaMemsetAsync(c->counters.p, 0, 10 * 8, c->stream));
-    if (c->join_active) {
+    if (c->tile_active) {
+      TileJoinParams J = tile_params(c);
+      const uint32_t T = c->tj_hi - c->tj_lo;
+      if (T) {
+        if (c->collect_stats) {
+          CK(cudaFuncSetAttribute(k_tile_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->tj_smem)));
+          k_tile_join<true><<<T, 256, c->tj_smem, c->stream>>>(J);
+          k_tile_join_big<true><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
+        } else {
+          CK(cudaFuncSetAttribute(k_tile_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->tj_smem)));
+          k_tile_join<false><<<T, 256, c->tj_smem, c->stream>>>(J);
+          k_tile_join_big<false><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
+        }
+        c->launches += 2;
+        CK(cudaGetLastError());
+      }
+    } else if (c->join_active) {
       NetJoinParams J{};
       J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.n = c->n; J.stride = c->stride; J.K = c->jK;
       J.table = c->jtab.p; J.n_buckets = c->jtab_buckets; J.b_lo = c->jb_lo; J.b_hi = c->jb_hi;
@@ -460,6 +549,7 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
     c->n_edges = host[0];
     for (int i = 0; i < 4; ++i) c->stats[i] = host[1 + i];
     c->stats[4] = c->n_edges;
+    if (c->tile_active && c->collect_stats) c->stats[0] = c->tj_total;     // entries of this rank's tiles (2 per amplicon over all ranks)
     if (c->join_active) {
       uint32_t dup = 0;
       CK(cudaMemcpy(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost));
@@ -545,8 +635,27 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
+  if (c->cluster_kernel == 0) {
+    // fused label+generation relaxation as one persistent cooperative kernel (d1_kernels.cuh: k_cluster_persistent)
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_persistent, 256, 0));
+    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+    const uint2 *e_p = c->edges.p;
+    uint64_t m_ = m;
+    unsigned long long *key_p = c->key.p;
+    uint32_t *par_p = c->parent.p, *lab_p = c->label.p, *gen_p = c->generation.p, n_ = n;
+    uint32_t *flags_p = reinterpret_cast<uint32_t *>(c->counters.p + 17), *rounds_p = reinterpret_cast<uint32_t *>(c->counters.p + 19);
+    uint32_t nwords = (n + 31) / 32;
+    c->cl_bits.alloc(static_cast<size_t>(nwords) * 3);
+    uint32_t *bits_p = c->cl_bits.p;
+    void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords};
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_persistent), dim3(grid), dim3(256), args, 0, c->stream));
+    c->launches++;
+    return;
+  }
   if (c->cluster_kernel != 1) {
-    // fused label+generation relaxation (d1_kernels.cuh: k_key_*)
+    // fused label+generation relaxation, host-looped (d1_kernels.cuh: k_key_*)
     k_key_init<<<vb, 256, 0, c->stream>>>(c->key.p, c->parent.p, n);
     c->launches++;
     for (int round = 0; m > 0 && round < 1 << 20; ++round) {

@@ -102,7 +102,7 @@ def test_golden_cases(built, name, mode):
     assert res.structure_text() == (GOLDEN / f"{name}.i").read_bytes()
     assert network_text(db, rp, col) == (GOLDEN / f"{name}.j").read_bytes()
     if mode == ENUM_JOIN and db.len.min() >= 16:
-        assert stats["variants"] == 2 * db.n             # two lookups per amplicon, no enumeration
+        assert stats["variants"] == 2 * db.n             # two K-mer entries per amplicon, no enumeration
     if mode == ENUM_FULL:   # the full enumeration probes exactly the reference's variant count
         assert stats["variants"] == int(orc.net_stats[0])
 
@@ -125,6 +125,66 @@ def test_lean_half_kernel_matches_first_kernel(built, name):
     l2, *_r2, s2 = run_engine(db, ENUM_HALF, net_kernel=2)
     assert np.array_equal(l1, l2) and np.array_equal(l2, orc.links())
     assert s1["variants"] == s2["variants"] and s1["filter_pass"] == s2["filter_pass"]
+
+
+# JOIN flavours: partitioned join in shared memory (default), the same with tiny tiles (every tile takes the
+# global-memory sweep of k_tile_join_big), and the global hash multimap of d1_join.cuh
+JOIN_FLAVOURS = [{}, {"tile_cmax": 8}, {"join_kernel": 1}]
+
+
+@pytest.mark.parametrize("flavour", JOIN_FLAVOURS)
+@pytest.mark.parametrize("name", CASES)
+def test_join_flavours_golden(built, name, flavour):
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    for ncb in (False, True):
+        links, sw, gen, par, rp, col, stats = run_engine(db, ENUM_JOIN, ncb=ncb, **flavour)
+        if not ncb:
+            assert np.array_equal(links, orc.links())
+            assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
+            assert network_text(db, rp, col) == (GOLDEN / f"{name}.j").read_bytes()
+        elif (GOLDEN / f"{name}.n.o").exists():
+            assert D1Result(db, sw, gen, par).swarms_text() == (GOLDEN / f"{name}.n.o").read_bytes()
+
+
+@pytest.mark.parametrize("flavour", JOIN_FLAVOURS)
+@pytest.mark.parametrize("n,L,seed,mode_ab", [(60000, 150, 42, 0), (40000, 80, 9, 1), (30000, 400, 5, 0), (20000, 31, 4, 1), (15000, 700, 6, 0)])
+def test_join_flavours_seeded(built, tmp_path, n, L, seed, mode_ab, flavour):
+    fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
+    db = HostDb(fa)
+    orc = Oracle(db)
+    orc.network()
+    links, *_ = run_engine(db, ENUM_JOIN, **flavour)
+    assert np.array_equal(links, orc.links())
+
+
+@pytest.mark.parametrize("group", [300, 3000])
+def test_join_dense_group(built, tmp_path, group):
+    """one dense group sharing both K-mers (every amplicon is a one- or two-edit variant of the same centroid, edits
+    in the middle).  3000: the tile holding it overflows shared memory and goes through k_tile_join_big; 300: it
+    fits, but its 45 k same-key pairs fill the tile's pair queue many times (resumable walk of k_tile_join)."""
+    rng = np.random.default_rng(5)
+    cen = rng.integers(0, 4, 200)
+    seqs = {"".join("ACGT"[b] for b in cen)}
+    while len(seqs) < group:
+        s = cen.copy()
+        p = int(rng.integers(70, 130))
+        s[p] = (s[p] + int(rng.integers(1, 4))) % 4
+        if rng.random() < 0.5:
+            q = int(rng.integers(70, 130))
+            s[q] = (s[q] + int(rng.integers(1, 4))) % 4
+        seqs.add("".join("ACGT"[b] for b in s))
+    text = "".join(f">d{i}_{1 + (i * 7919) % 50}\n{s}\n" for i, s in enumerate(sorted(seqs))).encode()
+    db = HostDb(text=text)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    for flavour in JOIN_FLAVOURS:
+        links, sw, gen, par, *_ = run_engine(db, ENUM_JOIN, **flavour)
+        assert np.array_equal(links, orc.links())
+        assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
 
 
 def test_duplicates_rejected(built):
@@ -152,7 +212,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
+    for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1, "cluster_kernel": 2}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
