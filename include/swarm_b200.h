@@ -58,7 +58,7 @@ const char *swb200_last_error(void);
  * "join_kernel" (JOIN mode: 0 auto = radix-partitioned join in shared memory, d1_tilejoin.cuh; 1 = global hash
  * multimap, d1_join.cuh — same links), "tile_cmax" (test hook: cap on the entries a tile may hold in shared memory),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "cluster_kernel" (0 fused label+generation relaxation in one persistent cooperative kernel, 2 the same with one launch per round, 1 label propagation then BFS), "dn_filter" (0 auto,
+ * "cluster_kernel" (0 fused label/generation relaxation of the frontier in one persistent cooperative kernel, 3 the same after counting-sorting the links by source, 2 one launch per round, 1 label propagation then BFS), "dn_filter" (0 auto,
  * 1 all-pairs q-gram filter),
  * "shard_rank"/"shard_world" (this context's share of the network build, SURVEY.md §8e: in JOIN mode the
  * K-mer table is sharded by hash range — every rank scans all lookups but builds and walks only its own
@@ -71,6 +71,18 @@ int  swb200_set_option(swb200_ctx *ctx, const char *key, int64_t value);
  * len[i] in nt; abundance[i].  Host pointers; copied (pinned staging) to the device. */
 int  swb200_load_db(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words,
                     const uint32_t *len, const uint64_t *abundance, uint32_t n);
+
+/* Multi-GPU upload: every rank holds the whole database on its device, but pushes only its own
+ * rows [first, first+count) over PCIe; the ranks then exchange rows device-to-device (NCCL all-gather over NVLink,
+ * in place on the buffers swb200_db_device returns: equal shards of ceil(n_total / shard_world) rows, the buffers
+ * are sized for that) and call swb200_db_commit.  Set "shard_world" before.  swb200_load_db_device adopts a database
+ * that is already in device memory (device pointers, copied). */
+int  swb200_load_db_shard(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
+                          const uint64_t *abundance, uint32_t n_total, uint32_t first, uint32_t count);
+int  swb200_db_device(swb200_ctx *ctx, void **d_words, void **d_len, void **d_abundance);
+int  swb200_db_commit(swb200_ctx *ctx);
+int  swb200_load_db_device(swb200_ctx *ctx, const void *d_words, uint32_t stride_words, const void *d_len,
+                           const void *d_abundance, uint32_t n);
 
 /* Replaces the "Hashing sequences" phase: zobrist_hash of every amplicon (src/db.cc:761,
  * src/zobrist.cc:134-184), hash_alloc + hash_insert + bloom_set (src/algod1.cc:1118-1139,188-208),
@@ -101,6 +113,26 @@ int  swb200_d1_import_links_device(swb200_ctx *ctx, const void *d_pairs, uint64_
  * the amplicon that claimed i (SWB200_NONE for seeds).  Any output pointer may be NULL. */
 int  swb200_d1_cluster(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent);
 
+/* The rows [first, first+count) of the last clustering (a rank's own share of the result). */
+int  swb200_d1_get_cluster(swb200_ctx *ctx, uint32_t first, uint32_t count, uint32_t *swarm_of, uint32_t *generation,
+                           uint32_t *parent);
+
+/* Multi-GPU clustering of ONE job.  Each rank calls swb200_d1_network on its share of the join
+ * (shard_rank / shard_world), then swb200_d1_cluster_dist on all ranks together: one persistent kernel per GPU
+ * routes the links to the owners of their sources, relaxes them in rounds and exchanges the cross-rank updates
+ * itself, over NVLink, by writing into the peers' inboxes (no link gather, no host round trip per round).
+ * Ownership is block-cyclic: rank r owns the ids of the blocks b = r, r+world, ... of 4096 consecutive ids; its result
+ * arrays hold those rows packed in ascending id order (swb200_dist_row_count rows; row i is amplicon
+ * swb200_dist_row_id(rank, world, i)).  The inboxes are peer-visible buffers the CALLER provides (CUDA IPC / torch
+ * symmetric memory): peer_buffers[r] = address, in this process, of rank r's buffer; every buffer has buffer_bytes >=
+ * swb200_dist_buffer_bytes(n, world, items_per_amplicon) (4 is ample unless the network is very dense; an overflow is
+ * reported as SWB200_ENOMEM).  Call swb200_dist_setup on every rank, then a barrier, before the first clustering. */
+uint64_t swb200_dist_buffer_bytes(uint32_t n_total, uint32_t world, uint32_t items_per_amplicon);
+uint32_t swb200_dist_row_count(uint32_t n_total, uint32_t rank, uint32_t world);
+uint32_t swb200_dist_row_id(uint32_t rank, uint32_t world, uint32_t row);
+int  swb200_dist_setup(swb200_ctx *ctx, uint32_t rank, uint32_t world, void *const *peer_buffers, uint64_t buffer_bytes);
+int  swb200_d1_cluster_dist(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent);
+
 /* Replaces the fastidious passes (mark_light_thread / check_heavy_thread, src/algod1.cc:374-552):
  * for every amplicon l of a light swarm (mass < boundary), graft_cand[l] = the smallest amplicon id h
  * belonging to a heavy swarm such that h and l share a microvariant, else SWB200_NONE (:244-258).
@@ -119,13 +151,17 @@ int  swb200_d1_fastidious(swb200_ctx *ctx, uint64_t boundary, uint32_t *graft_ca
 int  swb200_dn_cluster(swb200_ctx *ctx, uint32_t d, int no_cluster_breaking, const int64_t penalties[3],
                        uint32_t *swarm_of, uint32_t *generation, uint32_t *parent, uint32_t *pdiff);
 
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on: lets the caller bracket calls
+ * with its own CUDA events, or order collectives (NCCL) after the engine's work without a host round trip. */
+int  swb200_stream(swb200_ctx *ctx, void **stream);
+
 /* Device time (CUDA events on the engine's stream) of the last call, and accumulated per phase.
  * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 6 d>1 (all of swb200_dn_cluster) */
 double swb200_last_device_seconds(swb200_ctx *ctx);
 double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
- * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
+ * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create, [6] packed sequences gathered into shared memory (tile join); [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
  * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links. */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 

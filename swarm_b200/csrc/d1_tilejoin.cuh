@@ -52,7 +52,7 @@ struct TileJoinParams {
   uint64_t edge_cap;
   int ncb;
   uint32_t *dup_flag;
-  unsigned long long *stats;        // [0] entries joined [1] same-key pairs [2] pairs enumerated [3] exact comparisons
+  unsigned long long *stats;        // [0] entries joined [1] same-key pairs [2] pairs enumerated [3] exact comparisons [4] rows gathered
 };
 
 // entry = key | abh(7) | len(13) | id(id_bits), key = tag | piece in the remaining top bits (>= 12).  abh is a
@@ -136,7 +136,18 @@ __device__ __forceinline__ void tj_decide(const TileJoinParams &J, unsigned long
     if (((ri[0] ^ rj[0]) & kmask0) == 0 && (J.K <= 32 || ((ri[1] ^ rj[1]) & kmask1) == 0)) return;
   }
   if (STATS) st_x++;
-  const int cls = edit_class(ri, tj_len(J, ei), rj, tj_len(J, ej), J.stride);
+  const uint32_t Li = tj_len(J, ei), Lj = tj_len(J, ej);
+  int cls;
+  if (Li == Lj) {                                        // substitution: Hamming distance over all (zero padded) words, no early
+    uint32_t diff = 0;                                   // exit — every lane of the warp runs the same trip count
+    for (uint32_t k = 0; k < J.stride; ++k) {
+      const uint64_t d = ri[k] ^ rj[k];
+      diff += __popcll((d | (d >> 1)) & 0x5555555555555555ull);
+    }
+    cls = diff > 1 ? 2 : static_cast<int>(diff);
+  } else {
+    cls = edit_class(ri, Li, rj, Lj, J.stride);
+  }
   if (cls == 0) atomicExch(J.dup_flag, 1u);
   if (cls != 1) return;
   uint32_t a = tj_id(J, ei), v = tj_id(J, ej);
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(256) k_tile_join(TileJoinParams J) {
     if (tid + k * 256 < c) ent[boff[static_cast<uint32_t>(e[k] >> kshift) & (kTjBuckets - 1)] + rank[k]] = e[k];
   __syncthreads();
 
-  unsigned long long st_p = 0, st_s = 0, st_x = 0;
+  unsigned long long st_p = 0, st_s = 0, st_x = 0, st_r = 0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint32_t s = tid + k * 256;
@@ -245,6 +256,7 @@ __global__ void __launch_bounds__(256) k_tile_join(TileJoinParams J) {
     for (uint32_t q = lo; q < hi && !partner; ++q) partner = q != s && tj_compatible(J, es, ent[q]);
     pref[s] = partner ? hi - s - 1 : 0u;
     if (partner) {
+      if (STATS) st_r++;
       const uint64_t *w = J.words + static_cast<uint64_t>(tj_id(J, es)) * stride;
       uint64_t *r = rows + static_cast<size_t>(s) * stride;
       for (uint32_t x = 0; x < stride; ++x) r[x] = w[x];
@@ -297,12 +309,14 @@ __global__ void __launch_bounds__(256) k_tile_join(TileJoinParams J) {
       st_p += __shfl_xor_sync(kFull, st_p, mm);
       st_s += __shfl_xor_sync(kFull, st_s, mm);
       st_x += __shfl_xor_sync(kFull, st_x, mm);
+      st_r += __shfl_xor_sync(kFull, st_r, mm);
     }
     if ((tid & 31u) == 0) {
       atomicAdd(&J.stats[0], st_e);
       atomicAdd(&J.stats[1], st_p);
       atomicAdd(&J.stats[2], st_s);
       atomicAdd(&J.stats[3], st_x);
+      atomicAdd(&J.stats[4], st_r);
     }
   }
 }

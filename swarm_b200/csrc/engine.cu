@@ -8,6 +8,8 @@
 #include "d1_fastidious_join.cuh"
 #include "d1_join.cuh"
 #include "d1_tilejoin.cuh"
+#include "d1_cluster.cuh"
+#include "d1_dist.cuh"
 #include "dn_kernels.cuh"
 
 #include <algorithm>
@@ -100,7 +102,16 @@ struct swb200_ctx {
   bool have_network = false;
   int ncb = 0;
   // clustering
-  DevBuf<uint32_t> label, generation, parent, cl_bits;
+  DevBuf<uint32_t> label, generation, parent, cl_bits, cl_deg, cl_row, cl_srcs, cl_dsts;
+  DevBuf<unsigned long long> cl_tot, cl_ts;
+  // multi-GPU clustering over peer memory (d1_dist.cuh)
+  uint32_t dist_rank = 0, dist_world = 0;
+  unsigned char *dist_peer[kDistMaxWorld] = {};
+  uint64_t dist_cap = 0;
+  DevBuf<unsigned long long> dist_lcnt;
+  DevBuf<uint2> dist_links;
+  unsigned long long dist_calls = 0;
+  uint32_t dist_rounds = 0;
   DevBuf<unsigned long long> key;
   bool clustered = false;
   // fastidious
@@ -109,8 +120,11 @@ struct swb200_ctx {
   uint32_t max_len = 0, min_len = 0;
   uint32_t minmax[2] = {0, 0};
   uint32_t unsorted = 0;
+  bool db_pending = false;           // rows uploaded by load_db_shard, exchange + db_commit still due
   bool sorted_desc = false;          // abundances never increase with the id (the reference's order, src/db.cc:392-406)
-  int cluster_kernel = 0; // 0 fused key relaxation as one persistent cooperative kernel, 2 the same host-looped, 1 = label propagation + BFS
+  int cluster_kernel = 0; // 0 fused key relaxation of the frontier, one persistent cooperative kernel; 3 the same over links first sorted by
+                          // source (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
+                          // 1 label propagation + BFS
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
@@ -232,6 +246,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release(); c->cl_bits.release();
+  c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->dist_lcnt.release(); c->dist_links.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release();
@@ -254,18 +269,15 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
-  else if (k == "cluster_kernel" && v >= 0 && v <= 2) c->cluster_kernel = static_cast<int>(v);
+  else if (k == "cluster_kernel" && v >= 0 && v <= 3) c->cluster_kernel = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
   return SWB200_OK;
 }
 
-int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
-                   const uint64_t *abundance, uint32_t n) {
-  API_BEGIN(c)
-  if (!words || !len || !abundance || n == 0 || stride_words == 0) { g_err = "load_db: bad argument"; return SWB200_EINVAL; }
-  if (n >= 0xFFFFFFF0u) { g_err = "load_db: too many amplicons"; return SWB200_EINVAL; }
+// device buffers for a database of n amplicons with `stride_words` words per row
+static void db_alloc(swb200_ctx *c, uint32_t n, uint32_t stride_words) {
   c->indexed = c->have_network = c->clustered = false;
   // seeds per TMA batch: even, <= kMaxBatch, batch*stride*8 bytes <= 2 KB per buffer
   uint32_t batch = 256 / stride_words;
@@ -274,47 +286,17 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   c->n = n;
   c->stride = stride_words;
   c->n_padded = (n + batch - 1) / batch * batch;
-  const size_t wbytes = static_cast<size_t>(n) * stride_words * 8;
-  c->words.alloc(static_cast<size_t>(c->n_padded) * stride_words);
-  c->len.alloc(n);
-  c->abundance.alloc(n);
-  c->tic();
-  // pinned staging in chunks so the H2D copies run at full PCIe rate for pageable callers
-  const size_t chunk = 64u << 20;
-  char *stage = static_cast<char *>(c->staging(2 * chunk));
-  auto upload = [&](void *dst, const void *src, size_t bytes) {
-    size_t off = 0;
-    int which = 0;
-    cudaEvent_t done[2];
-    CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
-    bool used[2] = {false, false};
-    while (off < bytes) {
-      const size_t nb = std::min(chunk, bytes - off);
-      if (used[which]) CK(cudaEventSynchronize(done[which]));
-      std::memcpy(stage + which * chunk, static_cast<const char *>(src) + off, nb);
-      CK(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage + which * chunk, nb, cudaMemcpyHostToDevice, c->stream));
-      CK(cudaEventRecord(done[which], c->stream));
-      used[which] = true;
-      which ^= 1;
-      off += nb;
-    }
-    CK(cudaStreamSynchronize(c->stream));
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
-  };
-  cudaPointerAttributes attr{};
-  const bool is_pinned = cudaPointerGetAttributes(&attr, words) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  if (is_pinned) {
-    CK(cudaMemcpyAsync(c->words.p, words, wbytes, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->len.p, len, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->abundance.p, abundance, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    upload(c->words.p, words, wbytes);
-    upload(c->len.p, len, static_cast<size_t>(n) * 4);
-    upload(c->abundance.p, abundance, static_cast<size_t>(n) * 8);
-  }
+  // room for an in-place all-gather of equal shards of ceil(n / world) rows (swb200_load_db_shard)
+  const size_t shard = (static_cast<size_t>(n) + c->shard_world - 1) / c->shard_world;
+  const size_t rows = std::max<size_t>(c->n_padded, shard * c->shard_world);
+  c->words.alloc(rows * stride_words);
+  c->len.alloc(rows);
+  c->abundance.alloc(rows);
+}
+
+// after the rows are on the device: padding, length range, order check, Zobrist table
+static int db_finalize(swb200_ctx *c) {
+  const uint32_t n = c->n, stride_words = c->stride;
   if (c->n_padded > n)
     CK(cudaMemsetAsync(c->words.p + static_cast<size_t>(n) * stride_words, 0,
                        static_cast<size_t>(c->n_padded - n) * stride_words * 8, c->stream));
@@ -336,15 +318,112 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
     CK(cudaMemcpyAsync(&c->unsorted, c->counters.p + 20, 4, cudaMemcpyDeviceToHost, c->stream));
     c->launches += 2;
   }
-  c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
-  uint64_t sm = 0x5eedb200c0ffeeULL;
-  for (auto &z : c->h_ztab) z = splitmix64(sm);
-  c->ztab.alloc(c->h_ztab.size());
-  CK(cudaMemcpyAsync(c->ztab.p, c->h_ztab.data(), c->h_ztab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  if (c->h_ztab.size() != static_cast<size_t>(c->zlen) * 4) {
+    c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
+    uint64_t sm = 0x5eedb200c0ffeeULL;
+    for (auto &z : c->h_ztab) z = splitmix64(sm);
+    c->ztab.alloc(c->h_ztab.size());
+    CK(cudaMemcpyAsync(c->ztab.p, c->h_ztab.data(), c->h_ztab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  }
   c->toc(0);
   c->max_len = c->minmax[0];
   c->min_len = ~c->minmax[1];
   c->sorted_desc = c->unsorted == 0;
+  return SWB200_OK;
+}
+
+// host -> device copy of `bytes`; pinned sources go straight to the copy engine, pageable ones through a pinned
+// double buffer in 64 MiB chunks so the copies still run at the full PCIe rate
+static void db_upload(swb200_ctx *c, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return;
+  cudaPointerAttributes attr{};
+  const bool is_pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (is_pinned) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return;
+  }
+  const size_t chunk = 64u << 20;
+  char *stage = static_cast<char *>(c->staging(2 * chunk));
+  size_t off = 0;
+  int which = 0;
+  cudaEvent_t done[2];
+  CK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+  bool used[2] = {false, false};
+  while (off < bytes) {
+    const size_t nb = std::min(chunk, bytes - off);
+    if (used[which]) CK(cudaEventSynchronize(done[which]));
+    std::memcpy(stage + which * chunk, static_cast<const char *>(src) + off, nb);
+    CK(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage + which * chunk, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(done[which], c->stream));
+    used[which] = true;
+    which ^= 1;
+    off += nb;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaEventDestroy(done[0]);
+  cudaEventDestroy(done[1]);
+}
+
+int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
+                   const uint64_t *abundance, uint32_t n) {
+  API_BEGIN(c)
+  if (!words || !len || !abundance || n == 0 || stride_words == 0) { g_err = "load_db: bad argument"; return SWB200_EINVAL; }
+  if (n >= 0xFFFFFFF0u) { g_err = "load_db: too many amplicons"; return SWB200_EINVAL; }
+  db_alloc(c, n, stride_words);
+  c->tic();
+  db_upload(c, c->words.p, words, static_cast<size_t>(n) * stride_words * 8);
+  db_upload(c, c->len.p, len, static_cast<size_t>(n) * 4);
+  db_upload(c, c->abundance.p, abundance, static_cast<size_t>(n) * 8);
+  return db_finalize(c);
+  API_END()
+}
+
+int swb200_load_db_shard(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
+                         const uint64_t *abundance, uint32_t n_total, uint32_t first, uint32_t count) {
+  API_BEGIN(c)
+  if (n_total == 0 || stride_words == 0 || static_cast<uint64_t>(first) + count > n_total || (count && (!words || !len || !abundance))) {
+    g_err = "load_db_shard: bad argument";
+    return SWB200_EINVAL;
+  }
+  if (n_total >= 0xFFFFFFF0u) { g_err = "load_db_shard: too many amplicons"; return SWB200_EINVAL; }
+  db_alloc(c, n_total, stride_words);
+  c->tic();
+  db_upload(c, c->words.p + static_cast<size_t>(first) * stride_words, words, static_cast<size_t>(count) * stride_words * 8);
+  db_upload(c, c->len.p + first, len, static_cast<size_t>(count) * 4);
+  db_upload(c, c->abundance.p + first, abundance, static_cast<size_t>(count) * 8);
+  c->db_pending = true;
+  API_END()
+}
+
+int swb200_load_db_device(swb200_ctx *c, const void *d_words, uint32_t stride_words, const void *d_len, const void *d_abundance,
+                          uint32_t n) {
+  API_BEGIN(c)
+  if (!d_words || !d_len || !d_abundance || n == 0 || stride_words == 0 || n >= 0xFFFFFFF0u) { g_err = "load_db_device: bad argument"; return SWB200_EINVAL; }
+  db_alloc(c, n, stride_words);
+  c->tic();
+  CK(cudaMemcpyAsync(c->words.p, d_words, static_cast<size_t>(n) * stride_words * 8, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->len.p, d_len, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->abundance.p, d_abundance, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  return db_finalize(c);
+  API_END()
+}
+
+int swb200_db_device(swb200_ctx *c, void **d_words, void **d_len, void **d_abundance) {
+  if (!c || c->n == 0) { g_err = "db_device: no database"; return SWB200_EINVAL; }
+  if (d_words) *d_words = c->words.p;
+  if (d_len) *d_len = c->len.p;
+  if (d_abundance) *d_abundance = c->abundance.p;
+  return SWB200_OK;
+}
+
+int swb200_db_commit(swb200_ctx *c) {
+  API_BEGIN(c)
+  if (c->n == 0) { g_err = "db_commit: no database"; return SWB200_EINVAL; }
+  c->db_pending = false;
+  c->tic();
+  return db_finalize(c);
   API_END()
 }
 
@@ -367,6 +446,7 @@ static TileJoinParams tile_params(swb200_ctx *c) {
 int swb200_d1_index(swb200_ctx *c) {
   API_BEGIN(c)
   if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
+  if (c->db_pending) { g_err = "d1_index: swb200_load_db_shard must be followed by the row exchange and swb200_db_commit"; return SWB200_EINVAL; }
   c->join_active = c->tile_active = false;
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
   if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8 && c->join_kernel != 1 && c->stride <= 32 && c->max_len < 8192) {
@@ -543,12 +623,13 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
       CK(cudaGetLastError());
     } else
     run_network(c);
-    unsigned long long host[5];
+    unsigned long long host[6];
     CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_edges = host[0];
     for (int i = 0; i < 4; ++i) c->stats[i] = host[1 + i];
     c->stats[4] = c->n_edges;
+    c->stats[6] = host[5];
     if (c->tile_active && c->collect_stats) c->stats[0] = c->tj_total;     // entries of this rank's tiles (2 per amplicon over all ranks)
     if (c->join_active) {
       uint32_t dup = 0;
@@ -596,12 +677,10 @@ int swb200_d1_import_links_device(swb200_ctx *c, const void *d_pairs, uint64_t n
   API_BEGIN(c)
   if (!c->indexed || (!d_pairs && n_links)) { g_err = "import_links_device: bad state"; return SWB200_EINVAL; }
   if (d_pairs != c->edges.p) {
-    DevBuf<uint2> fresh;
-    fresh.alloc(std::max<uint64_t>(n_links, 1));
-    CK(cudaMemcpyAsync(fresh.p, d_pairs, n_links * 8, cudaMemcpyDeviceToDevice, c->stream));
+    // the gathered list replaces the local one; the buffer only ever grows (no cudaMalloc/cudaFree per step)
+    if (c->edges.n < n_links) c->edges.alloc(n_links + n_links / 8);
+    CK(cudaMemcpyAsync(c->edges.p, d_pairs, n_links * 8, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->edges.release();
-    c->edges = fresh;
   }
   c->n_edges = n_links;
   c->have_network = true;
@@ -635,8 +714,43 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
-  if (c->cluster_kernel == 0) {
-    // fused label+generation relaxation as one persistent cooperative kernel (d1_kernels.cuh: k_cluster_persistent)
+  if (c->cluster_kernel == 3 && m < 0xFFFFFFF0ull) {
+    // links counting-sorted by source + frontier relaxation, one persistent cooperative kernel (d1_cluster.cuh)
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_csr, 256, 0));
+    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+    ClusterParams C{};
+    C.edges = c->edges.p; C.m = m; C.n = n;
+    C.key = c->key.p; C.parent = c->parent.p; C.label = c->label.p; C.generation = c->generation.p;
+    C.nwords = (n + 31) / 32;
+    c->cl_bits.alloc(static_cast<size_t>(C.nwords) * 3);
+    c->cl_deg.alloc(n); c->cl_row.alloc(static_cast<size_t>(n) + 1);
+    c->cl_srcs.alloc(std::max<uint64_t>(m, 1)); c->cl_dsts.alloc(std::max<uint64_t>(m, 1));
+    c->cl_tot.alloc(grid);
+    C.bits = c->cl_bits.p; C.deg = c->cl_deg.p; C.row = c->cl_row.p; C.srcs = c->cl_srcs.p; C.dsts = c->cl_dsts.p;
+    C.cta_tot = c->cl_tot.p;
+    C.flags = reinterpret_cast<uint32_t *>(c->counters.p + 17); C.rounds_out = reinterpret_cast<uint32_t *>(c->counters.p + 19);
+    if (std::getenv("SWB200_CLUSTER_TS")) {                    // profiling aid: phase timestamps of the persistent kernel on stderr
+      c->cl_ts.alloc(64);
+      CK(cudaMemsetAsync(c->cl_ts.p, 0, 64 * 8, c->stream));
+      C.ts = c->cl_ts.p;
+    }
+    void *args[] = {&C};
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_csr), dim3(grid), dim3(256), args, 0, c->stream));
+    c->launches++;
+    if (C.ts) {
+      unsigned long long h[64];
+      CK(cudaMemcpyAsync(h, c->cl_ts.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      std::fprintf(stderr, "[cluster_csr n=%u m=%llu] us:", n, static_cast<unsigned long long>(m));
+      for (int i = 1; i < 64 && h[i]; ++i) std::fprintf(stderr, " %.1f", (h[i] - h[i - 1]) * 1e-3);
+      std::fprintf(stderr, "\n");
+    }
+    return;
+  }
+  if (c->cluster_kernel == 0 || c->cluster_kernel == 3) {
+    // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_persistent, 256, 0));
     const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
@@ -709,6 +823,141 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (parent) CK(cudaMemcpyAsync(parent, c->parent.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+int swb200_d1_get_cluster(swb200_ctx *c, uint32_t first, uint32_t count, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
+  API_BEGIN(c)
+  if (!c->clustered || static_cast<uint64_t>(first) + count > c->n) { g_err = "get_cluster: no clustering / bad range"; return SWB200_EINVAL; }
+  if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p + first, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (generation) CK(cudaMemcpyAsync(generation, c->generation.p + first, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (parent) CK(cudaMemcpyAsync(parent, c->parent.p + first, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+uint64_t swb200_dist_buffer_bytes(uint32_t n_total, uint32_t world, uint32_t items_per_amplicon) {
+  if (world == 0) return 0;
+  const uint64_t S = (static_cast<uint64_t>(n_total) + world - 1) / world;
+  // one sub-region per sender in both inboxes: links (8 B) and the message log of 16-byte records, which is sized
+  // for kDistLogFactor records per link slot (a link is re-offered every time its source is lowered: ~2.6x measured)
+  const uint64_t per_sender = std::max<uint64_t>(S * std::max<uint32_t>(items_per_amplicon, 1) / world, 1u << 14);
+  return kDistCtlBytes + per_sender * world * (sizeof(uint2) + kDistLogFactor * sizeof(DistRec));
+}
+
+// rows of the result this rank owns: block-cyclic, blocks of kDistBlock ids
+static uint32_t dist_own_rows(uint32_t n, uint32_t rank, uint32_t world) {
+  const uint64_t nblocks = (static_cast<uint64_t>(n) + kDistBlock - 1) / kDistBlock;
+  uint64_t rows = 0;
+  for (uint64_t b = rank; b < nblocks; b += world) rows += std::min<uint64_t>(kDistBlock, n - b * kDistBlock);
+  return static_cast<uint32_t>(rows);
+}
+
+uint32_t swb200_dist_row_count(uint32_t n_total, uint32_t rank, uint32_t world) {
+  return (world == 0 || rank >= world) ? 0 : dist_own_rows(n_total, rank, world);
+}
+
+uint32_t swb200_dist_row_id(uint32_t rank, uint32_t world, uint32_t row) {
+  return ((row / kDistBlock) * world + rank) * kDistBlock + (row % kDistBlock);
+}
+
+int swb200_dist_setup(swb200_ctx *c, uint32_t rank, uint32_t world, void *const *peer_buffers, uint64_t buffer_bytes) {
+  API_BEGIN(c)
+  if (world == 0 || world > kDistMaxWorld || rank >= world || !peer_buffers ||
+      buffer_bytes < kDistCtlBytes + static_cast<uint64_t>(world) * 64 * (sizeof(uint2) + kDistLogFactor * sizeof(DistRec))) {
+    g_err = "dist_setup: bad argument (1 <= world <= 16, one peer-visible buffer per rank)";
+    return SWB200_EINVAL;
+  }
+  for (uint32_t r = 0; r < world; ++r) {
+    if (!peer_buffers[r]) { g_err = "dist_setup: null peer buffer"; return SWB200_EINVAL; }
+    c->dist_peer[r] = static_cast<unsigned char *>(peer_buffers[r]);
+  }
+  c->dist_rank = rank;
+  c->dist_world = world;
+  c->dist_cap = (buffer_bytes - kDistCtlBytes) / (static_cast<uint64_t>(world) * (sizeof(uint2) + kDistLogFactor * sizeof(DistRec)));
+  c->dist_calls = 0;
+  c->dist_lcnt.alloc(2 * kDistMaxWorld);
+  c->dist_links.alloc(c->dist_cap * world);
+  CK(cudaMemsetAsync(c->dist_lcnt.p, 0, 2 * kDistMaxWorld * 8, c->stream));
+  CK(cudaMemsetAsync(c->dist_peer[rank], 0, kDistCtlBytes, c->stream));      // my own control block; the caller barriers before the first use
+  CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
+  API_BEGIN(c)
+  if (!c->have_network) { g_err = "d1_cluster_dist: call swb200_d1_network first"; return SWB200_EINVAL; }
+  if (c->dist_world == 0) { g_err = "d1_cluster_dist: call swb200_dist_setup first"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  DistParams D{};
+  D.rank = c->dist_rank; D.world = c->dist_world; D.n = n;
+  const uint64_t nblocks = (static_cast<uint64_t>(n) + kDistBlock - 1) / kDistBlock;
+  D.n_local = static_cast<uint32_t>((nblocks + D.world - 1) / D.world * kDistBlock);
+  D.edges = c->edges.p; D.m_local = c->n_edges;
+  c->key.alloc(std::max<uint32_t>(D.n_local, 1)); c->label.alloc(n); c->generation.alloc(n); c->parent.alloc(n);
+  D.nwords = (D.n_local + 31) / 32;
+  c->cl_bits.alloc(static_cast<size_t>(D.nwords) * 3);
+  D.key = c->key.p; D.parent = c->parent.p; D.label = c->label.p; D.generation = c->generation.p; D.bits = c->cl_bits.p;
+  D.my_links = c->dist_links.p; D.lcnt = c->dist_lcnt.p;
+  for (uint32_t r = 0; r < D.world; ++r) D.peer[r] = c->dist_peer[r];
+  D.cap_links = c->dist_cap;
+  D.cap_upd = c->dist_cap * kDistLogFactor;
+  D.epoch_base = (++c->dist_calls) << 24;
+  D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
+  if (const char *dbg = std::getenv("SWB200_DIST_DBG")) D.dbg = static_cast<uint32_t>(std::atoi(dbg));
+  if (std::getenv("SWB200_CLUSTER_TS")) {
+    c->cl_ts.alloc(128);
+    CK(cudaMemsetAsync(c->cl_ts.p, 0, 128 * 8, c->stream));
+    D.ts = c->cl_ts.p;
+  }
+  const size_t dyn = static_cast<size_t>(kDistChunk) * sizeof(DistRec);
+  CK(cudaFuncSetAttribute(k_cluster_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  int occ = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_dist, 256, dyn));
+  const unsigned grid = static_cast<unsigned>(c->sm_count * std::max(occ, 1));
+  c->tic();
+  void *args[] = {&D};
+  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_dist), dim3(grid), dim3(256), args, dyn, c->stream));
+  c->launches++;
+  uint32_t h[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t overflow = 0;
+  CK(cudaMemcpyAsync(h, D.lflags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&overflow, c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 4, cudaMemcpyDeviceToHost, c->stream));
+  c->toc(3);
+  c->dist_rounds = h[4];
+  if (D.ts) {
+    unsigned long long t[128];
+    CK(cudaMemcpy(t, c->cl_ts.p, sizeof t, cudaMemcpyDeviceToHost));
+    std::string line = "[cluster_dist rank " + std::to_string(D.rank) + " rounds " + std::to_string(h[4]) +
+                       "] us (route, barrier, compact, then relax/barrier/apply per round, tail):";
+    for (int i = 1; i < 128 && t[i]; ++i) line += " " + std::to_string(static_cast<long long>((t[i] - t[i - 1]) / 1000));
+    std::fprintf(stderr, "%s\n", line.c_str());
+  }
+  if (h[3]) { g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s"; return SWB200_ECUDA; }
+  if (overflow) {
+    CK(cudaMemsetAsync(c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 0, 4, c->stream));
+    CK(cudaMemsetAsync(c->dist_lcnt.p, 0, 2 * kDistMaxWorld * 8, c->stream));
+    g_err = "d1_cluster_dist: an inbox overflowed; set up larger peer buffers (swb200_dist_buffer_bytes with more items per amplicon)";
+    return SWB200_ENOMEM;
+  }
+  c->clustered = true;
+  // this rank's rows: block-cyclic (blocks of kDistBlock ids), packed in ascending id order
+  const uint32_t rows = dist_own_rows(n, D.rank, D.world);
+  const uint64_t full_blocks = rows / kDistBlock;
+  auto fetch = [&](uint32_t *dst, const uint32_t *src) {
+    if (!dst || rows == 0) return;
+    if (full_blocks)
+      CK(cudaMemcpy2DAsync(dst, kDistBlock * 4, src + static_cast<size_t>(D.rank) * kDistBlock, static_cast<size_t>(D.world) * kDistBlock * 4,
+                           kDistBlock * 4, full_blocks, cudaMemcpyDeviceToHost, c->stream));
+    const uint32_t tail = rows - static_cast<uint32_t>(full_blocks * kDistBlock);
+    if (tail)
+      CK(cudaMemcpyAsync(dst + full_blocks * kDistBlock, src + (full_blocks * D.world + D.rank) * kDistBlock, static_cast<size_t>(tail) * 4,
+                         cudaMemcpyDeviceToHost, c->stream));
+  };
+  fetch(swarm_of, c->label.p);
+  fetch(generation, c->generation.p);
+  fetch(parent, c->parent.p);
   CK(cudaStreamSynchronize(c->stream));
   API_END()
 }
@@ -942,6 +1191,12 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
     CK(cudaStreamSynchronize(c->stream));
   }
   API_END()
+}
+
+int swb200_stream(swb200_ctx *c, void **stream) {
+  if (!c || !stream) { g_err = "null argument"; return SWB200_EINVAL; }
+  *stream = reinterpret_cast<void *>(c->stream);
+  return SWB200_OK;
 }
 
 double swb200_last_device_seconds(swb200_ctx *c) { return c ? c->last_s : 0.0; }

@@ -51,6 +51,19 @@ def engine_lib():
         L.swb200_destroy.restype = None
         L.swb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.swb200_load_db.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32]
+        L.swb200_load_db_shard.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.swb200_db_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.swb200_db_commit.argtypes = [vp]
+        L.swb200_load_db_device.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_uint32]
+        L.swb200_d1_get_cluster.argtypes = [vp, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p]
+        L.swb200_dist_buffer_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.swb200_dist_buffer_bytes.restype = C.c_uint64
+        L.swb200_dist_row_count.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.swb200_dist_row_count.restype = C.c_uint32
+        L.swb200_dist_row_id.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.swb200_dist_row_id.restype = C.c_uint32
+        L.swb200_dist_setup.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint64]
+        L.swb200_d1_cluster_dist.argtypes = [vp, _u32p, _u32p, _u32p]
         L.swb200_d1_index.argtypes = [vp]
         L.swb200_d1_network.argtypes = [vp, C.c_int, _u64p]
         L.swb200_d1_get_network.argtypes = [vp, _u64p, _u32p]
@@ -61,6 +74,7 @@ def engine_lib():
         L.swb200_d1_cluster.argtypes = [vp, _u32p, _u32p, _u32p]
         L.swb200_d1_fastidious.argtypes = [vp, C.c_uint64, _u32p, _u64p, _u64p]
         L.swb200_dn_cluster.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(C.c_int64), _u32p, _u32p, _u32p, _u32p]
+        L.swb200_stream.argtypes = [vp, C.POINTER(vp)]
         L.swb200_last_device_seconds.argtypes = [vp]
         L.swb200_last_device_seconds.restype = C.c_double
         L.swb200_phase_device_seconds.argtypes = [vp, C.c_int]
@@ -250,6 +264,20 @@ class DnResult(D1Result):
         return self._text(host_lib().swbh_dn_write_structure, self.db._h, self._h, self.db.opts[0])
 
 
+def dist_buffer_bytes(n_total: int, world: int, items_per_amplicon: int = 4) -> int:
+    return int(engine_lib().swb200_dist_buffer_bytes(int(n_total), int(world), int(items_per_amplicon)))
+
+
+def dist_row_ids(n_total: int, rank: int, world: int) -> np.ndarray:
+    """amplicon ids of the rows swb200_d1_cluster_dist returns on `rank` (block-cyclic, blocks of 4096 ids)"""
+    L = engine_lib()
+    rows = int(L.swb200_dist_row_count(int(n_total), int(rank), int(world)))
+    blk = 4096
+    assert int(L.swb200_dist_row_id(1, 3, blk + 5)) == (1 * 3 + 1) * blk + 5      # the engine's block size
+    i = np.arange(rows, dtype=np.int64)
+    return (((i // blk) * world + rank) * blk + (i % blk)).astype(np.uint32)
+
+
 def scoring(match=5, mismatch=4, gap_open=12, gap_extend=4):
     out = (C.c_int64 * 3)()
     host_lib().swbh_scoring(match, mismatch, gap_open, gap_extend, out)
@@ -300,6 +328,43 @@ class Engine:
         self._ck(engine_lib().swb200_load_db(self._h, _ptr(words, _u64p), int(stride), _ptr(lengths, _u32p),
                                             _ptr(abundance, _u64p), n))
         self.n = n
+
+    def load_db_shard(self, words, stride, lengths, abundance, n_total, first):
+        """this rank's rows [first, first+len(lengths)) of a database of n_total amplicons; then exchange + db_commit"""
+        count = lengths.shape[0]
+        assert words.shape[0] == count * stride and abundance.shape[0] == count
+        self._ck(engine_lib().swb200_load_db_shard(self._h, _ptr(words, _u64p), int(stride), _ptr(lengths, _u32p),
+                                                  _ptr(abundance, _u64p), int(n_total), int(first), int(count)))
+        self.n = int(n_total)
+
+    def db_device(self):
+        w, l, a = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(engine_lib().swb200_db_device(self._h, C.byref(w), C.byref(l), C.byref(a)))
+        return w.value, l.value, a.value
+
+    def db_commit(self):
+        self._ck(engine_lib().swb200_db_commit(self._h))
+
+    def load_db_device(self, d_words: int, stride: int, d_len: int, d_abundance: int, n: int):
+        self._ck(engine_lib().swb200_load_db_device(self._h, C.c_void_p(d_words), int(stride), C.c_void_p(d_len),
+                                                   C.c_void_p(d_abundance), int(n)))
+        self.n = int(n)
+
+    def d1_get_cluster(self, first, count, out):
+        self._ck(engine_lib().swb200_d1_get_cluster(self._h, int(first), int(count), _ptr(out["swarm_of"], _u32p),
+                                                   _ptr(out["generation"], _u32p), _ptr(out["parent"], _u32p)))
+        return out["swarm_of"], out["generation"], out["parent"]
+
+    def dist_setup(self, rank: int, world: int, peer_ptrs, nbytes: int):
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        self._ck(engine_lib().swb200_dist_setup(self._h, int(rank), int(world), arr, int(nbytes)))
+
+    def d1_cluster_dist(self, out=None):
+        """multi-GPU clustering (every rank calls it); out: dict of caller-owned uint32 arrays for this rank's rows"""
+        o = out or {}
+        self._ck(engine_lib().swb200_d1_cluster_dist(self._h, _ptr(o.get("swarm_of"), _u32p), _ptr(o.get("generation"), _u32p),
+                                                    _ptr(o.get("parent"), _u32p)))
+        return o.get("swarm_of"), o.get("generation"), o.get("parent")
 
     def load(self, db: HostDb):
         self.load_db(db.words, db.stride, db.len, db.abundance)
@@ -360,6 +425,12 @@ class Engine:
                                                *[_ptr(a, _u32p) for a in outs]))
         return tuple(outs)
 
+    def stream(self) -> int:
+        """cudaStream_t of the engine (wrap with torch.cuda.ExternalStream to record events / order collectives)"""
+        p = C.c_void_p()
+        self._ck(engine_lib().swb200_stream(self._h, C.byref(p)))
+        return p.value or 0
+
     def last_device_seconds(self) -> float:
         return engine_lib().swb200_last_device_seconds(self._h)
 
@@ -370,7 +441,7 @@ class Engine:
         out = np.zeros(16, dtype=np.uint64)
         self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 16))
         return {"variants": int(out[0]), "filter_pass": int(out[1]), "slots_visited": int(out[2]),
-                "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5]),
+                "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5]), "rows_gathered": int(out[6]),
                 "fast_light_variants": int(out[8]), "fast_heavy_variants": int(out[9]),
                 "fast_tag_matches": int(out[10]), "fast_verified": int(out[11]),
                 "dn_qgram_comparisons": int(out[12]), "dn_alignments": int(out[13]), "dn_pruned": int(out[14]),

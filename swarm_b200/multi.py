@@ -46,15 +46,70 @@ class _DevView:
         self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
 
+def device_view(ptr: int, nbytes: int) -> torch.Tensor:
+    """int32 torch view of `nbytes` of device memory at `ptr` (no copy, no ownership)"""
+    return torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+
+
+def shard_rows(n_total: int, rank: int, world: int):
+    """(first, count) of the database rows rank `rank` uploads: equal shards of ceil(n/world), the last one short"""
+    per = (n_total + world - 1) // world
+    first = min(per * rank, n_total)
+    return first, min(per, n_total - first)
+
+
+def engine_stream(eng):
+    """the engine's CUDA stream as a torch stream: collectives issued under it are ordered after the engine's
+    kernels and before its next ones without a host synchronisation"""
+    return torch.cuda.ExternalStream(eng.stream())
+
+
+def all_gather_db(eng, n_total: int, stride: int, group=None):
+    """the one exchange of the upload path: every rank pushed its own rows over PCIe (swb200_load_db_shard); the
+    rows of the other ranks arrive device-to-device over NVLink (NCCL all-gather, in place on the engine's buffers)"""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        eng.db_commit()
+        return
+    per = (n_total + world - 1) // world
+    w_ptr, l_ptr, a_ptr = eng.db_device()
+    with torch.cuda.stream(engine_stream(eng)):
+        for ptr, row_bytes in ((w_ptr, stride * 8), (l_ptr, 4), (a_ptr, 8)):
+            whole = device_view(ptr, per * world * row_bytes)
+            each = per * row_bytes // 4
+            dist.all_gather_into_tensor(whole, whole[rank * each:(rank + 1) * each].clone(), group=group)
+    eng.db_commit()
+
+
 def exchange_engine_links(eng, group=None):
     """the one data-path collective: gather every rank's link list and hand the union back to the engine"""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     ptr, m = eng.d1_links_device()
-    if m:
-        local = torch.as_tensor(_DevView(ptr, m * 8), device="cuda").reshape(-1, 2)
-    else:
-        local = torch.zeros((0, 2), dtype=torch.int32, device="cuda")
-    merged = all_gather_links(local, group).contiguous()
+    with torch.cuda.stream(engine_stream(eng)):
+        if m:
+            local = device_view(ptr, m * 8).reshape(-1, 2)
+        else:
+            local = torch.zeros((0, 2), dtype=torch.int32, device="cuda")
+        merged = all_gather_links(local, group).contiguous()
+        eng.d1_import_links_device(merged.data_ptr(), merged.shape[0])      # stream-ordered D2D copy + sync inside
+
+
+def setup_dist_clustering(eng, n_total: int, items_per_amplicon: int = 4, group=None):
+    """peer-visible inboxes for swb200_d1_cluster_dist: one torch symmetric-memory buffer per rank (CUDA VMM / fabric
+    handles exchanged by torch), its peer addresses handed to the engine as plain pointers.  Collective."""
+    import torch.distributed._symmetric_memory as symm
+    from .ffi import dist_buffer_bytes
+    group = group or dist.group.WORLD
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = dist_buffer_bytes(n_total, world, items_per_amplicon)
+    buf = symm.empty((nbytes + 3) // 4, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+    hdl = symm.rendezvous(buf, group)
+    buf.zero_()
     torch.cuda.synchronize()
-    eng.d1_import_links_device(merged.data_ptr(), merged.shape[0])
+    eng.dist_setup(rank, world, [int(p) for p in hdl.buffer_ptrs], nbytes)
+    torch.cuda.synchronize()
+    dist.barrier(group)
+    eng._dist_keep = (buf, hdl)          # the engine only borrows the memory
+    return nbytes

@@ -1,5 +1,7 @@
 """GPU parity tests (-m gpu): the CUDA engine, called through the C ABI (include/swarm_b200.h),
 against the CPU oracle and the committed golden outputs of the reference binary.  Bit-exact."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -212,7 +214,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1, "cluster_kernel": 2}), (ENUM_HALF, {"net_kernel": 2}), (ENUM_JOIN, {})):
+    for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1, "cluster_kernel": 2}), (ENUM_HALF, {"net_kernel": 2, "cluster_kernel": 3}), (ENUM_JOIN, {})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
@@ -419,3 +421,40 @@ def test_mixed_lengths(built, tmp_path):
     eng.close()
     if g >= 0:
         assert np.array_equal(gc, orc.graft_raw)
+
+
+def test_dist_clustering_world1(built, tmp_path):
+    """swb200_d1_cluster_dist with a single rank (every link is local): same arrays as swb200_d1_cluster; twice, to
+    check that the inboxes and barrier epochs are reusable."""
+    import torch
+    from swarm_b200.ffi import dist_buffer_bytes
+    fa = helpers.make_fasta(tmp_path / "s.fa", 50000, 150, 17, 0)
+    db = HostDb(fa)
+    eng = Engine(0)
+    eng.load(db)
+    eng.d1_index()
+    eng.d1_network()
+    sw, gen, par = eng.d1_cluster()
+    nbytes = dist_buffer_bytes(db.n, 1)
+    buf = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device="cuda")
+    eng.dist_setup(0, 1, [buf.data_ptr()], nbytes)
+    for _ in range(2):
+        out = {k: np.empty(db.n, dtype=np.uint32) for k in ("swarm_of", "generation", "parent")}
+        eng.d1_cluster_dist(out)
+        assert np.array_equal(out["swarm_of"], sw) and np.array_equal(out["generation"], gen) and np.array_equal(out["parent"], par)
+    eng.close()
+
+
+def test_dist_clustering_world2(built, tmp_path):
+    """two ranks on two GPUs (torchrun): sharded upload, sharded join, peer-memory clustering == single-GPU rows"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fa = helpers.make_fasta(tmp_path / "s.fa", 300000, 150, 23, 0)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(Path(__file__).resolve().parent / "dist_worker.py"), str(fa)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("dist ok") == 2
