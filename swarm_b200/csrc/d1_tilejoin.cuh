@@ -52,6 +52,10 @@ struct TileJoinParams {
   uint64_t edge_cap;
   int ncb;
   uint32_t *dup_flag;
+  uint2 *plist_ent;                 // multi-GPU: (entry lo, entry hi) and ...
+  uint32_t *plist_tile;             // ... local tile of every piece this rank owns, appended by the counting pass
+  unsigned long long *plist_n;
+  uint64_t plist_cap;
   unsigned long long *stats;        // [0] entries joined [1] same-key pairs [2] pairs enumerated [3] exact comparisons [4] rows gathered
 };
 
@@ -101,6 +105,49 @@ __global__ void __launch_bounds__(256) k_tile_partition(TileJoinParams J) {
   }
 }
 
+// Multi-GPU flavour of the two passes: a rank owns 1/world of the tiles but has to hash ALL amplicons to find its
+// pieces, so the counting pass also appends the pieces it keeps to a list and the second pass scatters that list
+// instead of hashing everything again (index at 8 x 10 M: the part that does not scale).
+__global__ void __launch_bounds__(256) k_tile_partition_list(TileJoinParams J) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long e[2] = {0, 0};
+  uint32_t t[2] = {kNone, kNone};
+  if (a < J.n) {
+    const uint64_t *w = J.words + static_cast<uint64_t>(a) * J.stride;
+    const uint32_t L = J.len[a];
+    const uint64_t ab = J.abundance[a];
+#pragma unroll
+    for (uint32_t piece = 0; piece < 2; ++piece) {
+      const uint64_t h = piece_hash(w, J.stride, piece ? L - J.K : 0u, J.K, piece);
+      const uint32_t tile = static_cast<uint32_t>(__umul64hi(h, static_cast<uint64_t>(J.n_tiles)));
+      if (tile < J.t_lo || tile >= J.t_hi) continue;
+      t[piece] = tile - J.t_lo;
+      e[piece] = tj_pack(J, h, piece, L, ab, a);
+      atomicAdd(&J.tile_count[t[piece]], 1u);
+    }
+  }
+  const uint32_t b0 = __ballot_sync(kFull, t[0] != kNone), b1 = __ballot_sync(kFull, t[1] != kNone);
+  const uint32_t tot = __popc(b0) + __popc(b1);
+  if (tot == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(J.plist_n, static_cast<unsigned long long>(tot));
+  base = shfl_u64(base, 0);
+  const uint32_t lt = (1u << lane) - 1u;
+  const unsigned long long i0 = base + __popc(b0 & lt), i1 = base + __popc(b0) + __popc(b1 & lt);
+  if (t[0] != kNone && i0 < J.plist_cap) { J.plist_ent[i0] = make_uint2(static_cast<uint32_t>(e[0]), static_cast<uint32_t>(e[0] >> 32)); J.plist_tile[i0] = t[0]; }
+  if (t[1] != kNone && i1 < J.plist_cap) { J.plist_ent[i1] = make_uint2(static_cast<uint32_t>(e[1]), static_cast<uint32_t>(e[1] >> 32)); J.plist_tile[i1] = t[1]; }
+}
+
+__global__ void __launch_bounds__(256) k_tile_scatter_list(TileJoinParams J, uint64_t m) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t t = J.plist_tile[i];
+  const uint2 e = J.plist_ent[i];
+  const uint32_t pos = atomicAdd(&J.tile_cursor[t], 1u);
+  J.entries[J.tile_off[t] + pos] = (static_cast<unsigned long long>(e.y) << 32) | e.x;
+}
+
 // exclusive scan of the tile counts (one CTA) + the list of oversize tiles
 __global__ void __launch_bounds__(1024) k_tile_scan(TileJoinParams J) {
   __shared__ unsigned long long part[1024];
@@ -127,40 +174,67 @@ __global__ void __launch_bounds__(1024) k_tile_scan(TileJoinParams J) {
   if (threadIdx.x == 1023) J.tile_off[T] = part[1023];
 }
 
-// decide one same-key pair exactly and emit its links; rows are pointers to packed words (shared or global)
-template <bool STATS, typename Emit>
-__device__ __forceinline__ void tj_decide(const TileJoinParams &J, unsigned long long ei, unsigned long long ej,
-                                          const uint64_t *ri, const uint64_t *rj, uint64_t kmask0, uint64_t kmask1,
-                                          unsigned long long &st_x, Emit emit) {
-  if (tj_key(J, ei) & 1u) {                              // suffix tile: a pair that also shares the prefix belongs to the prefix tile
-    if (((ri[0] ^ rj[0]) & kmask0) == 0 && (J.K <= 32 || ((ri[1] ^ rj[1]) & kmask1) == 0)) return;
+// Exact test of one pair on packed words, WITHOUT data-dependent branches: 0 = identical, 1 = exactly one edit apart,
+// 2 = further.  Lengths differ by at most one.  x = the longer sequence, y the other, both zero padded:
+//   a_k = x_k ^ y_k                      -> Hamming distance (equal lengths) and P = first differing position
+//   b_k = (x shifted down one nt)_k ^ y_k -> Q = last position where x with one nucleotide removed EARLIER still differs
+// Equal lengths: one edit <=> Hamming distance 1.  Lengths Lx = Ly+1: deleting x[p] gives y <=> x[0,p) = y[0,p) and
+// x[p+1+i] = y[p+i] for all i, i.e. some p <= P has every dirty b position below it <=> Q < P (Q = -1: b is clean).
+// This is the lane-parallel check_variant (src/variants.cc:118-165); one uniform loop for substitutions and indels —
+// the earlier two-path version (early-exit Hamming / first-mismatch-then-shift) ran with 5-17 active lanes per warp.
+__device__ __forceinline__ int tj_classify(const uint64_t *ri, uint32_t Li, const uint64_t *rj, uint32_t Lj, uint32_t stride,
+                                           uint64_t kmask0, uint64_t kmask1, bool &pfx_eq) {
+  const bool swap = Li < Lj;
+  const uint64_t *x = swap ? rj : ri, *y = swap ? ri : rj;
+  // the loop only remembers the FIRST dirty word of a and the LAST dirty word of b (selects, no bit scans: the 64-bit
+  // ffs / clz per word of the first version cost ~70 instructions a word); the two bit positions are found once, after it
+  uint32_t ham = 0, ja = 0xFFFFFFFFu, jb = 0;
+  uint64_t aw = 0, bw = 0, xv = x[0], d0 = 0, d1 = 0;
+  for (uint32_t k = 0; k < stride; ++k) {
+    const uint64_t xn = (k + 1 < stride) ? x[k + 1] : 0ull;
+    const uint64_t yv = y[k];
+    const uint64_t a = xv ^ yv;
+    if (k == 0) d0 = a;
+    if (k == 1) d1 = a;
+    ham += __popcll((a | (a >> 1)) & 0x5555555555555555ull);
+    if (a != 0 && ja == 0xFFFFFFFFu) { ja = k; aw = a; }
+    const uint64_t b = ((xv >> 2) | (xn << 62)) ^ yv;
+    if (b != 0) { jb = k; bw = b; }
+    xv = xn;
   }
+  pfx_eq = (d0 & kmask0) == 0 && (d1 & kmask1) == 0;
+  if (Li == Lj) return ham > 1 ? 2 : static_cast<int>(ham);
+  if (bw == 0 || aw == 0) return 1;                       // b clean: drop x[0]; a clean: x = y + one trailing base
+  const uint32_t P = (ja << 5) + (static_cast<uint32_t>(__ffsll(static_cast<long long>((aw | (aw >> 1)) & 0x5555555555555555ull)) - 1) >> 1);
+  const uint32_t Q = (jb << 5) + (static_cast<uint32_t>(63 - __clzll(static_cast<long long>((bw | (bw >> 1)) & 0x5555555555555555ull))) >> 1);
+  return Q < P ? 1 : 2;
+}
+
+// decide one same-key pair and build its links (0, 1 or 2) in registers; rows are pointers to packed words
+// (shared or global memory)
+template <bool STATS>
+__device__ __forceinline__ uint32_t tj_pair(const TileJoinParams &J, unsigned long long ei, unsigned long long ej, const uint64_t *ri,
+                                            const uint64_t *rj, uint64_t kmask0, uint64_t kmask1, unsigned long long &st_x, uint2 &l0,
+                                            uint2 &l1) {
+  bool pfx_eq;
+  const int cls = tj_classify(ri, tj_len(J, ei), rj, tj_len(J, ej), J.stride, kmask0, kmask1, pfx_eq);
+  if ((tj_key(J, ei) & 1u) && pfx_eq) return 0;          // suffix tile: a pair that also shares the prefix belongs to the prefix tile
   if (STATS) st_x++;
-  const uint32_t Li = tj_len(J, ei), Lj = tj_len(J, ej);
-  int cls;
-  if (Li == Lj) {                                        // substitution: Hamming distance over all (zero padded) words, no early
-    uint32_t diff = 0;                                   // exit — every lane of the warp runs the same trip count
-    for (uint32_t k = 0; k < J.stride; ++k) {
-      const uint64_t d = ri[k] ^ rj[k];
-      diff += __popcll((d | (d >> 1)) & 0x5555555555555555ull);
-    }
-    cls = diff > 1 ? 2 : static_cast<int>(diff);
-  } else {
-    cls = edit_class(ri, Li, rj, Lj, J.stride);
-  }
   if (cls == 0) atomicExch(J.dup_flag, 1u);
-  if (cls != 1) return;
+  if (cls != 1) return 0;
   uint32_t a = tj_id(J, ei), v = tj_id(J, ej);
-  if (J.ncb) { emit(make_uint2(a, v)); emit(make_uint2(v, a)); return; }
+  if (J.ncb) { l0 = make_uint2(a, v); l1 = make_uint2(v, a); return 2; }
   if (J.sorted_desc) {                                   // ids ascend as abundances descend: min(a,v) -> max(a,v) always exists
     if (a > v) { const uint32_t t_ = a; a = v; v = t_; }
-    emit(make_uint2(a, v));
-    if (tj_abh(J, ei) == tj_abh(J, ej) && J.abundance[a] == J.abundance[v]) emit(make_uint2(v, a));
-    return;
+    l0 = make_uint2(a, v);
+    if (tj_abh(J, ei) == tj_abh(J, ej) && J.abundance[a] == J.abundance[v]) { l1 = make_uint2(v, a); return 2; }
+    return 1;
   }
   const uint64_t aa = J.abundance[a], av = J.abundance[v];
-  if (aa >= av) emit(make_uint2(a, v));
-  if (av >= aa) emit(make_uint2(v, a));
+  uint32_t nl = 0;
+  if (aa >= av) { l0 = make_uint2(a, v); nl = 1; }
+  if (av >= aa) { if (nl) l1 = make_uint2(v, a); else l0 = make_uint2(v, a); ++nl; }
+  return nl;
 }
 
 // exclusive scan of vals[0..N) in shared memory by 256 threads, PER consecutive items per thread (N <= 256*PER);
@@ -269,27 +343,43 @@ __global__ void __launch_bounds__(256) k_tile_join(TileJoinParams J) {
   const uint32_t K = J.K;
   const uint64_t kmask1 = K >= 64 ? ~0ull : (K > 32 ? (1ull << (2 * (K - 32))) - 1 : 0ull);
   const uint64_t kmask0 = K >= 32 ? ~0ull : (1ull << (2 * K)) - 1;
-  auto emit = [&](uint2 link) {
-    const uint32_t pos = atomicAdd(&out_n, 1u);
-    if (pos < kTjOutCap) out[pos] = link;
-    else {                                               // stage full: straight to the global list
-      const unsigned long long g = atomicAdd(J.edge_count, 1ull);
-      if (g < J.edge_cap) J.edges[g] = link;
+  const uint32_t lane = tid & 31u;
+  for (uint32_t p0 = 0; p0 < P; p0 += 256) {             // uniform trip count: the link staging below is warp-collective
+    const uint32_t p = p0 + tid;
+    uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
+    uint32_t nl = 0;
+    if (p < P) {
+      uint32_t lo = 0, hi = c;                           // last s with pref[s] <= p
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pref[mid] <= p) lo = mid; else hi = mid;
+      }
+      const uint32_t s = lo, q = s + 1 + (p - pref[s]);
+      const unsigned long long es = ent[s], eq = ent[q];
+      if (STATS) st_s++;
+      if (tj_compatible(J, es, eq)) {
+        if (STATS) st_p++;
+        nl = tj_pair<STATS>(J, es, eq, rows + static_cast<size_t>(s) * stride, rows + static_cast<size_t>(q) * stride, kmask0, kmask1, st_x, l0, l1);
+      }
     }
-  };
-  for (uint32_t p = tid; p < P; p += 256) {
-    uint32_t lo = 0, hi = c;                             // last s with pref[s] <= p
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (pref[mid] <= p) lo = mid; else hi = mid;
+    // links of the warp -> the tile's stage: one shared-memory atomic per warp and iteration
+    const uint32_t b1 = __ballot_sync(kFull, nl >= 1), b2 = __ballot_sync(kFull, nl >= 2);
+    const uint32_t tot = __popc(b1) + __popc(b2);
+    if (tot) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&out_n, tot);
+      base = __shfl_sync(kFull, base, 0);
+      const uint32_t lt = (1u << lane) - 1u;
+      const uint32_t i0 = base + __popc(b1 & lt), i1 = base + __popc(b1) + __popc(b2 & lt);
+      if (nl >= 1) {
+        if (i0 < kTjOutCap) out[i0] = l0;
+        else { const unsigned long long g = atomicAdd(J.edge_count, 1ull); if (g < J.edge_cap) J.edges[g] = l0; }   // stage full
+      }
+      if (nl >= 2) {
+        if (i1 < kTjOutCap) out[i1] = l1;
+        else { const unsigned long long g = atomicAdd(J.edge_count, 1ull); if (g < J.edge_cap) J.edges[g] = l1; }
+      }
     }
-    const uint32_t s = lo, q = s + 1 + (p - pref[s]);
-    const unsigned long long es = ent[s], eq = ent[q];
-    if (STATS) st_s++;
-    if (!tj_compatible(J, es, eq)) continue;
-    if (STATS) st_p++;
-    tj_decide<STATS>(J, es, eq, rows + static_cast<size_t>(s) * stride, rows + static_cast<size_t>(q) * stride, kmask0, kmask1, st_x,
-                     emit);
   }
   __syncthreads();
   const uint32_t m = min(out_n, kTjOutCap);
@@ -361,8 +451,7 @@ __global__ void __launch_bounds__(256) k_tile_join_big(TileJoinParams J) {
           uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
           if (hit) {
             if (STATS) st_p++;
-            auto emit = [&](uint2 link) { if (mine == 0) l0 = link; else l1 = link; ++mine; };
-            tj_decide<STATS>(J, e, f, ri, J.words + static_cast<uint64_t>(tj_id(J, f)) * J.stride, kmask0, kmask1, st_x, emit);
+            mine = tj_pair<STATS>(J, e, f, ri, J.words + static_cast<uint64_t>(tj_id(J, f)) * J.stride, kmask0, kmask1, st_x, l0, l1);
           }
           stage_push(S, scnt, mine, l0, l1, J.edges, J.edge_count, J.edge_cap, lane);
         }
