@@ -23,12 +23,12 @@ swarm_b200/libswarm_b200.so: $(ENGINE_SRC) $(ENGINE_DEP)
 	@grep -E "error|warning" swarm_b200/csrc/ptxas.log | grep -v "ptxas info" || true
 
 swarm_b200/libswarm_b200_host.so: $(HOST_SRC) $(HOST_DEP)
-	$(CXX) -O2 -g -std=c++17 -fPIC -shared -Wall -Wextra -Iinclude -o $@ $(HOST_SRC)
+	$(CXX) -O2 -g -std=c++17 -fPIC -shared -Wall -Wextra -pthread -Iinclude -o $@ $(HOST_SRC)
 
 # the drop-in command line: host layer compiled in, CUDA engine linked dynamically
 bin/swarm_b200: swarm_b200/host/main.cc $(HOST_SRC) $(HOST_DEP) swarm_b200/libswarm_b200.so
 	@mkdir -p bin
-	$(CXX) -O2 -g -std=c++17 -Wall -Wextra -Iinclude -o $@ swarm_b200/host/main.cc $(HOST_SRC) -Lswarm_b200 -lswarm_b200 -Wl,-rpath,'$$ORIGIN/../swarm_b200'
+	$(CXX) -O2 -g -std=c++17 -Wall -Wextra -pthread -Iinclude -o $@ swarm_b200/host/main.cc $(HOST_SRC) -Lswarm_b200 -lswarm_b200 -Wl,-rpath,'$$ORIGIN/../swarm_b200'
 
 tools/libgen_amplicons.so: tools/gen_amplicons.c
 	gcc -O2 -std=c11 -fPIC -shared -Wall -o $@ $< -lm

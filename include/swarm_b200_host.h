@@ -60,6 +60,11 @@ int  swbh_dn_assemble(const swbh_db *db, const uint32_t *swarm_of, const uint32_
                       const uint32_t *parent, const uint32_t *pdiff, swbh_result **out);
 int  swbh_dn_write_stats(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
 int  swbh_dn_write_structure(const swbh_db *db, const swbh_result *r, int usearch_abundance, char **out, uint64_t *out_len);
+/* -u, the UCLUST-like records (src/algod1.cc:851-934 at d=1, src/algo.cc:608-661 at d>1): C and S per swarm, one H per
+ * other member with the reference's scalar global alignment against the seed (src/nw.cc:40-252, CIGAR
+ * src/utils/cigar.cc:30-60).  penalties = swbh_scoring()'s output; `threads` workers align (output independent of it). */
+int  swbh_write_uclust(const swbh_db *db, const swbh_result *r, int64_t differences, const int64_t penalties[3],
+                       int usearch_abundance, int64_t append_abundance, int threads, char **out, uint64_t *out_len);
 /* alignment scoring conversion (src/swarm.cc:466-483): penalties[3] = mismatch, gap open, gap extend */
 void swbh_scoring(int64_t match_reward, int64_t mismatch_penalty, int64_t gap_open, int64_t gap_extend, int64_t penalties[3]);
 

@@ -127,6 +127,7 @@ def host_lib():
         L.swbh_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_seeds.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_write_uclust.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int64, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_network.argtypes = [vp, _u64p, _u32p, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
         L.swbh_dn_assemble.argtypes = [vp, _u32p, _u32p, _u32p, _u32p, C.POINTER(vp)]
         L.swbh_dn_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
@@ -227,6 +228,12 @@ class D1Result:
     def seeds_text(self) -> bytes:
         L = host_lib()
         return self._text(L.swbh_write_seeds, self.db._h, self._h, self.db.opts[0])
+
+    def uclust_text(self, differences=1, penalties=(18, 24, 13), threads=1) -> bytes:
+        """`-u` records; penalties = converted costs (mismatch, gap open, gap extension), defaults = swarm's defaults"""
+        L = host_lib()
+        pen = (C.c_int64 * 3)(*[int(x) for x in penalties])
+        return self._text(L.swbh_write_uclust, self.db._h, self._h, int(differences), pen, *self.db.opts, int(threads))
 
     def close(self):
         if getattr(self, "_h", None):

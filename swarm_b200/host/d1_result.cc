@@ -11,6 +11,7 @@
 //     clear graft_cand (:274-336, attach :214-241).
 #include "../../include/swarm_b200_host.h"
 #include "amplicon_db.h"
+#include "result.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -18,27 +19,6 @@
 #include <numeric>
 #include <string>
 #include <vector>
-
-struct swbh_db {
-  swb::AmpliconDb db;
-};
-
-struct swbh_result {
-  uint32_t n = 0;
-  std::vector<uint32_t> swarm_no;       // per amplicon: swarm number (by seed order)
-  std::vector<uint32_t> generation, parent, graft_cand, pdiff, radius;
-  std::vector<uint32_t> maxradius;       // per swarm (d>1)
-  // per swarm (before grafting numbering)
-  std::vector<uint32_t> seed, size, singletons, maxgen;
-  std::vector<uint64_t> mass, sumlen;
-  std::vector<uint8_t> attached;
-  std::vector<uint64_t> first;          // offset of the swarm's own members in `members`
-  std::vector<uint32_t> own_size;
-  std::vector<uint32_t> members;        // own members of every swarm, list order
-  std::vector<std::vector<uint32_t>> grafted;   // per heavy swarm: attached light swarm numbers, in attach order
-  uint64_t swarms_adjusted = 0, grafts = 0;
-  uint32_t largest = 0, maxgen_all = 0;
-};
 
 namespace {
 thread_local std::string g_err;
@@ -53,13 +33,9 @@ int give(const std::string &s, char **out, uint64_t *out_len) {
   return 0;
 }
 
-template <typename F>
-void for_each_member(const swbh_result &r, uint32_t sw, F &&f) {   // list order incl. grafted light swarms
-  for (uint64_t k = 0; k < r.own_size[sw]; ++k) f(r.members[r.first[sw] + k]);
-  for (uint32_t ls : r.grafted[sw])
-    for (uint64_t k = 0; k < r.own_size[ls]; ++k) f(r.members[r.first[ls] + k]);
-}
 }  // namespace
+
+namespace swb { int give_text(const std::string &s, char **out, uint64_t *out_len) { return give(s, out, out_len); } }
 
 extern "C" {
 
@@ -180,7 +156,7 @@ int swbh_write_swarms(const swbh_db *dbh, const swbh_result *r, int mothur, int6
   for (uint32_t sw = 0; sw < r->seed.size(); ++sw) {
     if (r->attached[sw]) continue;
     bool first = true;
-    for_each_member(*r, sw, [&](uint32_t a) {
+    swb::for_each_member(*r, sw, [&](uint32_t a) {
       if (mothur) s += first ? '\t' : ',';
       else if (!first) s += ' ';
       first = false;
@@ -214,7 +190,7 @@ int swbh_write_structure(const swbh_db *dbh, const swbh_result *r, int usearch, 
   for (uint32_t sw = 0; sw < r->seed.size(); ++sw) {
     if (r->attached[sw]) continue;
     const uint32_t seed = r->seed[sw];
-    for_each_member(*r, sw, [&](uint32_t a) {
+    swb::for_each_member(*r, sw, [&](uint32_t a) {
       if (a == seed) return;
       const uint32_t gp = r->graft_cand[a];
       if (gp != 0xFFFFFFFFu) {

@@ -206,16 +206,16 @@ int main(int argc, char **argv) {
     if (P.pen[0] > 255) fatal("Alignment scoring system yielded a mismatch penalty greater than 255, please use different parameter values.");
   }
   if (P.differences == 0) fatal("d = 0 (dereplication) is not provided by swarm_b200; use swarm -d 0 or vsearch --derep_fulllength.");
-  if (!P.uclust_file.empty()) fatal("the UCLUST writer (-u) is not provided by swarm_b200.");
 
   // open_files, src/utils/open_and_close_files.cc:35-93
   std::FILE *out = open_out(P.output_file);
   if (!out) fatal("Unable to open output file for writing.");
   std::FILE *logf = stderr;
   if (!P.log.empty()) { logf = open_out(P.log); if (!logf) fatal("Unable to open log file for writing."); }
-  std::FILE *seedsf = nullptr, *statsf = nullptr, *structf = nullptr, *netf = nullptr;
+  std::FILE *seedsf = nullptr, *statsf = nullptr, *structf = nullptr, *netf = nullptr, *uclustf = nullptr;
   if (!P.seeds.empty() && !(seedsf = open_out(P.seeds))) fatal("Unable to open seeds file for writing.");
   if (!P.statistics_file.empty() && !(statsf = open_out(P.statistics_file))) fatal("Unable to open statistics file for writing.");
+  if (!P.uclust_file.empty() && !(uclustf = open_out(P.uclust_file))) fatal("Unable to open uclust file for writing.");
   if (!P.internal_structure.empty() && !(structf = open_out(P.internal_structure))) fatal("Unable to open internal structure file for writing.");
   if (!P.network_file.empty() && !(netf = open_out(P.network_file))) fatal("Unable to open network file for writing.");
 
@@ -223,6 +223,7 @@ int main(int argc, char **argv) {
   std::fputs(kHeader, logf);
   std::fprintf(logf, "Database file:     %s\nOutput file:       %s\n", P.input.c_str(), P.output_file.c_str());
   if (!P.statistics_file.empty()) std::fprintf(logf, "Statistics file:   %s\n", P.statistics_file.c_str());
+  if (!P.uclust_file.empty()) std::fprintf(logf, "Uclust file:       %s\n", P.uclust_file.c_str());
   if (!P.internal_structure.empty()) std::fprintf(logf, "Int. struct. file  %s\n", P.internal_structure.c_str());
   if (!P.network_file.empty()) std::fprintf(logf, "Network file       %s\n", P.network_file.c_str());
   std::fprintf(logf, "Resolution (d):    %" PRId64 "\nThreads:           %" PRId64 "\n", P.differences, P.threads);
@@ -285,6 +286,11 @@ int main(int argc, char **argv) {
         fatal(swbh_last_error());
       write_all(structf, text, len);
     }
+    if (uclustf) {
+      if (swbh_write_uclust(db, res, P.differences, P.pen, P.usearch, P.append_abundance, static_cast<int>(P.threads), &text, &len) != 0)
+        fatal(swbh_last_error());
+      write_all(uclustf, text, len);
+    }
     if (statsf) {
       if ((P.differences == 1 ? swbh_write_stats(db, res, P.usearch, &text, &len) : swbh_dn_write_stats(db, res, P.usearch, &text, &len)) != 0)
         fatal(swbh_last_error());
@@ -296,7 +302,7 @@ int main(int argc, char **argv) {
     swbh_result_free(res);
   }
   swbh_db_free(db);
-  for (std::FILE *f : {netf, structf, statsf, seedsf, out}) if (f) std::fclose(f);
+  for (std::FILE *f : {netf, structf, uclustf, statsf, seedsf, out}) if (f) std::fclose(f);
   if (logf != stderr) std::fclose(logf);
   return EXIT_SUCCESS;
 }

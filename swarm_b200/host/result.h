@@ -1,0 +1,37 @@
+// swarm_b200/host/result.h — the host layer's internal view of a database handle and of an assembled
+// clustering result (shared by the writers in d1_result.cc, uclust.cc and derep.cc; not part of the C ABI).
+#pragma once
+#include "amplicon_db.h"
+
+#include <cstdint>
+#include <vector>
+
+struct swbh_db {
+  swb::AmpliconDb db;
+};
+
+struct swbh_result {
+  uint32_t n = 0;
+  std::vector<uint32_t> swarm_no;       // per amplicon: swarm number (by seed order)
+  std::vector<uint32_t> generation, parent, graft_cand, pdiff, radius;
+  std::vector<uint32_t> maxradius;       // per swarm (d>1)
+  // per swarm (before grafting numbering)
+  std::vector<uint32_t> seed, size, singletons, maxgen;
+  std::vector<uint64_t> mass, sumlen;
+  std::vector<uint8_t> attached;
+  std::vector<uint64_t> first;          // offset of the swarm's own members in `members`
+  std::vector<uint32_t> own_size;
+  std::vector<uint32_t> members;        // own members of every swarm, list order
+  std::vector<std::vector<uint32_t>> grafted;   // per heavy swarm: attached light swarm numbers, in attach order
+  uint64_t swarms_adjusted = 0, grafts = 0;
+  uint32_t largest = 0, maxgen_all = 0;
+};
+
+namespace swb {
+template <typename F>
+void for_each_member(const swbh_result &r, uint32_t sw, F &&f) {   // list order incl. grafted light swarms
+  for (uint64_t k = 0; k < r.own_size[sw]; ++k) f(r.members[r.first[sw] + k]);
+  for (uint32_t ls : r.grafted[sw])
+    for (uint64_t k = 0; k < r.own_size[ls]; ++k) f(r.members[r.first[ls] + k]);
+}
+}  // namespace swb

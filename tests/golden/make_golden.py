@@ -5,7 +5,7 @@
     python tests/golden/make_golden.py          # only possible where oracle/_ref/swarm exists
 
 Each case <name>.fasta gets: <name>.o (swarms), .s (stats), .i (structure), .j (network) at d=1;
-<name>.n.o with -n; <name>.f.o/.f.s/.f.i with --fastidious (-t 1: the reference's light pass has
+<name>.u (UCLUST-like records) for the cases of UCLUST below; <name>.n.o with -n; <name>.f.o/.f.s/.f.i with --fastidious (-t 1: the reference's light pass has
 unsynchronised inserts).  Inputs come from tools/gen_amplicons.c (seeded) or are
 hand-made below.  The fixtures are committed; this script is their provenance.
 """
@@ -63,9 +63,26 @@ CASES = [
 ]
 
 
+# -u (UCLUST-like records: alignments + CIGAR): name, flags, tag
+UCLUST = [("handmade", [], ""), ("c1_1k_150", [], ""), ("c1_1k_150", ["-f"], "f."), ("short_600_20", [], ""),
+          ("w65_300", [], ""), ("handmade", ["-d", "2"], "d2."), ("short_600_20", ["-d", "3"], "d3."),
+          ("tie_1500_60", ["-d", "2", "-n"], "d2n."), ("w32_400", ["-d", "2", "-m", "3", "-p", "2", "-g", "5", "-e", "3"], "d2pen."),
+          ("l400_250", ["-d", "2"], "d2."), ("usearch_300", ["-z"], "")]
+
+
+def make_uclust():
+    for name, flags, tag in UCLUST:
+        r = helpers.run_ref(HERE / f"{name}.fasta", *flags, outputs=("u",), threads=1)
+        assert r["rc"] == 0, r["stderr"]
+        (HERE / f"{name}.{tag}u").write_bytes(r["u"])
+    print("uclust ok")
+
+
 def main():
     if not helpers.have_ref():
         sys.exit("oracle/_ref/swarm missing: run `make -C oracle ref` where /root/reference exists")
+    if sys.argv[1:] == ["uclust"]:          # only (re)generate the -u fixtures; the inputs must exist
+        return make_uclust()
     (HERE / "handmade.fasta").write_bytes(HANDMADE)
     names = ["handmade"]
     for name, n, L, seed, mode, op in CASES:
@@ -117,6 +134,7 @@ def main():
     r = helpers.run_ref(HERE / "usearch_300.fasta", "-z", "-r", outputs=("o",))
     (HERE / "usearch_300.r.o").write_bytes(r["o"])
     print("usearch ok")
+    make_uclust()
 
 
 if __name__ == "__main__":

@@ -41,7 +41,6 @@ def test_help_and_version_exit_zero(built):
 
 def test_unsupported_modes_fail_loudly(built):
     assert subprocess.run([str(CLI), "-d", "0", FA], capture_output=True).returncode == 1
-    assert subprocess.run([str(CLI), "-u", "/dev/null", FA], capture_output=True).returncode == 1
 
 
 def _run(tmp, *flags, fasta=FA, outs=("o",)):
@@ -84,6 +83,16 @@ def test_cli_dn_usearch_mothur_stdin(built, tmp_path):
     # FASTA on stdin, swarms on stdout
     p = subprocess.run([str(CLI), "-l", os.devnull], input=(GOLDEN / "handmade.fasta").read_bytes(), capture_output=True)
     assert p.returncode == 0 and p.stdout == (GOLDEN / "handmade.o").read_bytes()
+
+
+@pytest.mark.gpu
+def test_cli_uclust(built, tmp_path):
+    for name, flags, tag in [("c1_1k_150", [], ""), ("c1_1k_150", ["-f"], "f."), ("short_600_20", ["-d", "3"], "d3."),
+                             ("tie_1500_60", ["-d", "2", "-n"], "d2n."), ("usearch_300", ["-z"], ""),
+                             ("w32_400", ["-d", "2", "-m", "3", "-p", "2", "-g", "5", "-e", "3"], "d2pen.")]:
+        r = _run(tmp_path, "-t", "4", *flags, fasta=str(GOLDEN / f"{name}.fasta"), outs=("u",))
+        assert r["u"] == (GOLDEN / f"{name}.{tag}u").read_bytes(), (name, tag)
+        assert b"Uclust file:" in r["log"]
 
 
 @pytest.mark.gpu

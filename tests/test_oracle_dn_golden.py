@@ -48,6 +48,9 @@ def test_dn_matches_reference(built, name, d, ncb, pen, tag):
     assert res.swarms_text() == (GOLDEN / f"{name}.{tag}.o").read_bytes()
     assert res.stats_text() == (GOLDEN / f"{name}.{tag}.s").read_bytes()
     assert res.structure_text() == (GOLDEN / f"{name}.{tag}.i").read_bytes()
+    u = GOLDEN / f"{name}.{tag}.u"
+    if u.exists():                                          # -u at d>1: hits in discovery order (src/algo.cc:608-661)
+        assert res.uclust_text(differences=d, penalties=p, threads=3) == u.read_bytes()
     # the oracle's own list order (rotations, src/algo.cc:205-256) is the (generation, id) order
     want = [l.split() for l in (GOLDEN / f"{name}.{tag}.o").read_text().splitlines()]
     flat = [h for l in want for h in l]

@@ -61,6 +61,57 @@ def test_swarms_stats_structure_match_reference(case):
     assert heads == want
 
 
+def test_uclust_records_match_reference(case):
+    """-u: C/S/H records with the scalar aligner's CIGAR (src/algod1.cc:851-934, src/nw.cc); the text must not depend
+    on the number of alignment workers"""
+    name, db, orc = case
+    f = GOLDEN / f"{name}.u"
+    if not f.exists():
+        pytest.skip("no -u fixture for this case")
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent)
+    assert res.uclust_text(threads=1) == f.read_bytes()
+    assert res.uclust_text(threads=5) == f.read_bytes()
+
+
+def test_uclust_with_grafts_and_usearch_headers(built):
+    db = HostDb(GOLDEN / "c1_1k_150.fasta")
+    orc = Oracle(db)
+    orc.network(); orc.cluster(); orc.fastidious(boundary=3)
+    res = D1Result(db, orc.swarm_of, orc.generation, orc.parent, graft_cand=orc.graft_cand, boundary=3)
+    assert res.uclust_text(threads=3) == (GOLDEN / "c1_1k_150.f.u").read_bytes()
+    db = HostDb(GOLDEN / "usearch_300.fasta", usearch_abundance=True)
+    orc = Oracle(db)
+    orc.network(); orc.cluster()
+    assert D1Result(db, orc.swarm_of, orc.generation, orc.parent).uclust_text() == (GOLDEN / "usearch_300.u").read_bytes()
+
+
+def test_uclust_cigar_known_answers(built):
+    """run-length rules of src/utils/cigar.cc:30-60 (a count of 1 is not printed) and the trace-back priorities of
+    src/nw.cc:111-191; the expected strings were produced by the reference binary (re-checked here when it is built).
+    Member m against seed s: I = nucleotide only in the member, D = only in the seed."""
+    seed = "ACGTTGCAAGGCTTACCGATAGGCTAACGT"
+    cases = [(seed[:10] + seed[11:], "96.7", "9MD20M"),          # one G of the GG run missing: the gap goes to the first
+             (seed[:10] + "T" + seed[10:], "96.8", "10MI20M"),
+             (seed[:-1] + "A", "96.7", "30M"),                   # a substitution is an M column
+             ("G" + seed, "96.8", "I30M"), (seed + "G", "96.8", "30MI"), (seed[2:], "93.3", "2D28M"),
+             (seed[:12] + "AA" + seed[12:], "93.8", "12M2I18M"),
+             (seed[:5] + "A" + seed[6:20] + seed[21:], "93.3", "20MD9M")]
+    for member, pct, cigar in cases:
+        text = f">s_9\n{seed}\n>m_1\n{member}\n".encode()
+        db = HostDb(text=text)
+        res = D1Result(db, np.zeros(2, np.uint32), np.array([0, 1], np.uint32), np.array([0xFFFFFFFF, 0], np.uint32))
+        lines = res.uclust_text().decode().splitlines()
+        assert lines[0] == "C\t0\t2\t*\t*\t*\t*\t*\ts_9\t*" and lines[1] == "S\t0\t30\t*\t*\t*\t*\t*\ts_9\t*"
+        assert lines[2] == f"H\t0\t{len(member)}\t{pct}\t+\t0\t0\t{cigar}\tm_1\ts_9"
+        if helpers.have_ref():
+            import os, tempfile
+            with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
+                f.write(text)
+            ref = helpers.run_ref(f.name, "-d", "3", outputs=("u",))["u"].decode().splitlines()
+            os.unlink(f.name)
+            assert ref == lines
+
+
 def test_network_matches_reference(case):
     name, db, orc = case
     pairs = orc.links()
