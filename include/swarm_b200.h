@@ -151,12 +151,21 @@ int  swb200_d1_fastidious(swb200_ctx *ctx, uint64_t boundary, uint32_t *graft_ca
 int  swb200_dn_cluster(swb200_ctx *ctx, uint32_t d, int no_cluster_breaking, const int64_t penalties[3],
                        uint32_t *swarm_of, uint32_t *generation, uint32_t *parent, uint32_t *pdiff);
 
+/* d=0, dereplication: replaces `dereplicating` (src/derep.cc:276-354: zobrist_hash + open-addressing table of
+ * clusters + exact sequence comparison, chains in index order).  rep[i] = the smallest id with i's sequence (the
+ * reference's seqno_first of i's cluster); mass / size / singletons are the cluster sums (src/derep.cc:322-344),
+ * stored at the representative's index and 0 elsewhere; any output pointer may be NULL.  The host orders clusters by
+ * mass descending, then representative (sort_seeds, :74-98).  Needs only swb200_load_db.  Device time: phase 7. */
+int  swb200_d0_dereplicate(swb200_ctx *ctx, uint32_t *rep, uint64_t *mass, uint32_t *size, uint32_t *singletons,
+                           uint64_t *n_clusters);
+
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on: lets the caller bracket calls
  * with its own CUDA events, or order collectives (NCCL) after the engine's work without a host round trip. */
 int  swb200_stream(swb200_ctx *ctx, void **stream);
 
 /* Device time (CUDA events on the engine's stream) of the last call, and accumulated per phase.
- * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 6 d>1 (all of swb200_dn_cluster) */
+ * phase: 0 load_db(H2D) 1 index 2 network 3 cluster 4 fastidious 6 d>1 (all of swb200_dn_cluster)
+ *        7 d=0 (swb200_d0_dereplicate) */
 double swb200_last_device_seconds(swb200_ctx *ctx);
 double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 

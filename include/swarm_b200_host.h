@@ -65,6 +65,23 @@ int  swbh_dn_write_structure(const swbh_db *db, const swbh_result *r, int usearc
  * src/utils/cigar.cc:30-60).  penalties = swbh_scoring()'s output; `threads` workers align (output independent of it). */
 int  swbh_write_uclust(const swbh_db *db, const swbh_result *r, int64_t differences, const int64_t penalties[3],
                        int usearch_abundance, int64_t append_abundance, int threads, char **out, uint64_t *out_len);
+/* d=0 (dereplication) result assembly + writers, src/derep.cc: clusters ordered by mass descending then seed index
+ * (sort_seeds :74-98), members in index order (:322-326); -o/-r :206-273, -w :190-203, -u :145-187, -i :121-142,
+ * -s :103-118.  Inputs are swb200_d0_dereplicate()'s outputs. */
+typedef struct swbh_derep swbh_derep;
+int  swbh_d0_assemble(const swbh_db *db, const uint32_t *rep, const uint64_t *mass, const uint32_t *size,
+                      const uint32_t *singletons, swbh_derep **out);
+void swbh_derep_free(swbh_derep *r);
+uint64_t swbh_derep_clusters(const swbh_derep *r);
+uint32_t swbh_derep_largest(const swbh_derep *r);
+uint64_t swbh_derep_heaviest(const swbh_derep *r);    /* "Heaviest swarm" of the log, src/derep.cc:417 */
+int  swbh_d0_write_swarms(const swbh_db *db, const swbh_derep *r, int mothur, int usearch_abundance, int64_t append_abundance,
+                          char **out, uint64_t *out_len);
+int  swbh_d0_write_seeds(const swbh_db *db, const swbh_derep *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_d0_write_uclust(const swbh_db *db, const swbh_derep *r, int usearch_abundance, int64_t append_abundance,
+                          char **out, uint64_t *out_len);
+int  swbh_d0_write_structure(const swbh_db *db, const swbh_derep *r, int usearch_abundance, char **out, uint64_t *out_len);
+int  swbh_d0_write_stats(const swbh_db *db, const swbh_derep *r, int usearch_abundance, char **out, uint64_t *out_len);
 /* alignment scoring conversion (src/swarm.cc:466-483): penalties[3] = mismatch, gap open, gap extend */
 void swbh_scoring(int64_t match_reward, int64_t mismatch_penalty, int64_t gap_open, int64_t gap_extend, int64_t penalties[3]);
 

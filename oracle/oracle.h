@@ -91,6 +91,11 @@ uint32_t orc_dn_cluster(const orc_db *db, uint32_t d, int no_cluster_breaking, c
                         uint32_t *order, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent,
                         uint32_t *pdiff, uint32_t *radius, uint64_t *stats /* NULL or [3] */);
 
+/* --- d=0 (oracle_d0.c): src/derep.cc:276-354 + sort_seeds :74-98.  rep[n] = seed of a's cluster, next[n] = chain in
+ * index order (0 ends it), per cluster in output order: seeds, mass, size, singletons (capacity n).  Returns #clusters. */
+uint32_t orc_d0_dereplicate(const orc_db *db, uint32_t *rep, uint32_t *next, uint32_t *seeds, uint64_t *mass,
+                            uint32_t *size, uint32_t *singletons);
+
 void orc_free(void *p);
 
 #ifdef __cplusplus

@@ -7,6 +7,6 @@ This package is only the thin ctypes binding used by the tests, ``bench.py`` and
 launcher; there is no Python or CPU implementation of the algorithms here — if the CUDA library is
 missing or no GPU is present every engine call raises.
 """
-from .ffi import Engine, HostDb, D1Result, DnResult, scoring, EngineError, lib_paths, ENUM_FULL, ENUM_HALF, ENUM_JOIN, NONE  # noqa: F401
+from .ffi import Engine, HostDb, D1Result, DnResult, DerepResult, scoring, EngineError, lib_paths, ENUM_FULL, ENUM_HALF, ENUM_JOIN, NONE  # noqa: F401
 
-__all__ = ["Engine", "HostDb", "D1Result", "DnResult", "scoring", "EngineError", "lib_paths", "ENUM_FULL", "ENUM_HALF", "ENUM_JOIN", "NONE"]
+__all__ = ["Engine", "HostDb", "D1Result", "DnResult", "DerepResult", "scoring", "EngineError", "lib_paths", "ENUM_FULL", "ENUM_HALF", "ENUM_JOIN", "NONE"]

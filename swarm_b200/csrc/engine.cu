@@ -11,6 +11,7 @@
 #include "d1_cluster.cuh"
 #include "d1_dist.cuh"
 #include "dn_kernels.cuh"
+#include "d0_derep.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -149,6 +150,10 @@ struct swb200_ctx {
   DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
   DevBuf<uint2> tasks;
   uint64_t dnstats[4] = {0, 0, 0, 0};
+  // d = 0
+  DevBuf<unsigned long long> dr_table, dr_mass;
+  DevBuf<uint32_t> dr_slot, dr_rep, dr_size, dr_single;
+  uint64_t drstats[3] = {0, 0, 0};
   // pinned staging
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -252,6 +257,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release();
+  c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1208,6 +1214,41 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
     CK(cudaMemcpyAsync(graft_cand, c->graft.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  API_END()
+}
+
+// d = 0 (src/derep.cc:276-354): classes of identical sequences, kernels in d0_derep.cuh.  Device-timed as phase 7.
+int swb200_d0_dereplicate(swb200_ctx *c, uint32_t *rep, uint64_t *mass, uint32_t *size, uint32_t *singletons, uint64_t *n_clusters) {
+  API_BEGIN(c)
+  if (c->n == 0) { g_err = "d0_dereplicate: no database loaded"; return SWB200_EINVAL; }
+  if (c->db_pending) { g_err = "d0_dereplicate: swb200_load_db_shard must be followed by the row exchange and swb200_db_commit"; return SWB200_EINVAL; }
+  const uint32_t n = c->n;
+  const uint64_t slots = table_slots(n);                    // the reference's sizing rule (src/derep.cc:397)
+  c->dr_table.alloc(slots); c->dr_slot.alloc(n); c->dr_rep.alloc(n); c->dr_mass.alloc(n); c->dr_size.alloc(n); c->dr_single.alloc(n);
+  DerepParams D{};
+  D.words = c->words.p; D.len = c->len.p; D.abundance = c->abundance.p; D.n = n; D.stride = c->stride;
+  D.table = c->dr_table.p; D.slot_mask = slots - 1; D.slot_of = c->dr_slot.p; D.rep = c->dr_rep.p;
+  D.mass = c->dr_mass.p; D.size = c->dr_size.p; D.singletons = c->dr_single.p;
+  D.stats = c->counters.p + 24; D.count_steps = c->collect_stats;
+  const unsigned blocks = (n + 255) / 256;
+  c->tic();
+  CK(cudaMemsetAsync(c->dr_table.p, 0xFF, slots * 8, c->stream));
+  CK(cudaMemsetAsync(c->dr_mass.p, 0, static_cast<size_t>(n) * 8, c->stream));
+  CK(cudaMemsetAsync(c->dr_size.p, 0, static_cast<size_t>(n) * 4, c->stream));
+  CK(cudaMemsetAsync(c->dr_single.p, 0, static_cast<size_t>(n) * 4, c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 24, 0, 3 * 8, c->stream));
+  k_derep_claim<<<blocks, 256, 0, c->stream>>>(D);
+  k_derep_gather<<<blocks, 256, 0, c->stream>>>(D);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  c->toc(7);
+  CK(cudaMemcpyAsync(c->drstats, c->counters.p + 24, 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (rep) CK(cudaMemcpyAsync(rep, c->dr_rep.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (mass) CK(cudaMemcpyAsync(mass, c->dr_mass.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (size) CK(cudaMemcpyAsync(size, c->dr_size.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (singletons) CK(cudaMemcpyAsync(singletons, c->dr_single.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (n_clusters) *n_clusters = c->drstats[0];
   API_END()
 }
 

@@ -74,6 +74,7 @@ def engine_lib():
         L.swb200_d1_cluster.argtypes = [vp, _u32p, _u32p, _u32p]
         L.swb200_d1_fastidious.argtypes = [vp, C.c_uint64, _u32p, _u64p, _u64p]
         L.swb200_dn_cluster.argtypes = [vp, C.c_uint32, C.c_int, C.POINTER(C.c_int64), _u32p, _u32p, _u32p, _u32p]
+        L.swb200_d0_dereplicate.argtypes = [vp, _u32p, _u64p, _u32p, _u32p, _u64p]
         L.swb200_stream.argtypes = [vp, C.POINTER(vp)]
         L.swb200_last_device_seconds.argtypes = [vp]
         L.swb200_last_device_seconds.restype = C.c_double
@@ -132,6 +133,20 @@ def host_lib():
         L.swbh_dn_assemble.argtypes = [vp, _u32p, _u32p, _u32p, _u32p, C.POINTER(vp)]
         L.swbh_dn_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_dn_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_d0_assemble.argtypes = [vp, _u32p, _u64p, _u32p, _u32p, C.POINTER(vp)]
+        L.swbh_derep_free.argtypes = [vp]
+        L.swbh_derep_free.restype = None
+        L.swbh_derep_clusters.argtypes = [vp]
+        L.swbh_derep_clusters.restype = C.c_uint64
+        L.swbh_derep_largest.argtypes = [vp]
+        L.swbh_derep_largest.restype = C.c_uint32
+        L.swbh_derep_heaviest.argtypes = [vp]
+        L.swbh_derep_heaviest.restype = C.c_uint64
+        L.swbh_d0_write_swarms.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
+        L.swbh_d0_write_seeds.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_d0_write_uclust.argtypes = [vp, vp, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
+        L.swbh_d0_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_d0_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_scoring.argtypes = [C.c_int64] * 4 + [C.POINTER(C.c_int64)]
         L.swbh_scoring.restype = None
         L.swbh_free.argtypes = [vp]
@@ -238,6 +253,54 @@ class D1Result:
     def close(self):
         if getattr(self, "_h", None):
             host_lib().swbh_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DerepResult:
+    """d=0: clusters of identical sequences in the reference's output order, built by the host layer from the
+    engine's rep / mass / size / singletons arrays (swb200_d0_dereplicate)."""
+
+    def __init__(self, db: HostDb, rep, mass, size, singletons):
+        L = host_lib()
+        self.db = db
+        rep = np.ascontiguousarray(rep, dtype=np.uint32)
+        mass = np.ascontiguousarray(mass, dtype=np.uint64)
+        size = np.ascontiguousarray(size, dtype=np.uint32)
+        singletons = np.ascontiguousarray(singletons, dtype=np.uint32)
+        h = C.c_void_p()
+        if L.swbh_d0_assemble(db._h, _ptr(rep, _u32p), _ptr(mass, _u64p), _ptr(size, _u32p), _ptr(singletons, _u32p), C.byref(h)) != 0:
+            raise ValueError(L.swbh_last_error().decode())
+        self._h = h
+        self.clusters = L.swbh_derep_clusters(h)
+        self.largest = L.swbh_derep_largest(h)
+        self.heaviest = L.swbh_derep_heaviest(h)
+
+    _text = D1Result._text
+
+    def swarms_text(self, mothur=False) -> bytes:
+        return self._text(host_lib().swbh_d0_write_swarms, self.db._h, self._h, int(mothur), *self.db.opts)
+
+    def seeds_text(self) -> bytes:
+        return self._text(host_lib().swbh_d0_write_seeds, self.db._h, self._h, self.db.opts[0])
+
+    def uclust_text(self) -> bytes:
+        return self._text(host_lib().swbh_d0_write_uclust, self.db._h, self._h, *self.db.opts)
+
+    def structure_text(self) -> bytes:
+        return self._text(host_lib().swbh_d0_write_structure, self.db._h, self._h, self.db.opts[0])
+
+    def stats_text(self) -> bytes:
+        return self._text(host_lib().swbh_d0_write_stats, self.db._h, self._h, self.db.opts[0])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            host_lib().swbh_derep_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -431,6 +494,15 @@ class Engine:
         self._ck(engine_lib().swb200_dn_cluster(self._h, int(d), int(bool(no_cluster_breaking)), pen,
                                                *[_ptr(a, _u32p) for a in outs]))
         return tuple(outs)
+
+    def d0_dereplicate(self):
+        """d=0: (rep, mass, size, singletons, n_clusters); the sums live at the representatives' indices"""
+        rep, size, singles = (np.empty(self.n, dtype=np.uint32) for _ in range(3))
+        mass = np.empty(self.n, dtype=np.uint64)
+        k = C.c_uint64()
+        self._ck(engine_lib().swb200_d0_dereplicate(self._h, _ptr(rep, _u32p), _ptr(mass, _u64p), _ptr(size, _u32p),
+                                                   _ptr(singles, _u32p), C.byref(k)))
+        return rep, mass, size, singles, k.value
 
     def stream(self) -> int:
         """cudaStream_t of the engine (wrap with torch.cuda.ExternalStream to record events / order collectives)"""

@@ -35,7 +35,10 @@ int give(const std::string &s, char **out, uint64_t *out_len) {
 
 }  // namespace
 
-namespace swb { int give_text(const std::string &s, char **out, uint64_t *out_len) { return give(s, out, out_len); } }
+namespace swb {
+int give_text(const std::string &s, char **out, uint64_t *out_len) { return give(s, out, out_len); }
+void set_host_error(const std::string &e) { g_err = e; }
+}  // namespace swb
 
 extern "C" {
 

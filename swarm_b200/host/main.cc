@@ -1,12 +1,12 @@
-// swarm_b200/host/main.cc — `swarm_b200`: drop-in command line for swarm's d >= 1 clustering on a B200.
+// swarm_b200/host/main.cc — `swarm_b200`: drop-in command line for swarm (d = 0, d = 1, d > 1) on a B200.
 //
 // Host mirror of /root/reference src/swarm.cc (options :93-124, checks :486-630, dispatch :633-675) and
 // src/utils/open_and_close_files.cc:35-93, written from scratch: same options, same validation messages,
-// same output bytes (`-o -r -s -i -w -j`), same exit code (1 after "\nError: ..." on stderr,
+// same output bytes (`-o -r -s -i -w -j -u`), same exit code (1 after "\nError: ..." on stderr,
 // src/utils/fatal.h:27,38-46).  The clustering itself is the CUDA engine behind include/swarm_b200.h.
-// Not provided: d = 0 dereplication (src/derep.cc) and the uclust writer `-u` (needs the scalar NW +
-// CIGAR of src/nw.cc): both end with an error message.  `-t`, `-x`, `-c`, `-y` are accepted and validated
-// but have nothing to configure (no CPU thread pool, no SSE dispatch, no Bloom filter to size).
+// d = 0 (dereplication, src/derep.cc) runs on the engine too; `-u` aligns on the host like the reference
+// (uclust.cc, `-t` workers).  `-x`, `-c`, `-y` are accepted and validated but have nothing to configure (no SSE
+// dispatch, no Bloom filter to size).
 #include "../../include/swarm_b200.h"
 #include "../../include/swarm_b200_host.h"
 
@@ -205,7 +205,6 @@ int main(int argc, char **argv) {
     if (P.differences > sat16) fatal("Resolution (d) too high for the given scoring system.");
     if (P.pen[0] > 255) fatal("Alignment scoring system yielded a mismatch penalty greater than 255, please use different parameter values.");
   }
-  if (P.differences == 0) fatal("d = 0 (dereplication) is not provided by swarm_b200; use swarm -d 0 or vsearch --derep_fulllength.");
 
   // open_files, src/utils/open_and_close_files.cc:35-93
   std::FILE *out = open_out(P.output_file);
@@ -251,6 +250,28 @@ int main(int argc, char **argv) {
     const char *dev = std::getenv("SWARM_B200_DEVICE");
     engine_check(swb200_create(&ctx, dev ? std::atoi(dev) : 0));
     engine_check(swb200_load_db(ctx, swbh_db_words(db), swbh_db_stride_words(db), swbh_db_lengths(db), swbh_db_abundances(db), n));
+    if (P.differences == 0) {                                  // dereplicate, src/derep.cc:393-418
+      std::vector<uint32_t> rep(n), size(n), singles(n);
+      std::vector<uint64_t> mass(n);
+      uint64_t clusters = 0;
+      engine_check(swb200_d0_dereplicate(ctx, rep.data(), mass.data(), size.data(), singles.data(), &clusters));
+      swb200_destroy(ctx);
+      swbh_derep *dr = nullptr;
+      if (swbh_d0_assemble(db, rep.data(), mass.data(), size.data(), singles.data(), &dr) != 0) fatal(swbh_last_error());
+      if (swbh_d0_write_swarms(db, dr, P.mothur, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
+      write_all(out, text, len);
+      if (seedsf) { if (swbh_d0_write_seeds(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); }
+      if (uclustf) { if (swbh_d0_write_uclust(db, dr, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error()); write_all(uclustf, text, len); }
+      if (structf) { if (swbh_d0_write_structure(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(structf, text, len); }
+      if (statsf) { if (swbh_d0_write_stats(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(statsf, text, len); }
+      std::fprintf(logf, "\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\nHeaviest swarm:    %" PRIu64 "\n", swbh_derep_clusters(dr),
+                   swbh_derep_largest(dr), swbh_derep_heaviest(dr));
+      swbh_derep_free(dr);
+      swbh_db_free(db);
+      for (std::FILE *f : {netf, structf, uclustf, statsf, seedsf, out}) if (f) std::fclose(f);
+      if (logf != stderr) std::fclose(logf);
+      return EXIT_SUCCESS;
+    }
     std::vector<uint32_t> swarm_of(n), generation(n), parent(n), extra(n, SWB200_NONE);
     if (P.differences == 1) {
       engine_check(swb200_d1_index(ctx));
@@ -300,6 +321,9 @@ int main(int argc, char **argv) {
     std::fprintf(logf, "\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\nMax generations:   %u\n", swbh_result_swarms(res), swbh_result_largest(res),
                  P.differences == 1 ? swbh_result_maxgen(res) : std::max(1u, swbh_result_maxgen(res)));
     swbh_result_free(res);
+  } else {                                                     // empty input: the reference still reports (and the mothur line is written)
+    if (P.mothur && P.differences < 2) std::fprintf(out, "swarm_%" PRId64 "\t0\n", P.differences);   // src/algo.cc writes nothing
+    std::fprintf(logf, "\nNumber of swarms:  0\nLargest swarm:     0\n%s0\n", P.differences == 0 ? "Heaviest swarm:    " : "Max generations:   ");
   }
   swbh_db_free(db);
   for (std::FILE *f : {netf, structf, uclustf, statsf, seedsf, out}) if (f) std::fclose(f);

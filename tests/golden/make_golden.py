@@ -78,11 +78,46 @@ def make_uclust():
     print("uclust ok")
 
 
+def make_derep():
+    """d=0 inputs need identical sequences: reads drawn (seeded) from the first 250 sequences of c1_1k_150 with fresh
+    labels and small abundances (many 1s -> singletons, equal masses -> the seed-index tie-break), some in lower
+    case / with U, plus sequences that pack to the same words and differ only in length (A, AA, AAA)."""
+    import random
+    rng = random.Random(20261017)
+    seqs = [l for l in (HERE / "c1_1k_150.fasta").read_text().splitlines() if not l.startswith(">")][:250]
+    reads = []
+    for i, sq in enumerate(seqs):
+        for k in range(rng.choice([1, 1, 1, 2, 2, 3, 4, 6, 9])):
+            t = sq
+            r = rng.random()
+            if r < 0.15:
+                t = sq.lower()
+            elif r < 0.3:
+                t = sq.replace("T", "U")
+            reads.append((f"r{i}x{k}", rng.choice([1, 1, 1, 2, 3, 5, 40]), t))
+    for k, t in enumerate(["A", "AA", "AAA", "a", "AA", "C", "ACGT" * 16, "ACGT" * 16 + "A", "ACGT" * 16]):
+        reads.append((f"tiny{k}", rng.choice([1, 2, 2]), t))
+    rng.shuffle(reads)
+    (HERE / "derep_mix.fasta").write_text("".join(f">{h}_{ab}\n{t}\n" for h, ab, t in reads))
+    (HERE / "derep_mix_z.fasta").write_text("".join(f">{h};size={ab};\n{t}\n" for h, ab, t in reads[:300]))
+    for name, flags in [("derep_mix", []), ("derep_mix_z", ["-z"])]:
+        r = helpers.run_ref(HERE / f"{name}.fasta", "-d", "0", *flags, outputs=("o", "s", "i", "w", "u"))
+        assert r["rc"] == 0, r["stderr"]
+        for k in "osiwu":
+            (HERE / f"{name}.d0.{k}").write_bytes(r[k])
+        (HERE / f"{name}.d0.log").write_bytes(r["log"][r["log"].index(b"\nNumber of swarms"):])
+        r = helpers.run_ref(HERE / f"{name}.fasta", "-d", "0", "-r", *flags, outputs=("o",))
+        (HERE / f"{name}.d0.r.o").write_bytes(r["o"])
+    print("derep ok")
+
+
 def main():
     if not helpers.have_ref():
         sys.exit("oracle/_ref/swarm missing: run `make -C oracle ref` where /root/reference exists")
     if sys.argv[1:] == ["uclust"]:          # only (re)generate the -u fixtures; the inputs must exist
         return make_uclust()
+    if sys.argv[1:] == ["derep"]:
+        return make_derep()
     (HERE / "handmade.fasta").write_bytes(HANDMADE)
     names = ["handmade"]
     for name, n, L, seed, mode, op in CASES:
@@ -135,6 +170,7 @@ def main():
     (HERE / "usearch_300.r.o").write_bytes(r["o"])
     print("usearch ok")
     make_uclust()
+    make_derep()
 
 
 if __name__ == "__main__":

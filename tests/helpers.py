@@ -64,6 +64,8 @@ def oracle_lib():
         L.orc_nw_diffs.restype = C.c_uint64
         L.orc_dn_cluster.argtypes = [C.POINTER(OrcDb), C.c_uint32, C.c_int, C.POINTER(C.c_int64)] + [_u32p] * 6 + [_u64p]
         L.orc_dn_cluster.restype = C.c_uint32
+        L.orc_d0_dereplicate.argtypes = [C.POINTER(OrcDb), _u32p, _u32p, _u32p, _u64p, _u32p, _u32p]
+        L.orc_d0_dereplicate.restype = C.c_uint32
         L.orc_free.argtypes = [C.c_void_p]
         _orc = L
     return _orc
@@ -162,6 +164,20 @@ class Oracle:
                                         _p(self.pdiff, _u32p), _p(self.radius, _u32p), _p(st, _u64p))
         self.dn_stats = st
         return self.swarm_of, self.generation, self.parent, self.pdiff
+
+    def derep(self):
+        """d=0 (oracle_d0.c): returns (rep, mass, size, singletons) laid out like the engine's outputs — sums at the
+        representatives' indices — plus self.d0_seeds (clusters in output order) and self.d0_next (chains)"""
+        L = oracle_lib()
+        n = self.db.n
+        rep, nxt, seeds, size, singles = (np.zeros(n, dtype=np.uint32) for _ in range(5))
+        mass = np.zeros(n, dtype=np.uint64)
+        k = L.orc_d0_dereplicate(C.byref(self.c), _p(rep, _u32p), _p(nxt, _u32p), _p(seeds, _u32p), _p(mass, _u64p),
+                                 _p(size, _u32p), _p(singles, _u32p))
+        self.d0_seeds, self.d0_next, self.d0_clusters = seeds[:k].copy(), nxt, k
+        m2, s2, g2 = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        m2[seeds[:k]], s2[seeds[:k]], g2[seeds[:k]] = mass[:k], size[:k], singles[:k]
+        return rep, m2, s2, g2
 
     def swarm_lists(self):
         """final member lists (list order) of the non-attached swarms, following `next`"""

@@ -39,8 +39,18 @@ def test_help_and_version_exit_zero(built):
         assert p.returncode == 0 and b"swarm_b200" in p.stderr
 
 
-def test_unsupported_modes_fail_loudly(built):
-    assert subprocess.run([str(CLI), "-d", "0", FA], capture_output=True).returncode == 1
+def test_no_cpu_fallback(built):
+    """without a GPU every clustering mode must end with an engine error, never with a CPU-computed result"""
+    import ctypes
+    try:
+        has_gpu = ctypes.CDLL("libcuda.so.1").cuInit(0) == 0
+    except OSError:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    for flags in (["-d", "0"], [], ["-f"], ["-d", "2"]):
+        p = subprocess.run([str(CLI), *flags, "-o", os.devnull, FA], capture_output=True)
+        assert p.returncode == 1 and b"Error: GPU engine:" in p.stderr, flags
 
 
 def _run(tmp, *flags, fasta=FA, outs=("o",)):

@@ -1,0 +1,163 @@
+"""d = 0 (dereplication, /root/reference src/derep.cc): the oracle restatement (oracle/oracle_d0.c) and the host
+writers against golden outputs of the reference binary (CPU), and the engine's kernels (csrc/d0_derep.cuh) against the
+oracle, the golden files and size-independent properties (GPU)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN, Oracle
+from swarm_b200 import DerepResult, HostDb
+
+CASES = [("derep_mix", False), ("derep_mix_z", True)]
+
+
+def _check_texts(res, name):
+    assert res.swarms_text() == (GOLDEN / f"{name}.d0.o").read_bytes()
+    assert res.swarms_text(mothur=True) == (GOLDEN / f"{name}.d0.r.o").read_bytes()
+    assert res.stats_text() == (GOLDEN / f"{name}.d0.s").read_bytes()
+    assert res.structure_text() == (GOLDEN / f"{name}.d0.i").read_bytes()
+    assert res.seeds_text() == (GOLDEN / f"{name}.d0.w").read_bytes()
+    assert res.uclust_text() == (GOLDEN / f"{name}.d0.u").read_bytes()
+    log = (GOLDEN / f"{name}.d0.log").read_text()
+    assert log == f"\nNumber of swarms:  {res.clusters}\nLargest swarm:     {res.largest}\nHeaviest swarm:    {res.heaviest}\n"
+
+
+@pytest.mark.parametrize("name,usearch", CASES)
+def test_oracle_and_writers_match_reference(built, name, usearch):
+    db = HostDb(GOLDEN / f"{name}.fasta", usearch_abundance=usearch)
+    orc = Oracle(db)
+    rep, mass, size, singles = orc.derep()
+    # the oracle's chains are the clusters' members in index order
+    for s in orc.d0_seeds[:50]:
+        chain, a = [int(s)], int(orc.d0_next[s])
+        while a:
+            chain.append(a)
+            a = int(orc.d0_next[a])
+        assert chain == np.flatnonzero(rep == s).tolist()
+    _check_texts(DerepResult(db, rep, mass, size, singles), name)
+
+
+def test_length_is_part_of_the_key(built):
+    # "A", "AA", "AAA" pack to the same zero words (A = 0): only the length tells them apart
+    db = HostDb(text=b">a_3\nA\n>b_2\nAA\n>c_2\nAAA\n>d_1\naa\n>e_1\nA\n")
+    rep, mass, size, singles = Oracle(db).derep()
+    heads = [db.header(i) for i in range(db.n)]
+    groups = sorted(sorted(heads[j] for j in np.flatnonzero(rep == r)) for r in np.unique(rep))
+    assert groups == [["a_3", "e_1"], ["b_2", "d_1"], ["c_2"]]
+    assert DerepResult(db, rep, mass, size, singles).swarms_text() == b"a_3 e_1\nb_2 d_1\nc_2\n"
+
+
+def test_assemble_rejects_inconsistent_arrays(built):
+    db = HostDb(text=b">a_3\nA\n>b_2\nAA\n")
+    z32, z64 = np.zeros(2, np.uint32), np.zeros(2, np.uint64)
+    with pytest.raises(ValueError):
+        DerepResult(db, np.array([1, 1], np.uint32), z64, z32, z32)          # rep must point at a first occurrence
+    with pytest.raises(ValueError):
+        DerepResult(db, np.array([0, 1], np.uint32), z64, z32, z32)          # sizes must add up to n
+
+
+def test_cli_empty_input_matches_reference(built, tmp_path):
+    if not helpers.have_ref():
+        pytest.skip("reference binary not built")
+    fa = tmp_path / "empty.fa"
+    fa.write_bytes(b"")
+    cli = str(helpers.ROOT / "bin" / "swarm_b200")
+    for flags in (["-d", "0"], ["-d", "0", "-r"], [], ["-r"], ["-d", "2"], ["-d", "2", "-r"]):
+        outs = []
+        for exe in (cli, str(helpers.REF_BIN)):
+            o, l = tmp_path / "o", tmp_path / "l"
+            p = subprocess.run([exe, *flags, "-o", str(o), "-l", str(l), str(fa)], capture_output=True)
+            assert p.returncode == 0
+            log = l.read_bytes()
+            outs.append((o.read_bytes(), log[log.index(b"\nNumber of swarms"):]))
+        assert outs[0] == outs[1], flags
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,usearch", CASES)
+def test_engine_matches_oracle_and_reference(built, name, usearch):
+    from swarm_b200 import Engine
+    db = HostDb(GOLDEN / f"{name}.fasta", usearch_abundance=usearch)
+    eng = Engine(0)
+    eng.load(db)
+    rep, mass, size, singles, k = eng.d0_dereplicate()
+    want = Oracle(db).derep()
+    for got, exp in zip((rep, mass, size, singles), want):
+        assert np.array_equal(got, exp)
+    res = DerepResult(db, rep, mass, size, singles)
+    assert k == res.clusters
+    _check_texts(res, name)
+
+
+@pytest.mark.gpu
+def test_engine_tiny_and_length_edge_cases(built):
+    from swarm_b200 import Engine
+    for text in (b">a_3\nA\n>b_2\nAA\n>c_2\nAAA\n>d_1\naa\n>e_1\nA\n", b">only_7\nACGTACGT\n",
+                 b"".join(b">s%d_1\nACGTTGCA\n" % i for i in range(1000))):
+        db = HostDb(text=text)
+        eng = Engine(0)
+        eng.load(db)
+        rep, mass, size, singles, k = eng.d0_dereplicate()
+        for got, exp in zip((rep, mass, size, singles), Oracle(db).derep()):
+            assert np.array_equal(got, exp)
+        assert k == len(np.unique(rep))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,copies,L", [(200_000, 5, 150), (50_000, 40, 64), (300_000, 1, 33)])
+def test_engine_seeded_reads_properties(built, tmp_path, n, copies, L):
+    """n unique sequences, each present 1..copies times: rep is the first occurrence, sums add up, and the result
+    equals the oracle's (the oracle handles these sizes in seconds)"""
+    from swarm_b200 import Engine
+    fa = tmp_path / "u.fa"
+    helpers.make_fasta(fa, n, L, 11)
+    seqs = [l for l in fa.read_text().splitlines() if not l.startswith(">")]
+    rng = np.random.default_rng(5)
+    reps = rng.integers(1, copies + 1, size=n)
+    idx = np.repeat(np.arange(n), reps)
+    rng.shuffle(idx)
+    ab = rng.choice([1, 1, 2, 7], size=len(idx))
+    text = "".join(f">r{j}_{ab[j]}\n{seqs[i]}\n" for j, i in enumerate(idx)).encode()
+    db = HostDb(text=text)
+    eng = Engine(0)
+    eng.load(db)
+    rep, mass, size, singles, k = eng.d0_dereplicate()
+    assert k == n and int(size.sum()) == db.n and int(mass.sum()) == int(db.abundance.sum())
+    assert np.array_equal(rep[rep], rep) and np.all(rep <= np.arange(db.n))
+    for got, exp in zip((rep, mass, size, singles), Oracle(db).derep()):
+        assert np.array_equal(got, exp)
+    # idempotence: dereplicating the representatives finds nothing to merge
+    keep = np.flatnonzero(rep == np.arange(db.n))
+    text2 = "".join(f">{db.header(int(i))}\n{seqs_of(db, int(i))}\n" for i in keep[:20000]).encode()
+    db2 = HostDb(text=text2)
+    eng2 = Engine(0)
+    eng2.load(db2)
+    rep2 = eng2.d0_dereplicate()[0]
+    assert np.array_equal(rep2, np.arange(db2.n))
+
+
+def seqs_of(db, i):
+    w = db.words.reshape(db.n, db.stride)[i]
+    return "".join("ACGT"[(int(w[p >> 5]) >> ((p & 31) * 2)) & 3] for p in range(int(db.len[i])))
+
+
+@pytest.mark.gpu
+def test_cli_d0_outputs(built, tmp_path):
+    cli = str(helpers.ROOT / "bin" / "swarm_b200")
+    for name, flags in (("derep_mix", []), ("derep_mix_z", ["-z"])):
+        outs = {k: tmp_path / k for k in "osiwu"}
+        cmd = [cli, "-d", "0", *flags, "-l", str(tmp_path / "log")]
+        for k, f in outs.items():
+            cmd += ["-" + k, str(f)]
+        p = subprocess.run(cmd + [str(GOLDEN / f"{name}.fasta")], capture_output=True)
+        assert p.returncode == 0, p.stderr
+        for k, f in outs.items():
+            assert f.read_bytes() == (GOLDEN / f"{name}.d0.{k}").read_bytes(), (name, k)
+        log = (tmp_path / "log").read_bytes()
+        assert log[log.index(b"\nNumber of swarms"):] == (GOLDEN / f"{name}.d0.log").read_bytes()
+        p = subprocess.run([cli, "-d", "0", "-r", *flags, "-l", os.devnull, str(GOLDEN / f"{name}.fasta")], capture_output=True)
+        assert p.returncode == 0 and p.stdout == (GOLDEN / f"{name}.d0.r.o").read_bytes()
