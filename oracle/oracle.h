@@ -40,6 +40,7 @@ void     orc_zobrist_exit(void);
 uint64_t orc_zobrist_value(uint32_t pos, uint32_t base);
 uint64_t orc_zobrist_hash(const uint64_t *seq, uint32_t len);
 uint64_t orc_mt19937_64_next(void);                  /* exposed for the known-answer test */
+void     orc_mt19937_64_seed(uint64_t seed);         /* std::mt19937_64 default seed = 5489 */
 
 /* --- microvariants: src/variants.cc:184-249 (enumeration), :118-165 (verification), :78-115 --- */
 uint32_t orc_generate_variants(const uint64_t *seq, uint32_t len, uint64_t hash, orc_var *out);

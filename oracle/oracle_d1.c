@@ -21,6 +21,7 @@ static void mt_seed(uint64_t seed) {
   mt[0] = seed;
   for (mti = 1; mti < 312; mti++) mt[mti] = 6364136223846793005ULL * (mt[mti - 1] ^ (mt[mti - 1] >> 62)) + (uint64_t)mti;
 }
+void orc_mt19937_64_seed(uint64_t seed) { mt_seed(seed); }
 uint64_t orc_mt19937_64_next(void) {
   static const uint64_t mag01[2] = {0ULL, 0xB5026F5AA96619E9ULL};
   if (mti >= 312) {

@@ -18,7 +18,8 @@ def test_mt19937_64_known_answer(built):
     L = helpers.oracle_lib()
     L.orc_zobrist_exit()
     import ctypes as C
-    # default seed 5489 is what orc_mt19937_64_next uses before any orc_zobrist_init
+    L.orc_mt19937_64_seed.argtypes = [C.c_uint64]
+    L.orc_mt19937_64_seed(5489)          # the default seed of std::mt19937_64
     vals = [L.orc_mt19937_64_next() for _ in range(10000)]
     assert vals[-1] == 9981545732273789042
 
