@@ -22,6 +22,8 @@ int  swbh_db_read_fasta(const char *path, int usearch_abundance, int64_t append_
 int  swbh_db_parse(const char *text, uint64_t size, int usearch_abundance, int64_t append_abundance,
                    int check_dup_sequences, swbh_db **out);
 void swbh_db_free(swbh_db *db);
+/* workers of the FASTA ingest (0 = hardware concurrency, at most 32; 1 = serial).  Results do not depend on it. */
+void swbh_set_threads(int threads);
 
 uint32_t swbh_db_count(const swbh_db *db);            /* db_getsequencecount   src/db.cc:806-809 */
 uint32_t swbh_db_longest(const swbh_db *db);          /* db_getlongestsequence src/db.cc:812-815 */

@@ -593,7 +593,12 @@ __global__ void k_key_unpack(const unsigned long long *key, uint32_t *label, uin
 // link: after the first two rounds most links are skipped (the first cut relaxed every link in every round and
 // was bound by ~300 M random L2 sectors: 1.2 ms at 10 M amplicons).  bits = 3 rotating bitmaps of `nwords` words:
 // round r reads bits[r%3], sets bits[(r+1)%3], clears bits[(r+2)%3].
+// HINT: the link list (70 MB at 10 M amplicons, re-read every round) is loaded with the streaming policy (ld.global.cs,
+// evict-first) and the per-amplicon outputs are stored with st.global.cs, so that they do not push the randomly accessed
+// key[] (80 MB) out of the 126 MB L2: the working set of this kernel sits right at the L2's capacity, and without the
+// hints the same binary measured 1.1 ms on one box and 2.7 ms on another (gpurun_out/r1s vs r1u).
 constexpr int kClU = 8;
+template <bool HINT>
 __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *parent,
                                                             uint32_t *label, uint32_t *generation, uint32_t n,
                                                             volatile uint32_t *flags, uint32_t *rounds_out, uint32_t *bits,
@@ -601,7 +606,10 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (uint64_t v = tid; v < n; v += nth) { key[v] = static_cast<unsigned long long>(v) << 32; parent[v] = kNone; }
+  for (uint64_t v = tid; v < n; v += nth) {
+    key[v] = static_cast<unsigned long long>(v) << 32;
+    if (HINT) __stcs(&parent[v], kNone); else parent[v] = kNone;
+  }
   for (uint64_t w = tid; w < 3ull * nwords; w += nth) bits[w] = 0;
   if (tid == 0) { flags[0] = 0; flags[1] = 0; flags[2] = 0; }
   grid.sync();
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
       for (int k = 0; k < kClU; ++k) {
         const uint64_t e = base + static_cast<uint64_t>(k) * nth;
         act[k] = e < m;
-        ed[k] = act[k] ? edges[e] : make_uint2(0u, 0u);
+        ed[k] = act[k] ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(0u, 0u);
       }
       if (round) {
         uint32_t w[kClU];
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
 #pragma unroll
     for (int k = 0; k < kClU; ++k) {
       const uint64_t e = base + static_cast<uint64_t>(k) * nth;
-      ed[k] = e < m ? edges[e] : make_uint2(kNone, kNone);
+      ed[k] = e < m ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(kNone, kNone);
     }
 #pragma unroll
     for (int k = 0; k < kClU; ++k) {
@@ -666,7 +674,11 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
     for (int k = 0; k < kClU; ++k)
       if (ed[k].x != kNone && ks[k] + 1ull == kd[k]) atomicMin(&parent[ed[k].y], ed[k].x);
   }
-  for (uint64_t v = tid; v < n; v += nth) { label[v] = static_cast<uint32_t>(key[v] >> 32); generation[v] = static_cast<uint32_t>(key[v]); }
+  for (uint64_t v = tid; v < n; v += nth) {
+    const unsigned long long kv = key[v];
+    if (HINT) { __stcs(&label[v], static_cast<uint32_t>(kv >> 32)); __stcs(&generation[v], static_cast<uint32_t>(kv)); }
+    else { label[v] = static_cast<uint32_t>(kv >> 32); generation[v] = static_cast<uint32_t>(kv); }
+  }
   if (tid == 0 && rounds_out) *rounds_out = round + 1;
 }
 

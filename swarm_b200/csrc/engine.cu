@@ -126,6 +126,7 @@ struct swb200_ctx {
   int cluster_kernel = 0; // 0 fused key relaxation of the frontier, one persistent cooperative kernel; 3 the same over links first sorted by
                           // source (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
                           // 1 label propagation + BFS
+  int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
@@ -278,6 +279,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
   else if (k == "cluster_kernel" && v >= 0 && v <= 3) c->cluster_kernel = static_cast<int>(v);
+  else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -776,7 +778,8 @@ static void run_cluster(swb200_ctx *c) {
   if (c->cluster_kernel == 0 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_persistent, 256, 0));
+    auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
     const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
     const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
     const uint2 *e_p = c->edges.p;
@@ -788,7 +791,7 @@ static void run_cluster(swb200_ctx *c) {
     c->cl_bits.alloc(static_cast<size_t>(nwords) * 3);
     uint32_t *bits_p = c->cl_bits.p;
     void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords};
-    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_persistent), dim3(grid), dim3(256), args, 0, c->stream));
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(grid), dim3(256), args, 0, c->stream));
     c->launches++;
     return;
   }

@@ -1,5 +1,14 @@
 // swarm_b200/host/amplicon_db.cc — FASTA → sorted, 2-bit packed, fixed-stride SoA database.
 // Behavioural mirror of /root/reference src/db.cc (citations inline); written from scratch.
+//
+// Two parsers produce the same database.  db_parse_serial() is the statement of the rules: it walks the text once,
+// in order, and owns every error message.  db_parse_parallel() is the ingest path for large inputs (SURVEY.md §8 row
+// f1: at 10 M amplicons the reference spends ~12 s here on one core, three orders of magnitude more than the GPU
+// spends clustering): the text is cut at record starts into one range per worker, every worker packs its records,
+// abundance annotations are parsed per record, duplicate labels (and, for d > 1, duplicate sequences) are found with
+// a lock-free open-addressing set of record indices, the order is a parallel merge sort and the SoA gather is split
+// by rows.  It only ever COMPLETES on well-formed input: anything irregular (a NUL byte, an illegal character, a
+// missing annotation, a duplicate ...) makes it give up, and the serial parser then reports the reference's message.
 #include "amplicon_db.h"
 
 #include <algorithm>
@@ -7,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <unordered_set>
 
 namespace swb {
@@ -77,7 +88,7 @@ inline int map_nt(unsigned char c) {   // src/db.cc:100-114: 1-based code, 0 = n
 
 }  // namespace
 
-std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db) {
+std::string db_parse_serial(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db) {
   db = AmpliconDb{};
   std::vector<RawEntry> entries;
   std::vector<uint64_t> packed;
@@ -242,6 +253,323 @@ std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, Ampl
   }
   db.header_off[n] = hp;
   return "";
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// parallel ingest
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+std::atomic<int> g_threads{0};           // 0 = hardware concurrency (at most 32)
+
+unsigned ingest_threads() {
+  int t = g_threads.load();
+  if (t <= 0) t = static_cast<int>(std::min(32u, std::max(1u, std::thread::hardware_concurrency())));
+  return static_cast<unsigned>(t);
+}
+
+template <typename F>
+void run_workers(unsigned T, F &&f) {
+  if (T <= 1) { f(0u); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(T);
+  for (unsigned t = 0; t < T; ++t) pool.emplace_back([&f, t] { f(t); });
+  for (auto &th : pool) th.join();
+}
+
+struct ParEntry {
+  uint64_t header_pos;
+  uint64_t word_pos;         // first packed word inside the buffer of worker `range`
+  uint64_t abundance;
+  uint32_t header_len, len;
+  int32_t ab_start, ab_end;
+  uint32_t range;
+};
+
+struct Range {
+  uint64_t begin = 0, end = 0;
+  std::vector<ParEntry> entries;
+  std::vector<uint64_t> packed;
+  uint64_t nucleotides = 0;
+  uint32_t longest = 0, longest_header = 0;
+  bool ok = true;
+};
+
+// 0..3 nucleotide code, 4 = line break (skipped), 5 = anything else (src/db.cc:100-114,555-603)
+struct NtTable {
+  uint8_t v[256];
+  NtTable() {
+    for (auto &x : v) x = 5;
+    v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = v['U'] = v['u'] = 3;
+    v['\n'] = v['\r'] = 4;
+  }
+};
+const NtTable kNt;
+
+void parse_range(const char *text, Range &R, uint32_t range_no) {
+  uint64_t pos = R.begin;
+  const uint64_t end = R.end;
+  R.packed.reserve((end - pos) / 28 + 16);
+  R.entries.reserve((end - pos) / 160 + 16);
+  while (pos < end) {
+    if (text[pos] != '>') { R.ok = false; return; }
+    const void *nl = std::memchr(text + pos, '\n', end - pos);
+    uint64_t le = nl ? static_cast<uint64_t>(static_cast<const char *>(nl) - text) + 1 : end;
+    ParEntry e{};
+    e.range = range_no;
+    e.header_pos = pos + 1;
+    uint32_t hl = 0;
+    while (pos + 1 + hl < le) {
+      const char c = text[pos + 1 + hl];
+      if (c == ' ' || c == '\r' || c == '\n') break;
+      ++hl;
+    }
+    if (hl > kMaxHeaderLength) { R.ok = false; return; }
+    e.header_len = hl;
+    R.longest_header = std::max(R.longest_header, hl);
+    pos = le;
+    const size_t first_word = R.packed.size();
+    uint64_t buf = 0, length = 0;
+    uint32_t nbuf = 0;
+    // the sequence runs to the next line that starts with '>' (a '>' elsewhere is an illegal character)
+    while (pos < end && text[pos] != '>') {
+      for (;;) {
+        const uint8_t code = kNt.v[static_cast<unsigned char>(text[pos])];
+        if (code < 4) {
+          buf |= static_cast<uint64_t>(code) << (2 * nbuf);
+          ++length;
+          if (++nbuf == 32) { R.packed.push_back(buf); buf = 0; nbuf = 0; }
+        } else if (code == 5) { R.ok = false; return; }
+        ++pos;
+        if (pos >= end || text[pos - 1] == '\n') break;
+      }
+    }
+    if (length == 0 || length > kMaxSequenceLength) { R.ok = false; return; }
+    if (nbuf > 0) R.packed.push_back(buf);
+    e.len = static_cast<uint32_t>(length);
+    e.word_pos = first_word;
+    R.nucleotides += length;
+    R.longest = std::max(R.longest, e.len);
+    R.entries.push_back(e);
+  }
+}
+
+inline uint64_t hash_bytes(const void *p, size_t n, uint64_t seed) {
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  uint64_t h = seed ^ (n * 0x9e3779b97f4a7c15ull);
+  while (n >= 8) {
+    uint64_t w;
+    std::memcpy(&w, b, 8);
+    h = (h ^ w) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    b += 8; n -= 8;
+  }
+  uint64_t w = 0;
+  std::memcpy(&w, b, n);
+  h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+  return h ^ (h >> 29);
+}
+
+// a key of the duplicate checks: bytes + a tag that must also match (the sequence length: "A" and "AA" pack to equal words)
+struct Key { const void *p; size_t n; uint32_t tag; };
+
+// lock-free open-addressing set of record indices: false as soon as two records carry equal keys
+template <typename KeyOf>
+bool all_distinct(uint32_t n, unsigned T, KeyOf &&key_of) {
+  uint64_t slots = 16;
+  while (slots < static_cast<uint64_t>(n) * 2) slots <<= 1;
+  std::vector<std::atomic<uint32_t>> table(slots);
+  std::vector<uint64_t> hashes(n);
+  std::atomic<bool> dup{false};
+  run_workers(T, [&](unsigned t) {
+    const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+    for (uint64_t s = slots * t / T; s < slots * (t + 1) / T; ++s) table[s].store(0xFFFFFFFFu, std::memory_order_relaxed);
+    for (uint64_t i = lo; i < hi; ++i) { const Key k = key_of(static_cast<uint32_t>(i)); hashes[i] = hash_bytes(k.p, k.n, k.tag); }
+  });
+  run_workers(T, [&](unsigned t) {
+    const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+    for (uint64_t i = lo; i < hi && !dup.load(std::memory_order_relaxed); ++i) {
+      const Key k = key_of(static_cast<uint32_t>(i));
+      uint64_t j = hashes[i] & (slots - 1);
+      for (;;) {
+        uint32_t cur = table[j].load(std::memory_order_acquire);
+        if (cur == 0xFFFFFFFFu && table[j].compare_exchange_strong(cur, static_cast<uint32_t>(i), std::memory_order_acq_rel)) break;
+        if (hashes[cur] == hashes[i]) {
+          const Key o = key_of(cur);
+          if (o.tag == k.tag && o.n == k.n && std::memcmp(o.p, k.p, k.n) == 0) { dup.store(true); break; }
+        }
+        j = (j + 1) & (slots - 1);
+      }
+    }
+  });
+  return !dup.load();
+}
+
+template <typename Rec, typename Less>
+void parallel_sort(std::vector<Rec> &v, unsigned T, Less less) {
+  const size_t n = v.size();
+  if (T <= 1 || n < (1u << 16)) { std::sort(v.begin(), v.end(), less); return; }
+  unsigned parts = 1;
+  while (parts * 2 <= T) parts *= 2;
+  std::vector<size_t> cut(parts + 1);
+  for (unsigned p = 0; p <= parts; ++p) cut[p] = n * p / parts;
+  run_workers(parts, [&](unsigned p) { std::sort(v.begin() + static_cast<int64_t>(cut[p]), v.begin() + static_cast<int64_t>(cut[p + 1]), less); });
+  for (unsigned width = 1; width < parts; width *= 2) {
+    const unsigned merges = parts / (2 * width);
+    run_workers(merges, [&](unsigned m) {
+      const size_t a = cut[2 * width * m], b = cut[2 * width * m + width], c = cut[2 * width * (m + 1)];
+      std::inplace_merge(v.begin() + static_cast<int64_t>(a), v.begin() + static_cast<int64_t>(b), v.begin() + static_cast<int64_t>(c), less);
+    });
+  }
+}
+
+// returns false when the input is not plainly well-formed (the serial parser then decides and words the error)
+bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db, unsigned T) {
+  if (size == 0 || std::memchr(text, '\0', size) != nullptr) return false;
+  // ranges start at a '>' that follows a line break
+  std::vector<Range> ranges(T);
+  {
+    uint64_t prev = 0;
+    for (unsigned t = 0; t < T; ++t) {
+      uint64_t want = t + 1 == T ? size : size * (t + 1) / T;
+      if (want < prev) want = prev;
+      while (want < size && !(want > 0 && text[want] == '>' && text[want - 1] == '\n')) {
+        const void *g = std::memchr(text + want + 1, '>', size - want - 1);
+        want = g ? static_cast<uint64_t>(static_cast<const char *>(g) - text) : size;
+      }
+      ranges[t].begin = prev; ranges[t].end = want;
+      prev = want;
+    }
+  }
+  run_workers(T, [&](unsigned t) { parse_range(text, ranges[t], t); });
+  uint64_t n64 = 0;
+  for (const Range &R : ranges) { if (!R.ok) return false; n64 += R.entries.size(); }
+  if (n64 == 0 || n64 >= 0xFFFFFFF0ull) return false;
+  const uint32_t n = static_cast<uint32_t>(n64);
+  std::vector<ParEntry> entries;
+  entries.reserve(n);
+  db = AmpliconDb{};
+  for (Range &R : ranges) {
+    entries.insert(entries.end(), R.entries.begin(), R.entries.end());
+    std::vector<ParEntry>().swap(R.entries);
+    db.nucleotides += R.nucleotides;
+    db.longest = std::max(db.longest, R.longest);
+    db.longest_header = std::max(db.longest_header, R.longest_header);
+  }
+  // abundance annotations and identifiers (src/db.cc:286-347,676-758): any irregular record ends the fast path
+  std::atomic<bool> bad{false};
+  run_workers(T, [&](unsigned t) {
+    const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+    for (uint64_t i = lo; i < hi; ++i) {
+      ParEntry &e = entries[i];
+      const char *h = text + e.header_pos;
+      int64_t number = 0; int32_t s = 0, u = 0;
+      const bool found = opt.usearch_abundance ? find_usearch_abundance(h, e.header_len, s, u, number)
+                                               : find_swarm_abundance(h, e.header_len, s, u, number);
+      int64_t abundance = 0;
+      if (found) { if (number <= 0) { bad.store(true); return; } abundance = number; }
+      if (abundance == 0) {
+        s = u = static_cast<int32_t>(e.header_len);
+        if (opt.append_abundance == 0) { bad.store(true); return; }
+        abundance = opt.append_abundance;
+      }
+      if (s == 0 && u == static_cast<int32_t>(e.header_len)) { bad.store(true); return; }
+      e.abundance = static_cast<uint64_t>(abundance);
+      e.ab_start = s; e.ab_end = u;
+    }
+  });
+  if (bad.load()) return false;
+  auto words_of = [&](const ParEntry &e) { return ranges[e.range].packed.data() + e.word_pos; };
+  auto label_of = [&](uint32_t i) {
+    const ParEntry &e = entries[i];
+    const int32_t id_start = e.ab_start > 0 ? 0 : e.ab_end;
+    const int32_t id_len = e.ab_start > 0 ? e.ab_start : static_cast<int32_t>(e.header_len) - e.ab_end;
+    return Key{text + e.header_pos + id_start, static_cast<size_t>(id_len), 0u};
+  };
+  if (!all_distinct(n, T, label_of)) return false;
+  if (opt.check_duplicate_sequences) {                                            // src/db.cc:763-796 (d > 1)
+    auto seq_of = [&](uint32_t i) {
+      const ParEntry &e = entries[i];
+      return Key{words_of(e), static_cast<size_t>((e.len + 31) / 32) * 8, e.len};
+    };
+    if (!all_distinct(n, T, seq_of)) return false;
+  }
+  // order: abundance descending, then header ascending (src/db.cc:392-411)
+  // sort records carry the abundance and the first 8 header bytes (big-endian, zero padded: a shorter header that is
+  // a prefix sorts first, like strcmp) so that almost every comparison is decided without touching the text
+  struct SortRec { uint64_t abundance, prefix; uint32_t idx; };
+  std::vector<SortRec> order(n);
+  auto less = [&](const SortRec &a, const SortRec &b) {
+    if (a.abundance != b.abundance) return a.abundance > b.abundance;
+    if (a.prefix != b.prefix) return a.prefix < b.prefix;
+    const ParEntry &x = entries[a.idx], &y = entries[b.idx];
+    const uint32_t m = std::min(x.header_len, y.header_len);
+    const int c = std::memcmp(text + x.header_pos, text + y.header_pos, m);
+    if (c != 0) return c < 0;
+    return x.header_len < y.header_len;
+  };
+  {
+    run_workers(T, [&](unsigned t) {
+      const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const ParEntry &e = entries[i];
+        uint64_t pfx = 0;
+        for (uint32_t k = 0; k < 8; ++k) pfx = (pfx << 8) | (k < e.header_len ? static_cast<unsigned char>(text[e.header_pos + k]) : 0u);
+        order[i] = SortRec{e.abundance, pfx, static_cast<uint32_t>(i)};
+      }
+    });
+    std::atomic<bool> sorted{true};
+    run_workers(T, [&](unsigned t) {
+      const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = std::min<uint64_t>(n - 1, static_cast<uint64_t>(n) * (t + 1) / T);
+      for (uint64_t i = lo; i < hi && sorted.load(std::memory_order_relaxed); ++i)
+        if (less(order[i + 1], order[i])) sorted.store(false);
+    });
+    if (!sorted.load()) parallel_sort(order, T, less);
+  }
+  // gather into the SoA layout
+  db.n = n;
+  db.stride = std::max<uint32_t>(1, (db.longest + 31) / 32);
+  db.words.assign(static_cast<uint64_t>(n) * db.stride, 0);
+  db.len.resize(n); db.abundance.resize(n); db.ab_start.resize(n); db.ab_end.resize(n);
+  db.header_off.resize(static_cast<uint64_t>(n) + 1);
+  std::vector<uint64_t> part(T + 1, 0);
+  run_workers(T, [&](unsigned t) {
+    const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+    uint64_t b = 0;
+    for (uint64_t i = lo; i < hi; ++i) b += entries[order[i].idx].header_len + 1;
+    part[t + 1] = b;
+  });
+  for (unsigned t = 0; t < T; ++t) part[t + 1] += part[t];
+  db.headers.resize(part[T]);
+  run_workers(T, [&](unsigned t) {
+    const uint64_t lo = static_cast<uint64_t>(n) * t / T, hi = static_cast<uint64_t>(n) * (t + 1) / T;
+    uint64_t hp = part[t];
+    for (uint64_t i = lo; i < hi; ++i) {
+      const ParEntry &e = entries[order[i].idx];
+      db.len[i] = e.len; db.abundance[i] = e.abundance; db.ab_start[i] = e.ab_start; db.ab_end[i] = e.ab_end;
+      std::memcpy(db.words.data() + i * db.stride, words_of(e), static_cast<size_t>((e.len + 31) / 32) * 8);
+      db.header_off[i] = hp;
+      std::memcpy(db.headers.data() + hp, text + e.header_pos, e.header_len);
+      db.headers[hp + e.header_len] = '\0';
+      hp += e.header_len + 1;
+    }
+  });
+  db.header_off[n] = part[T];
+  return true;
+}
+
+}  // namespace
+
+void set_ingest_threads(int threads) { g_threads.store(threads); }
+static uint64_t ingest_min_bytes() {          // SWARM_B200_INGEST_MIN_BYTES: test hook, lets small inputs take the parallel path
+  const char *e = std::getenv("SWARM_B200_INGEST_MIN_BYTES");
+  return e ? std::strtoull(e, nullptr, 10) : (1u << 20);
+}
+
+std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db) {
+  const unsigned T = ingest_threads();
+  if (T > 1 && size >= ingest_min_bytes() && db_parse_parallel(text, size, opt, db, T)) return "";
+  return db_parse_serial(text, size, opt, db);
 }
 
 std::string db_read_file(const std::string &path, const DbOptions &opt, AmpliconDb &db) {

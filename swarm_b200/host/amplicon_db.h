@@ -44,7 +44,11 @@ struct AmpliconDb {
 
 // Parse a FASTA text held in memory.  Returns "" on success, else the reference's error text
 // (without the "\nError: " prefix the caller adds — src/utils/fatal.h:27).
+// Large well-formed inputs are parsed by `set_ingest_threads` workers (0 = hardware concurrency, at most 32; 1 = the
+// serial parser only); the database and every error message are the same either way.
 std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db);
+std::string db_parse_serial(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db);
+void set_ingest_threads(int threads);
 std::string db_read_file(const std::string &path, const DbOptions &opt, AmpliconDb &db);
 
 // id printers (src/db.cc:946-1026)

@@ -60,6 +60,7 @@ int swbh_db_parse(const char *text, uint64_t size, int usearch, int64_t append, 
   *out = h;
   return 0;
 }
+void swbh_set_threads(int threads) { swb::set_ingest_threads(threads); }
 void swbh_db_free(swbh_db *db) { delete db; }
 uint32_t swbh_db_count(const swbh_db *d) { return d->db.n; }
 uint32_t swbh_db_longest(const swbh_db *d) { return d->db.longest; }

@@ -236,6 +236,7 @@ int main(int argc, char **argv) {
   else std::fprintf(logf, "Fastidious:        No\n\n");
 
   // db_read
+  if (used['t' - 'a']) swbh_set_threads(static_cast<int>(P.threads));      // -t bounds the ingest workers; default: all cores
   swbh_db *db = nullptr;
   if (swbh_db_read_fasta(P.input.c_str(), P.usearch ? 1 : 0, P.append_abundance, P.differences > 1 ? 1 : 0, &db) != 0)
     fatal(swbh_last_error());

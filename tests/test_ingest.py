@@ -1,0 +1,121 @@
+"""FASTA ingest: the multi-threaded parser of swarm_b200/host/amplicon_db.cc must build exactly
+the database of the serial one (which mirrors /root/reference src/db.cc and is pinned by the golden tests), and every
+malformed input must end with the serial parser's — i.e. the reference's — message."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN
+from swarm_b200 import HostDb
+from swarm_b200.ffi import host_lib
+
+
+def _parse(text, threads, **kw):
+    L = host_lib()
+    os.environ["SWARM_B200_INGEST_MIN_BYTES"] = "1"          # test hook: small inputs take the parallel path too
+    L.swbh_set_threads(threads)
+    try:
+        try:
+            db = HostDb(text=text, **kw)
+        except ValueError as e:
+            return ("error", str(e))
+        out = ("ok", db.n, db.longest, db.stride, db.nucleotides, db.words.tobytes(), db.len.tobytes(), db.abundance.tobytes(),
+               tuple(db.headers()), db.opts)
+        db.close()
+        return out
+    finally:
+        L.swbh_set_threads(0)
+        os.environ.pop("SWARM_B200_INGEST_MIN_BYTES", None)
+
+
+FASTAS = sorted(p.name for p in GOLDEN.glob("*.fasta"))
+
+
+@pytest.mark.parametrize("name", FASTAS)
+def test_parallel_equals_serial_on_golden_inputs(built, name):
+    text = (GOLDEN / name).read_bytes()
+    kw = {"usearch_abundance": name.startswith("usearch") or name.endswith("_z.fasta")}
+    want = _parse(text, 1, **kw)
+    assert want[0] == "ok"
+    for t in (2, 3, 8):
+        assert _parse(text, t, **kw) == want
+    # d > 1 adds the duplicate-sequence check (src/db.cc:763-796): same verdict from both parsers
+    assert _parse(text, 5, check_dup_sequences=True, **kw) == _parse(text, 1, check_dup_sequences=True, **kw)
+
+
+BAD = [
+    b">a_1\nACGT\n>b_2\nACXT\n",                                  # illegal character
+    b">a_1\nACGT\n>b_2\nAC\x01T\n",                               # illegal non-printable character
+    b">a_1\nACGT\n>b\nACGT\n>c\nAAAA\n",                          # abundance annotations missing
+    b">a_1\nACGT\n>a_2\nACGA\n",                                  # duplicated identifier
+    b">a_1\nACGT\n>b_0\nACGA\n",                                  # illegal abundance
+    b">a_1\nACGT\n>_3\nACGA\n",                                   # empty identifier
+    b">a_1\n>b_2\nACGT\n",                                        # empty sequence
+    b"ACGT\n>b_2\nACGT\n",                                        # no header first
+    b"\n>a_1\nACGT\n",
+    b">a_1\nAC\x00GT\n>b_1\nAAAA\n",                              # NUL byte (C-string semantics of the reference's reader)
+    b">a_1\nACGT\n>b_1\nAC>GT\n",                                 # '>' inside a sequence line
+]
+
+
+@pytest.mark.parametrize("i", range(len(BAD)))
+def test_malformed_inputs_give_the_serial_message(built, i):
+    pad = b"".join(b">p%d_3\nACGTACGTAC\n" % k for k in range(40))       # several ranges, the defect in the middle
+    for text in (BAD[i], pad + BAD[i] + pad.replace(b">p", b">q")):
+        want = _parse(text, 1)
+        for t in (2, 7):
+            assert _parse(text, t) == want
+    assert _parse(BAD[i], 1)[0] in ("error", "ok")
+
+
+def test_duplicate_sequences_only_matter_when_asked(built):
+    text = b">a_3\nACGT\n>b_2\nacgu\n>c_1\nAC\nGT\n"
+    assert _parse(text, 4)[0] == "ok" and _parse(text, 4) == _parse(text, 1)
+    e1, e4 = _parse(text, 1, check_dup_sequences=True), _parse(text, 4, check_dup_sequences=True)
+    assert e1 == e4 and e1[0] == "error" and "identical sequences" in e1[1]
+    # equal packed words, different lengths: not duplicates
+    ok = b">a_3\nA\n>b_2\nAA\n>c_1\nAAA\n"
+    assert _parse(ok, 3, check_dup_sequences=True) == _parse(ok, 1, check_dup_sequences=True) and _parse(ok, 3, check_dup_sequences=True)[0] == "ok"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_layouts_and_range_boundaries(built, seed):
+    """records with wrapped sequence lines, CRLF, blank lines, '>' and spaces inside header lines, no final newline:
+    every split of the text into worker ranges must give the serial database"""
+    rng = random.Random(seed)
+    recs = []
+    for k in range(rng.randint(30, 400)):
+        L = rng.choice([1, 2, 31, 32, 33, 64, 65, rng.randint(1, 200)])
+        s = "".join(rng.choice("ACGTacgtUu") for _ in range(L))
+        w = rng.choice([L, 7, 60, 1])
+        nl = rng.choice(["\n", "\n", "\r\n"])
+        lines = nl.join(s[i:i + w] for i in range(0, L, w))
+        if rng.random() < 0.1:
+            lines += nl                                              # a blank line inside the record
+        hdr = f"x{k}{rng.choice(['', 'y>z', '-'])}_{rng.choice([1, 1, 2, 9, 9, 500])}{rng.choice(['', ' desc > more', ' t'])}"
+        recs.append(f">{hdr}{nl}{lines}{nl}")
+    text = "".join(recs)
+    if seed % 2:
+        text = text.rstrip("\r\n")
+    text = text.encode()
+    want = _parse(text, 1)
+    assert want[0] == "ok"
+    for t in (2, 3, 5, 8, 13):
+        assert _parse(text, t) == want
+
+
+def test_large_input_takes_the_parallel_path_by_default(built, tmp_path):
+    fa = tmp_path / "big.fa"
+    helpers.make_fasta(fa, 20000, 100, 3)                             # > 1 MiB: parallel without the test hook
+    text = fa.read_bytes()
+    assert len(text) > (1 << 20)
+    L = host_lib()
+    L.swbh_set_threads(1)
+    a = HostDb(fa)
+    L.swbh_set_threads(0)
+    b = HostDb(fa)
+    assert a.n == b.n == 20000 and np.array_equal(a.words, b.words) and np.array_equal(a.len, b.len)
+    assert np.array_equal(a.abundance, b.abundance) and a.headers() == b.headers()
