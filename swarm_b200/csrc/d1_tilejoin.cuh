@@ -54,8 +54,8 @@ struct TileJoinParams {
   uint32_t *dup_flag;
   uint2 *plist_ent;                 // multi-GPU: (entry lo, entry hi) and ...
   uint32_t *plist_tile;             // ... local tile of every piece this rank owns, appended by the counting pass
-  unsigned long long *plist_n;
-  uint64_t plist_cap;
+  unsigned long long *plist_n;      // kPlistSubs counters, kPlistPad words apart: CTA b appends to sub-list b % kPlistSubs
+  uint64_t plist_cap;               // capacity of ONE sub-list
   unsigned long long *stats;        // [0] entries joined [1] same-key pairs [2] pairs enumerated [3] exact comparisons [4] rows gathered
 };
 
@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(256) k_tile_partition(TileJoinParams J) {
   }
 }
 
+// the kept pieces go to kPlistSubs sub-lists with their own counters: one counter for every warp of the scan serialised
+// on a single L2 address (index at 2 x 10 M: 0.67 -> 1.10 ms, gpurun_out/r1n_call7)
+constexpr uint32_t kPlistSubs = 64, kPlistPad = 16;
+
 // Multi-GPU flavour of the two passes: a rank owns 1/world of the tiles but has to hash ALL amplicons to find its
 // pieces, so the counting pass also appends the pieces it keeps to a list and the second pass scatters that list
 // instead of hashing everything again (index at 8 x 10 M: the part that does not scale).
@@ -131,17 +135,21 @@ __global__ void __launch_bounds__(256) k_tile_partition_list(TileJoinParams J) {
   const uint32_t tot = __popc(b0) + __popc(b1);
   if (tot == 0) return;
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(J.plist_n, static_cast<unsigned long long>(tot));
+  const uint32_t sub = blockIdx.x % kPlistSubs;
+  if (lane == 0) base = atomicAdd(&J.plist_n[sub * kPlistPad], static_cast<unsigned long long>(tot));
   base = shfl_u64(base, 0);
   const uint32_t lt = (1u << lane) - 1u;
   const unsigned long long i0 = base + __popc(b0 & lt), i1 = base + __popc(b0) + __popc(b1 & lt);
-  if (t[0] != kNone && i0 < J.plist_cap) { J.plist_ent[i0] = make_uint2(static_cast<uint32_t>(e[0]), static_cast<uint32_t>(e[0] >> 32)); J.plist_tile[i0] = t[0]; }
-  if (t[1] != kNone && i1 < J.plist_cap) { J.plist_ent[i1] = make_uint2(static_cast<uint32_t>(e[1]), static_cast<uint32_t>(e[1] >> 32)); J.plist_tile[i1] = t[1]; }
+  const uint64_t at = static_cast<uint64_t>(sub) * J.plist_cap;
+  if (t[0] != kNone && i0 < J.plist_cap) { J.plist_ent[at + i0] = make_uint2(static_cast<uint32_t>(e[0]), static_cast<uint32_t>(e[0] >> 32)); J.plist_tile[at + i0] = t[0]; }
+  if (t[1] != kNone && i1 < J.plist_cap) { J.plist_ent[at + i1] = make_uint2(static_cast<uint32_t>(e[1]), static_cast<uint32_t>(e[1] >> 32)); J.plist_tile[at + i1] = t[1]; }
 }
 
-__global__ void __launch_bounds__(256) k_tile_scatter_list(TileJoinParams J, uint64_t m) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= m) return;
+// grid (ceil(longest sub-list / 256), kPlistSubs)
+__global__ void __launch_bounds__(256) k_tile_scatter_list(TileJoinParams J) {
+  const uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= J.plist_n[blockIdx.y * kPlistPad]) return;
+  const uint64_t i = static_cast<uint64_t>(blockIdx.y) * J.plist_cap + k;
   const uint32_t t = J.plist_tile[i];
   const uint2 e = J.plist_ent[i];
   const uint32_t pos = atomicAdd(&J.tile_cursor[t], 1u);

@@ -142,6 +142,7 @@ struct swb200_ctx {
   DevBuf<unsigned long long> tj_off, tj_entries;
   DevBuf<uint2> tj_plist_ent;
   DevBuf<uint32_t> tj_plist_tile;
+  DevBuf<unsigned long long> tj_plist_cnt;
   uint32_t tj_tiles = 0, tj_lo = 0, tj_hi = 0, tj_cmax = 0;
   uint32_t tj_cmax_override = 0;     // test hook: pretend shared memory holds fewer entries (exercises k_tile_join_big)
   unsigned long long tj_total = 0;
@@ -257,7 +258,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->dist_lcnt.release(); c->dist_links.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
-  c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release();
+  c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -481,28 +482,31 @@ int swb200_d1_index(swb200_ctx *c) {
     unsigned long long total = 0;
     if (T) {
       const bool use_list = c->shard_world > 1;          // hash every amplicon once, keep the pieces of this rank's tiles in a list
-      unsigned long long listed = 0;
+      unsigned long long listed[kPlistSubs * kPlistPad];
       if (use_list) {
-        const uint64_t cap = static_cast<uint64_t>(c->n) * 2 / c->shard_world * 5 / 4 + (1u << 16);
-        c->tj_plist_ent.alloc(cap); c->tj_plist_tile.alloc(cap);
+        // capacity of a sub-list: its share of the rank's expected pieces + 25 % + slack
+        const uint64_t cap = (static_cast<uint64_t>(c->n) * 2 / c->shard_world * 5 / 4 + (1u << 16)) / kPlistSubs + 1024;
+        c->tj_plist_ent.alloc(cap * kPlistSubs); c->tj_plist_tile.alloc(cap * kPlistSubs); c->tj_plist_cnt.alloc(kPlistSubs * kPlistPad);
         J.plist_ent = c->tj_plist_ent.p; J.plist_tile = c->tj_plist_tile.p; J.plist_cap = cap;
-        J.plist_n = c->counters.p + 21;
-        CK(cudaMemsetAsync(c->counters.p + 21, 0, 8, c->stream));
+        J.plist_n = c->tj_plist_cnt.p;
+        CK(cudaMemsetAsync(c->tj_plist_cnt.p, 0, sizeof listed, c->stream));
         k_tile_partition_list<<<pb, 256, 0, c->stream>>>(J);
       } else {
         k_tile_partition<true><<<pb, 256, 0, c->stream>>>(J);
       }
       k_tile_scan<<<1, 1024, 0, c->stream>>>(J);
       CK(cudaMemcpyAsync(&total, c->tj_off.p + T, 8, cudaMemcpyDeviceToHost, c->stream));
-      if (use_list) CK(cudaMemcpyAsync(&listed, c->counters.p + 21, 8, cudaMemcpyDeviceToHost, c->stream));
+      if (use_list) CK(cudaMemcpyAsync(listed, c->tj_plist_cnt.p, sizeof listed, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       c->tj_total = total;
       c->tj_entries.alloc(std::max<unsigned long long>(total, 1));
       J.entries = c->tj_entries.p;
-      if (use_list && listed <= J.plist_cap) {
-        if (listed) k_tile_scatter_list<<<static_cast<unsigned>((listed + 255) / 256), 256, 0, c->stream>>>(J, listed);
+      unsigned long long longest_list = 0;
+      if (use_list) for (uint32_t s = 0; s < kPlistSubs; ++s) longest_list = std::max(longest_list, listed[s * kPlistPad]);
+      if (use_list && longest_list <= J.plist_cap) {
+        if (longest_list) k_tile_scatter_list<<<dim3(static_cast<unsigned>((longest_list + 255) / 256), kPlistSubs), 256, 0, c->stream>>>(J);
       } else {
-        k_tile_partition<false><<<pb, 256, 0, c->stream>>>(J);      // single GPU, or the list overflowed (a very skewed hash range)
+        k_tile_partition<false><<<pb, 256, 0, c->stream>>>(J);      // single GPU, or a sub-list overflowed (a very skewed hash range)
       }
       CK(cudaGetLastError());
       c->launches += 3;

@@ -58,17 +58,19 @@ struct Aligner {
         const uint64_t h_above = h[c];
         uint64_t left = e[c];
         uint64_t best = diag + (dn == q[c] ? 0 : mismatch);
-        uint8_t f = up < best ? kUp : 0;
+        // the four decisions of the cell as flag arithmetic (no data-dependent branches: on real sequences they are
+        // unpredictable and cost more than the arithmetic)
+        uint32_t f = static_cast<uint32_t>(up < best);                                  // kUp
         best = std::min(best, std::min(up, left));
-        if (left == best) f |= kLeft;
+        f |= static_cast<uint32_t>(left == best) << 1;                                  // kLeft
         h[c] = best;
         const uint64_t opened = best + go + ge;
         left += ge; up += ge;
-        if (up < opened) f |= kExtUp;
-        if (left < opened) f |= kExtLeft;
+        f |= static_cast<uint32_t>(up < opened) << 2;                                   // kExtUp
+        f |= static_cast<uint32_t>(left < opened) << 3;                                 // kExtLeft
         up = std::min(up, opened);
         e[c] = std::min(left, opened);
-        row[c] = f;
+        row[c] = static_cast<uint8_t>(f);
         diag = h_above;
       }
     }
