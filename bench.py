@@ -7,8 +7,9 @@
 A "step" is one pass of the d=1 hot path (index -> network -> cluster) over one synthetic amplicon
 set (BASELINE.md §3.2 generator, seed 42).  N=1 workload = BASELINE.json configs[1]: 10 M x 150 bp.
   value : whole-job amplicons/s with the packed database already resident in HBM (device path only)
-  e2e   : the same metric through the C ABI with HOST buffers: swb200_load_db (H2D from pinned host
-          memory) + index + network + cluster + D2H of the three result arrays, every step
+  e2e   : the same metric through the C ABI with HOST buffers: swb200_load_db_compact (H2D from pinned host
+          memory: packed words, u16 lengths, abundance runs — 420 MB instead of swb200_load_db's 520 MB at 10 M)
+          + index + network + cluster + D2H of the three result arrays, every step
   roofline     : the network kernel, algorithmic bytes per launch (SURVEY.md §8d formula) / CUDA-event time
   cpu_baseline : oracle/_ref/swarm_timed (the unmodified reference + phase timers) on a bounded sample
 N>1 (torchrun, one rank per GPU), weak scaling: ONE clustering job of N x --amplicons amplicons.  Every GPU holds
@@ -272,6 +273,11 @@ def main():
         pw[:], pl[:], pa[:] = db.words, db.len, db.abundance
         db.close()
         eng.load_db(pw, stride, pl, pa)
+        # the compact form of the same database (u16 lengths, abundance runs): what the end-to-end path uploads
+        from swarm_b200.ffi import compact_form
+        l16, rab, rst = compact_form(pl, pa)
+        pl16, prab, prst = pinned(n, torch.int16).view(np.uint16), pinned(rab.shape[0], torch.int64).view(np.uint64), pinned(rst.shape[0], torch.int32).view(np.uint32)
+        pl16[:], prab[:], prst[:] = l16, rab, rst
     else:
         W, Ln, Ab, stride = build_weak_dataset(args, rank, world)
         n = W.shape[0]
@@ -289,7 +295,7 @@ def main():
     own_ids = dist_row_ids(n, rank, world) if dist_mode else np.arange(first, first + count, dtype=np.uint32)
     res = {k: pinned(own_ids.shape[0], torch.int32).view(np.uint32) for k in ("swarm_of", "generation", "parent")}
     res_gc = pinned(own_ids.shape[0], torch.int32).view(np.uint32)
-    h2d = pw.nbytes + pl.nbytes + pa.nbytes
+    h2d = (pw.nbytes + pl16.nbytes + prab.nbytes + prst.nbytes) if world == 1 else (pw.nbytes + pl.nbytes + pa.nbytes)
     d2h = (4 if args.fastidious else 3) * 4 * own_ids.shape[0]
     ext = engine_stream(eng)
     if dist_mode:
@@ -308,7 +314,7 @@ def main():
 
     def e2e_step():
         if world == 1:
-            eng.load_db(pw, stride, pl, pa)
+            eng.load_db_compact(pw, stride, pl16, prab, prst)
         else:
             eng.load_db_shard(pw, stride, pl, pa, n, first)
             all_gather_db(eng, n, stride)
@@ -424,7 +430,8 @@ def main():
                           "cluster": 1e3 * sum(phase[3]) / len(phase[3]),
                           "fastidious": (1e3 * sum(phase[4]) / len(phase[4])) if args.fastidious else None},
             "e2e": {"value": n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": 1e3 * dt_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+                    "ms_per_step": 1e3 * dt_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
+                    "api": ("swb200_load_db_compact" if world == 1 else "swb200_load_db_shard + all-gather") + " -> d1_index -> d1_network -> d1_cluster(host arrays)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

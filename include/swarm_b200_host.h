@@ -33,6 +33,9 @@ const uint64_t *swbh_db_words(const swbh_db *db);     /* db_getsequence  (fixed 
 const uint32_t *swbh_db_lengths(const swbh_db *db);   /* db_getsequencelen                        */
 const uint64_t *swbh_db_abundances(const swbh_db *db);/* db_getabundance                          */
 const char *swbh_db_header(const swbh_db *db, uint32_t i);  /* db_getheader                       */
+/* the arguments of swb200_load_db_compact(): 16-bit lengths + abundance runs (built on first use, owned by db).
+ * Returns n_runs, or 0 when a sequence is longer than 65 535 nt (use swb200_load_db then). */
+uint32_t swbh_db_compact(swbh_db *db, const uint16_t **len16, const uint64_t **run_abundance, const uint32_t **run_start);
 
 /* d=1 result assembly + writers (src/algod1.cc:791-815 `-o`, :1043-1062 `-s`, :990-1040 `-i`,
  * :755-788 `-j`, :937-987 `-w`, :818-849 `-r`).  Inputs are the engine's outputs: swarm_of /

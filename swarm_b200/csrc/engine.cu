@@ -75,6 +75,22 @@ uint64_t table_slots(uint64_t n) {
 
 }  // namespace
 
+// expansion kernels of swb200_load_db_compact: 16-bit lengths -> u32, abundance runs -> one value per amplicon
+__global__ void __launch_bounds__(256) k_expand_len16(const uint16_t *in, uint32_t *out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void __launch_bounds__(256) k_expand_runs(const uint64_t *value, const uint32_t *start, uint32_t n_runs, uint64_t *out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t lo = 0, hi = n_runs;                          // last run with start[run] <= i
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (start[mid] <= i) lo = mid; else hi = mid;
+  }
+  out[i] = value[lo];
+}
+
 struct swb200_ctx {
   int device = 0;
   int sm_count = 148;
@@ -152,6 +168,10 @@ struct swb200_ctx {
   DevBuf<uint32_t> qgrams, ediff, dirs, pdiff;
   DevBuf<uint2> tasks;
   uint64_t dnstats[4] = {0, 0, 0, 0};
+  // compact loader staging
+  DevBuf<uint16_t> ld_len16;
+  DevBuf<uint64_t> ld_run_value;
+  DevBuf<uint32_t> ld_run_start;
   // d = 0
   DevBuf<unsigned long long> dr_table, dr_mass;
   DevBuf<uint32_t> dr_slot, dr_rep, dr_size, dr_single;
@@ -259,6 +279,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
+  c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -387,6 +408,34 @@ int swb200_load_db(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, 
   db_upload(c, c->words.p, words, static_cast<size_t>(n) * stride_words * 8);
   db_upload(c, c->len.p, len, static_cast<size_t>(n) * 4);
   db_upload(c, c->abundance.p, abundance, static_cast<size_t>(n) * 8);
+  return db_finalize(c);
+  API_END()
+}
+
+// same database as swb200_load_db from fewer host bytes: lengths as u16, abundances as runs (the database is sorted by
+// abundance, so a run is one distinct value): 10 M x 150 bp = 420 MB over PCIe instead of 520 MB
+int swb200_load_db_compact(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint16_t *len16,
+                           const uint64_t *run_abundance, const uint32_t *run_start, uint32_t n_runs, uint32_t n) {
+  API_BEGIN(c)
+  if (!words || !len16 || !run_abundance || !run_start || n == 0 || n_runs == 0 || n_runs > n || stride_words == 0) {
+    g_err = "load_db_compact: bad argument";
+    return SWB200_EINVAL;
+  }
+  if (n >= 0xFFFFFFF0u) { g_err = "load_db_compact: too many amplicons"; return SWB200_EINVAL; }
+  if (run_start[0] != 0 || run_start[n_runs] != n) { g_err = "load_db_compact: runs must cover [0, n)"; return SWB200_EINVAL; }
+  for (uint32_t r = 0; r < n_runs; ++r)
+    if (run_start[r] >= run_start[r + 1]) { g_err = "load_db_compact: empty or unordered run"; return SWB200_EINVAL; }
+  db_alloc(c, n, stride_words);
+  c->ld_len16.alloc(n); c->ld_run_value.alloc(n_runs); c->ld_run_start.alloc(static_cast<size_t>(n_runs) + 1);
+  c->tic();
+  db_upload(c, c->ld_len16.p, len16, static_cast<size_t>(n) * 2);
+  db_upload(c, c->ld_run_value.p, run_abundance, static_cast<size_t>(n_runs) * 8);
+  db_upload(c, c->ld_run_start.p, run_start, (static_cast<size_t>(n_runs) + 1) * 4);
+  const unsigned blocks = (n + 255) / 256;
+  k_expand_len16<<<blocks, 256, 0, c->stream>>>(c->ld_len16.p, c->len.p, n);
+  k_expand_runs<<<blocks, 256, 0, c->stream>>>(c->ld_run_value.p, c->ld_run_start.p, n_runs, c->abundance.p, n);
+  c->launches += 2;
+  db_upload(c, c->words.p, words, static_cast<size_t>(n) * stride_words * 8);
   return db_finalize(c);
   API_END()
 }

@@ -51,6 +51,7 @@ def engine_lib():
         L.swb200_destroy.restype = None
         L.swb200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         L.swb200_load_db.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32]
+        L.swb200_load_db_compact.argtypes = [vp, _u64p, C.c_uint32, C.POINTER(C.c_uint16), _u64p, _u32p, C.c_uint32, C.c_uint32]
         L.swb200_load_db_shard.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.swb200_db_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.swb200_db_commit.argtypes = [vp]
@@ -156,6 +157,15 @@ def host_lib():
         del cpp
         _host_lib = L
     return _host_lib
+
+
+def compact_form(lengths, abundance):
+    """(len16, run_abundance, run_start) of a database sorted by abundance: the arguments of swb200_load_db_compact"""
+    lengths = np.asarray(lengths)
+    abundance = np.ascontiguousarray(abundance, dtype=np.uint64)
+    assert lengths.max(initial=0) <= 65535
+    starts = np.flatnonzero(np.concatenate(([True], abundance[1:] != abundance[:-1]))).astype(np.uint32)
+    return lengths.astype(np.uint16), abundance[starts].copy(), np.concatenate((starts, [abundance.shape[0]])).astype(np.uint32)
 
 
 class HostDb:
@@ -399,6 +409,14 @@ class Engine:
         assert words.shape[0] == n * stride and abundance.shape[0] == n
         self._ck(engine_lib().swb200_load_db(self._h, _ptr(words, _u64p), int(stride), _ptr(lengths, _u32p),
                                             _ptr(abundance, _u64p), n))
+        self.n = n
+
+    def load_db_compact(self, words, stride, len16, run_abundance, run_start):
+        """swb200_load_db_compact: u16 lengths + abundance runs (see compact_form)"""
+        n = len16.shape[0]
+        assert words.shape[0] == n * stride and len16.dtype == np.uint16 and run_start.shape[0] == run_abundance.shape[0] + 1
+        self._ck(engine_lib().swb200_load_db_compact(self._h, _ptr(words, _u64p), int(stride), len16.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                    _ptr(run_abundance, _u64p), _ptr(run_start, _u32p), int(run_abundance.shape[0]), n))
         self.n = n
 
     def load_db_shard(self, words, stride, lengths, abundance, n_total, first):

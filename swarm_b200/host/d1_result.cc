@@ -72,6 +72,24 @@ const uint64_t *swbh_db_abundances(const swbh_db *d) { return d->db.abundance.da
 const char *swbh_db_header(const swbh_db *d, uint32_t i) { return d->db.header(i); }
 void swbh_free(void *p) { std::free(p); }
 
+// the arguments of swb200_load_db_compact(): 16-bit lengths and abundance runs.  Returns the number of runs, or 0 when
+// the database cannot be expressed that way (a sequence longer than 65 535 nt) — the caller then uses swb200_load_db.
+uint32_t swbh_db_compact(swbh_db *d, const uint16_t **len16, const uint64_t **run_abundance, const uint32_t **run_start) {
+  const swb::AmpliconDb &db = d->db;
+  if (db.n == 0 || db.longest > 65535) return 0;
+  if (d->len16.size() != db.n) {
+    d->len16.resize(db.n);
+    d->run_abundance.clear(); d->run_start.clear();
+    for (uint32_t i = 0; i < db.n; ++i) {
+      d->len16[i] = static_cast<uint16_t>(db.len[i]);
+      if (i == 0 || db.abundance[i] != db.abundance[i - 1]) { d->run_abundance.push_back(db.abundance[i]); d->run_start.push_back(i); }
+    }
+    d->run_start.push_back(db.n);
+  }
+  *len16 = d->len16.data(); *run_abundance = d->run_abundance.data(); *run_start = d->run_start.data();
+  return static_cast<uint32_t>(d->run_abundance.size());
+}
+
 int swbh_d1_assemble(const swbh_db *dbh, const uint32_t *swarm_of, const uint32_t *generation, const uint32_t *parent,
                      const uint32_t *graft_cand, uint64_t boundary, swbh_result **out) {
   (void)boundary;

@@ -250,7 +250,12 @@ int main(int argc, char **argv) {
     swb200_ctx *ctx = nullptr;
     const char *dev = std::getenv("SWARM_B200_DEVICE");
     engine_check(swb200_create(&ctx, dev ? std::atoi(dev) : 0));
-    engine_check(swb200_load_db(ctx, swbh_db_words(db), swbh_db_stride_words(db), swbh_db_lengths(db), swbh_db_abundances(db), n));
+    {
+      const uint16_t *len16 = nullptr; const uint64_t *run_ab = nullptr; const uint32_t *run_start = nullptr;
+      const uint32_t runs = swbh_db_compact(db, &len16, &run_ab, &run_start);
+      if (runs != 0) engine_check(swb200_load_db_compact(ctx, swbh_db_words(db), swbh_db_stride_words(db), len16, run_ab, run_start, runs, n));
+      else engine_check(swb200_load_db(ctx, swbh_db_words(db), swbh_db_stride_words(db), swbh_db_lengths(db), swbh_db_abundances(db), n));
+    }
     if (P.differences == 0) {                                  // dereplicate, src/derep.cc:393-418
       std::vector<uint32_t> rep(n), size(n), singles(n);
       std::vector<uint64_t> mass(n);

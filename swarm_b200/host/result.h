@@ -8,6 +8,10 @@
 
 struct swbh_db {
   swb::AmpliconDb db;
+  // the compact form swb200_load_db_compact() takes, built on first use
+  std::vector<uint16_t> len16;
+  std::vector<uint64_t> run_abundance;
+  std::vector<uint32_t> run_start;
 };
 
 struct swbh_result {

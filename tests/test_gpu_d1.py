@@ -458,3 +458,44 @@ def test_dist_clustering_world2(built, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("dist ok") == 2
+
+
+@pytest.mark.parametrize("name", ["handmade", "tie_1500_60", "c1_1k_150"])
+def test_compact_loader_gives_the_same_database(built, name):
+    """swb200_load_db_compact (u16 lengths + abundance runs, expanded on the device) == swb200_load_db: same links,
+    same clustering, same grafts (the fastidious pass reads the abundances again for the swarm masses)"""
+    from swarm_b200.ffi import compact_form
+    db = HostDb(GOLDEN / f"{name}.fasta")
+    outs = []
+    for compact in (False, True):
+        eng = Engine(0)
+        if compact:
+            l16, rab, rst = compact_form(db.len, db.abundance)
+            assert rst[0] == 0 and rst[-1] == db.n and len(rab) == len(np.unique(db.abundance))
+            eng.load_db_compact(np.ascontiguousarray(db.words), db.stride, l16, rab, rst)
+        else:
+            eng.load(db)
+        eng.d1_index()
+        eng.d1_network()
+        links = eng.d1_export_links()
+        links = links[np.lexsort((links[:, 1], links[:, 0]))]
+        sw, gen, par = eng.d1_cluster()
+        gc, nl, nh = eng.d1_fastidious(boundary=3)
+        outs.append((links, sw, gen, par, gc, nl, nh))
+        eng.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    res = D1Result(db, outs[1][1], outs[1][2], outs[1][3], graft_cand=outs[1][4] if outs[1][5] and outs[1][6] else None)
+    assert res.swarms_text() == (GOLDEN / f"{name}.f.o").read_bytes()
+
+
+def test_compact_loader_rejects_bad_runs(built):
+    db = HostDb(GOLDEN / "handmade.fasta")
+    eng = Engine(0)
+    l16 = db.len.astype(np.uint16)
+    w = np.ascontiguousarray(db.words)
+    for rst in ([1, db.n], [0, db.n - 1], [0, 5, 5, db.n], [0, 7, 3, db.n]):
+        rst = np.array(rst, dtype=np.uint32)
+        with pytest.raises(EngineError):
+            eng.load_db_compact(w, db.stride, l16, np.ones(len(rst) - 1, dtype=np.uint64), rst)
+    eng.close()

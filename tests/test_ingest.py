@@ -119,3 +119,22 @@ def test_large_input_takes_the_parallel_path_by_default(built, tmp_path):
     b = HostDb(fa)
     assert a.n == b.n == 20000 and np.array_equal(a.words, b.words) and np.array_equal(a.len, b.len)
     assert np.array_equal(a.abundance, b.abundance) and a.headers() == b.headers()
+
+
+def test_compact_form_of_the_database(built):
+    """swbh_db_compact (host C ABI) == ffi.compact_form (numpy): u16 lengths + abundance runs that expand to the arrays"""
+    import ctypes as C
+    from swarm_b200.ffi import compact_form
+    L = host_lib()
+    L.swbh_db_compact.restype = C.c_uint32
+    L.swbh_db_compact.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint32))]
+    for name in ("tie_1500_60", "c1_1k_150", "handmade"):
+        db = HostDb(GOLDEN / f"{name}.fasta")
+        p16, pab, pst = C.POINTER(C.c_uint16)(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
+        runs = L.swbh_db_compact(db._h, C.byref(p16), C.byref(pab), C.byref(pst))
+        l16, rab, rst = compact_form(db.len, db.abundance)
+        assert runs == len(rab)
+        assert np.array_equal(np.ctypeslib.as_array(p16, shape=(db.n,)), l16)
+        assert np.array_equal(np.ctypeslib.as_array(pab, shape=(runs,)), rab)
+        assert np.array_equal(np.ctypeslib.as_array(pst, shape=(runs + 1,)), rst)
+        assert np.array_equal(np.repeat(rab, np.diff(rst.astype(np.int64))), db.abundance)
