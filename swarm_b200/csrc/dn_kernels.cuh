@@ -303,6 +303,107 @@ __global__ void __launch_bounds__(128) k_dn_align(DnParams P, uint64_t task0, ui
   }
 }
 
+// ---- the same aligner for ANY band half-width (d > 6 with the default scoring: w > 15) ------------------------------
+// k_dn_align keeps the band of a row in registers, which stops at w = 15.  Here the previous row's H and E live in a
+// per-thread global scratch indexed by COLUMN (interleaved over threads, so a warp's accesses coalesce) and the four
+// direction flags of cell (r, c) go to nibble c of row r: the recurrence, the boundary values, the band rule (cells
+// outside |c - r| <= w are infinite, the band argument of DESIGN.md §3.6 makes that exact for every accepted pair) and
+// the backtrack are the ones of k_dn_align; with w >= the sequence length this is the full matrix of src/nw.cc.
+// Slower per cell (two loads and two stores), used only where the register kernel cannot go.
+__global__ void __launch_bounds__(128) k_dn_align_wide(DnParams P, int32_t *hrow, int32_t *erow, uint64_t task0, uint64_t ntasks) {
+  const uint64_t gtid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t nthreads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const int w = static_cast<int>(P.w);
+  const int32_t go = P.gapopen, ge = P.gapextend, mis = P.mismatch;
+  unsigned long long pruned = 0, done_cnt = 0;
+  for (uint64_t task = task0 + gtid; task < task0 + ntasks; task += nthreads) {
+    const uint2 tk = P.tasks[task];
+    const uint32_t qid = tk.x, tid = tk.y;
+    const int qlen = static_cast<int>(P.len[qid]), dlen = static_cast<int>(P.len[tid]);
+    const uint64_t *qw = P.words + static_cast<uint64_t>(qid) * P.stride;
+    const uint64_t *tw = P.words + static_cast<uint64_t>(tid) * P.stride;
+    done_cnt++;
+    for (int c = 0; c < qlen; ++c) {                       // "row -1": the DP boundary (src/nw.cc:64-68), inside its band
+      const bool ok = c <= w;
+      hrow[static_cast<uint64_t>(c) * nthreads + gtid] = ok ? go + (c + 1) * ge : kDnInf;
+      erow[static_cast<uint64_t>(c) * nthreads + gtid] = ok ? 2 * go + (c + 2) * ge : kDnInf;
+    }
+    bool reject = false;
+    for (int r = 0; r < dlen; ++r) {
+      const uint32_t tb = base_at(tw, static_cast<uint32_t>(r));
+      const int c_lo = max(0, r - w), c_hi = min(qlen - 1, r + w);
+      int32_t top, diagonal;
+      if (r - w <= 0) {                                    // true left boundary (src/nw.cc:75-76)
+        top = 2 * go + (r + 2) * ge;
+        diagonal = r == 0 ? 0 : go + r * ge;
+      } else {
+        top = kDnInf;                                      // cell (r, c_lo - 1) is outside the band
+        diagonal = hrow[static_cast<uint64_t>(c_lo - 1) * nthreads + gtid];   // H(r-1, c_lo-1)
+      }
+      int32_t rowmin = kDnInf;
+      uint32_t dw = 0;
+      for (int c = c_lo; c <= c_hi; ++c) {
+        const uint64_t at = static_cast<uint64_t>(c) * nthreads + gtid;
+        const int32_t prevdiag = hrow[at];                 // H(r-1, c)
+        int32_t left = erow[at];                           // E(r-1, c)
+        diagonal += (base_at(qw, static_cast<uint32_t>(c)) == tb) ? 0 : mis;
+        uint32_t f = 0;
+        if (top < diagonal) { f |= 1u; diagonal = top; }
+        if (left < diagonal) diagonal = left;
+        if (left == diagonal) f |= 2u;
+        hrow[at] = diagonal;
+        rowmin = min(rowmin, diagonal);
+        diagonal += go + ge;
+        left += ge;
+        top += ge;
+        if (top < diagonal) f |= 4u;
+        if (left < diagonal) f |= 8u;
+        top = min(diagonal, top);
+        left = min(diagonal, left);
+        erow[at] = left;
+        diagonal = prevdiag;
+        dw |= f << ((c & 7) * 4);
+        if ((c & 7) == 7 || c == c_hi) {
+          P.dirs[(static_cast<uint64_t>(r) * P.dir_words + (c >> 3)) * nthreads + gtid] = dw;
+          dw = 0;
+        }
+      }
+      if (c_lo > c_hi || rowmin > P.bound) { reject = true; pruned++; break; }
+    }
+    if (reject) continue;
+    if (abs(qlen - dlen) > w) continue;                    // the corner cell is outside the band
+    if (hrow[static_cast<uint64_t>(qlen - 1) * nthreads + gtid] > P.bound) continue;
+    // backtrack (src/nw.cc:133-187)
+    int column = qlen, row = dlen;
+    uint32_t alength = 0, matches = 0;
+    int op = 0;                                            // 0 none, 1 'I', 2 'D', 3 'M'
+    while (column > 0 && row > 0) {
+      const int r = row - 1, c = column - 1;
+      const uint32_t wv = P.dirs[(static_cast<uint64_t>(r) * P.dir_words + (c >> 3)) * nthreads + gtid];
+      const uint32_t cell = (wv >> ((c & 7) * 4)) & 15u;
+      ++alength;
+      if (op == 1 && (cell & 8u)) { --row; }
+      else if (op == 2 && (cell & 4u)) { --column; }
+      else if (cell & 2u) { --row; op = 1; }
+      else if (cell & 1u) { --column; op = 2; }
+      else {
+        if (base_at(qw, static_cast<uint32_t>(c)) == base_at(tw, static_cast<uint32_t>(r))) ++matches;
+        --column; --row; op = 3;
+      }
+    }
+    alength += static_cast<uint32_t>(column + row);
+    const uint32_t diffs = alength - matches;
+    if (diffs <= P.d) {
+      const unsigned long long at = atomicAdd(P.edge_count, 1ull);
+      if (at < P.edge_cap) { P.edges[at] = make_uint2(qid, tid); P.ediff[at] = diffs; }
+    }
+  }
+  if (P.stats) {
+    if (done_cnt) atomicAdd(&P.stats[1], done_cnt);
+    if (pruned) atomicAdd(&P.stats[2], pruned);
+  }
+}
+
 // ---- candidate generation by pigeonhole join (preferred; the all-pairs k_dn_filter is the fallback) --------
 // <= d differences leave at least one of d+1 disjoint pieces of t untouched: P_j = t[jK,(j+1)K) for j < d and
 // the suffix piece t[Lt-K, Lt), K = min(64, minlen/(d+1)).  Every amplicon stores its d+1 piece hashes; every

@@ -137,6 +137,7 @@ struct swb200_ctx {
   uint32_t max_len = 0, min_len = 0;
   uint32_t minmax[2] = {0, 0};
   uint32_t unsorted = 0;
+  bool too_long = false;             // longest sequence > 5 000 nt: d = 0 only
   bool db_pending = false;           // rows uploaded by load_db_shard, exchange + db_commit still due
   bool sorted_desc = false;          // abundances never increase with the id (the reference's order, src/db.cc:392-406)
   int cluster_kernel = 0; // 0 fused key relaxation of the frontier, one persistent cooperative kernel; 3 the same over links first sorted by
@@ -337,10 +338,8 @@ static int db_finalize(swb200_ctx *c) {
   // (every hit is verified exactly).
   c->longest = stride_words * 32;
   c->zlen = c->longest + 2;
-  if (static_cast<size_t>(c->zlen) * 32 > 160 * 1024) {
-    g_err = "sequences longer than 5,000 nt are not supported by the on-chip Zobrist table";
-    return SWB200_EUNSUPPORTED;
-  }
+  // the clustering kernels keep per-position tables on chip; dereplication (d = 0) has no such limit
+  c->too_long = static_cast<size_t>(c->zlen) * 32 > 160 * 1024;
   {
     CK(cudaMemsetAsync(c->counters.p + 15, 0, 8, c->stream));
     k_minmax_u32<<<c->sm_count * 2, 256, 0, c->stream>>>(c->len.p, n, reinterpret_cast<uint32_t *>(c->counters.p + 15));
@@ -350,7 +349,7 @@ static int db_finalize(swb200_ctx *c) {
     CK(cudaMemcpyAsync(&c->unsorted, c->counters.p + 20, 4, cudaMemcpyDeviceToHost, c->stream));
     c->launches += 2;
   }
-  if (c->h_ztab.size() != static_cast<size_t>(c->zlen) * 4) {
+  if (!c->too_long && c->h_ztab.size() != static_cast<size_t>(c->zlen) * 4) {
     c->h_ztab.resize(static_cast<size_t>(c->zlen) * 4);
     uint64_t sm = 0x5eedb200c0ffeeULL;
     for (auto &z : c->h_ztab) z = splitmix64(sm);
@@ -507,6 +506,7 @@ int swb200_d1_index(swb200_ctx *c) {
   API_BEGIN(c)
   if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
   if (c->db_pending) { g_err = "d1_index: swb200_load_db_shard must be followed by the row exchange and swb200_db_commit"; return SWB200_EINVAL; }
+  if (c->too_long) { g_err = "sequences longer than 5,000 nt are not supported by the on-chip Zobrist table"; return SWB200_EUNSUPPORTED; }
   c->join_active = c->tile_active = false;
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
   if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8 && c->join_kernel != 1 && c->stride <= 32 && c->max_len < 8192) {
@@ -1046,20 +1046,19 @@ int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const 
                       uint32_t *generation, uint32_t *parent, uint32_t *pdiff) {
   API_BEGIN(c)
   if (c->n == 0 || !penalties || d < 2) { g_err = "dn_cluster: needs a database, penalties and d >= 2"; return SWB200_EINVAL; }
+  if (c->too_long) { g_err = "sequences longer than 5,000 nt are not supported by the clustering kernels"; return SWB200_EUNSUPPORTED; }
   const uint32_t n = c->n;
   const int64_t mis = penalties[0], go = penalties[1], ge = penalties[2];
   if (mis <= 0 || go < 0 || ge <= 0) { g_err = "dn_cluster: bad penalties"; return SWB200_EINVAL; }
   const int64_t B = static_cast<int64_t>(d) * std::max(mis, go + ge);
   const int64_t w64 = B >= go + ge ? (B - go) / ge : 0;
-  if (w64 > 15 || B > (1 << 24)) {
-    g_err = "dn_cluster: band half-width " + std::to_string(w64) + " > 15 (d too large for this scoring system) is not supported yet";
-    return SWB200_EUNSUPPORTED;
-  }
+  if (B > (1 << 24)) { g_err = "dn_cluster: d x penalty exceeds 2^24"; return SWB200_EUNSUPPORTED; }
+  const bool wide = w64 > 15;                     // beyond the register band of k_dn_align: k_dn_align_wide
   DnParams P{};
   P.words = c->words.p; P.len = c->len.p; P.abundance = c->abundance.p;
   P.n = n; P.stride = c->stride; P.d = d; P.ncb = no_cluster_breaking ? 1 : 0;
   P.mismatch = static_cast<int32_t>(mis); P.gapopen = static_cast<int32_t>(go); P.gapextend = static_cast<int32_t>(ge);
-  P.bound = static_cast<int32_t>(B); P.w = static_cast<uint32_t>(w64); P.max_popc = 10 * d;
+  P.bound = static_cast<int32_t>(B); P.w = static_cast<uint32_t>(std::min<int64_t>(w64, static_cast<int64_t>(c->max_len) + 1)); P.max_popc = 10 * d;
   P.max_len = c->max_len;
   c->qgrams.alloc(static_cast<size_t>(n) * 32);
   P.qgrams = c->qgrams.p;
@@ -1105,7 +1104,20 @@ int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const 
   c->edges.alloc(std::max<uint64_t>(ntasks, 1));
   c->ediff.alloc(std::max<uint64_t>(ntasks, 1));
   P.edges = c->edges.p; P.ediff = c->ediff.p; P.edge_cap = c->edges.n;
-  if (ntasks) {
+  if (ntasks && wide) {
+    // direction nibbles by absolute column, previous row's H and E by column: per thread max_len * (dir_words + 2) words
+    P.dir_words = (std::max<uint32_t>(c->max_len, 1) + 7) / 8;
+    const uint64_t per_thread = static_cast<uint64_t>(std::max<uint32_t>(c->max_len, 1)) * (P.dir_words + 2) * 4;
+    uint64_t threads = std::min<uint64_t>(static_cast<uint64_t>(c->sm_count) * 16 * 128, (4ull << 30) / per_thread / 128 * 128);
+    threads = std::max<uint64_t>(128, std::min<uint64_t>(threads, (ntasks + 127) / 128 * 128));
+    c->dirs.alloc(threads * per_thread / 4);
+    P.dirs = c->dirs.p;
+    int32_t *hrow = reinterpret_cast<int32_t *>(c->dirs.p + threads * static_cast<uint64_t>(c->max_len) * P.dir_words);
+    int32_t *erow = hrow + threads * static_cast<uint64_t>(c->max_len);
+    k_dn_align_wide<<<static_cast<int>(threads / 128), 128, 0, c->stream>>>(P, hrow, erow, 0, ntasks);
+    c->launches++;
+    CK(cudaGetLastError());
+  } else if (ntasks) {
     const uint32_t nb = 2 * P.w + 1;
     P.dir_words = (nb + 7) / 8;
     const uint64_t per_thread = static_cast<uint64_t>(std::max<uint32_t>(c->max_len, 1)) * P.dir_words * 4;

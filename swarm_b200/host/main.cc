@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -235,11 +236,21 @@ int main(int argc, char **argv) {
   if (P.fastidious) std::fprintf(logf, "Fastidious:        Yes, with boundary %" PRId64 "\n\n", P.boundary);
   else std::fprintf(logf, "Fastidious:        No\n\n");
 
+  // The CUDA context (driver initialisation, ~0.3-0.5 s) is created on a helper thread while the FASTA is parsed.
+  swb200_ctx *ctx = nullptr;
+  int ctx_status = SWB200_OK;
+  std::string ctx_error;
+  std::thread ctx_thread([&] {
+    const char *dev = std::getenv("SWARM_B200_DEVICE");
+    ctx_status = swb200_create(&ctx, dev ? std::atoi(dev) : 0);
+    if (ctx_status != SWB200_OK) ctx_error = swb200_last_error();      // the error text is thread-local
+  });
   // db_read
   if (used['t' - 'a']) swbh_set_threads(static_cast<int>(P.threads));      // -t bounds the ingest workers; default: all cores
   swbh_db *db = nullptr;
-  if (swbh_db_read_fasta(P.input.c_str(), P.usearch ? 1 : 0, P.append_abundance, P.differences > 1 ? 1 : 0, &db) != 0)
-    fatal(swbh_last_error());
+  const int db_status = swbh_db_read_fasta(P.input.c_str(), P.usearch ? 1 : 0, P.append_abundance, P.differences > 1 ? 1 : 0, &db);
+  ctx_thread.join();
+  if (db_status != 0) fatal(swbh_last_error());
   const uint32_t n = swbh_db_count(db);
   std::fprintf(logf, "Database info:     %" PRIu64 " nt in %u sequences, longest %u nt\n", swbh_db_nucleotides(db), n, swbh_db_longest(db));
 
@@ -247,9 +258,7 @@ int main(int argc, char **argv) {
   char *text = nullptr;
   uint64_t len = 0;
   if (n > 0) {
-    swb200_ctx *ctx = nullptr;
-    const char *dev = std::getenv("SWARM_B200_DEVICE");
-    engine_check(swb200_create(&ctx, dev ? std::atoi(dev) : 0));
+    if (ctx_status != SWB200_OK) fatal("GPU engine: " + ctx_error);
     {
       const uint16_t *len16 = nullptr; const uint64_t *run_ab = nullptr; const uint32_t *run_start = nullptr;
       const uint32_t runs = swbh_db_compact(db, &len16, &run_ab, &run_start);
@@ -328,6 +337,7 @@ int main(int argc, char **argv) {
                  P.differences == 1 ? swbh_result_maxgen(res) : std::max(1u, swbh_result_maxgen(res)));
     swbh_result_free(res);
   } else {                                                     // empty input: the reference still reports (and the mothur line is written)
+    if (ctx) swb200_destroy(ctx);
     if (P.mothur && P.differences < 2) std::fprintf(out, "swarm_%" PRId64 "\t0\n", P.differences);   // src/algo.cc writes nothing
     std::fprintf(logf, "\nNumber of swarms:  0\nLargest swarm:     0\n%s0\n", P.differences == 0 ? "Heaviest swarm:    " : "Max generations:   ");
   }

@@ -78,6 +78,20 @@ def make_uclust():
     print("uclust ok")
 
 
+# d >= 7 with the default scoring: the reference switches to its 16-bit aligner (src/algo.cc:96-120), the engine to
+# k_dn_align_wide (band half-width > 15)
+DN_WIDE = [("c1_1k_150", 7), ("w65_300", 9), ("w64_400", 12), ("l400_250", 7), ("handmade", 8)]
+
+
+def make_dn_wide():
+    for name, d in DN_WIDE:
+        r = helpers.run_ref(HERE / f"{name}.fasta", "-d", str(d), outputs=("o", "s", "i"), threads=2)
+        assert r["rc"] == 0, r["stderr"]
+        for k in "osi":
+            (HERE / f"{name}.d{d}.{k}").write_bytes(r[k])
+    print("d>=7 ok")
+
+
 def make_derep():
     """d=0 inputs need identical sequences: reads drawn (seeded) from the first 250 sequences of c1_1k_150 with fresh
     labels and small abundances (many 1s -> singletons, equal masses -> the seed-index tie-break), some in lower
@@ -118,6 +132,8 @@ def main():
         return make_uclust()
     if sys.argv[1:] == ["derep"]:
         return make_derep()
+    if sys.argv[1:] == ["dn_wide"]:
+        return make_dn_wide()
     (HERE / "handmade.fasta").write_bytes(HANDMADE)
     names = ["handmade"]
     for name, n, L, seed, mode, op in CASES:
@@ -147,6 +163,7 @@ def main():
         assert r["rc"] == 0, r["stderr"]
         for k in "osi":
             (HERE / f"{name}.{tag}.{k}").write_bytes(r[k])
+    make_dn_wide()
     helpers.make_fasta(HERE / "l400_250.fasta", 250, 400, 12, 0, 0.3)
     r = helpers.run_ref(HERE / "l400_250.fasta", "-d", "2", outputs=("o", "s", "i"), threads=2)
     for k in "osi":

@@ -86,6 +86,9 @@ def test_cli_dn_usearch_mothur_stdin(built, tmp_path):
     assert b"Number of swarms:" in r["log"] and b"Converted costs:   mismatch: 18, gap opening: 24, gap extension: 13" in r["log"]
     r = _run(tmp_path, "-d", "2", "-m", "3", "-p", "2", "-g", "5", "-e", "3", fasta=str(GOLDEN / "w32_400.fasta"), outs=("o", "i"))
     assert r["o"] == (GOLDEN / "w32_400.d2pen.o").read_bytes() and r["i"] == (GOLDEN / "w32_400.d2pen.i").read_bytes()
+    r = _run(tmp_path, "-d", "7", fasta=str(GOLDEN / "c1_1k_150.fasta"), outs=("o", "s", "i"))      # band beyond the register kernel
+    for k in "osi":
+        assert r[k] == (GOLDEN / f"c1_1k_150.d7.{k}").read_bytes()
     r = _run(tmp_path, "-z", fasta=str(GOLDEN / "usearch_300.fasta"), outs=("o", "s", "i", "w"))
     for k in "osiw":
         assert r[k] == (GOLDEN / f"usearch_300.{k}").read_bytes()

@@ -146,6 +146,26 @@ def seqs_of(db, i):
 
 
 @pytest.mark.gpu
+def test_long_sequences_are_dereplicated_but_not_clustered(built):
+    """the clustering kernels keep per-position tables on chip (<= 5 000 nt); d = 0 has no such limit"""
+    from swarm_b200 import Engine, EngineError
+    rng = np.random.default_rng(3)
+    a = "".join(rng.choice(list("ACGT"), 6000))
+    b = a[:5999] + ("A" if a[5999] != "A" else "C")
+    db = HostDb(text=f">x_3\n{a}\n>y_2\n{b}\n>z_1\n{a}\n>w_1\n{a[:5999]}\n".encode())
+    eng = Engine(0)
+    eng.load(db)
+    rep, mass, size, singles, k = eng.d0_dereplicate()
+    for got, exp in zip((rep, mass, size, singles), Oracle(db).derep()):
+        assert np.array_equal(got, exp)
+    assert k == 3 and rep.tolist() == [0, 1, 2, 0]          # order: x_3, y_2, w_1, z_1 (abundance, then header)
+    with pytest.raises(EngineError):
+        eng.d1_index()
+    with pytest.raises(EngineError):
+        eng.dn_cluster(2)
+
+
+@pytest.mark.gpu
 def test_cli_d0_outputs(built, tmp_path):
     cli = str(helpers.ROOT / "bin" / "swarm_b200")
     for name, flags in (("derep_mix", []), ("derep_mix_z", ["-z"])):

@@ -327,7 +327,10 @@ def test_fastidious_seeded_vs_oracle(built, tmp_path, n, L, seed, mode_ab, bound
 DN_CASES = [("handmade", 2, False, None, "d2"), ("c1_1k_150", 2, False, None, "d2"), ("short_600_20", 2, False, None, "d2"),
             ("short_600_20", 3, False, None, "d3"), ("tie_1500_60", 2, False, None, "d2"), ("tie_1500_60", 2, True, None, "d2n"),
             ("w65_300", 3, False, None, "d3"), ("w64_400", 4, False, None, "d4"), ("w32_400", 2, False, (3, 2, 5, 3), "d2pen"),
-            ("l400_250", 2, False, None, "d2")]
+            ("l400_250", 2, False, None, "d2"),
+            # band half-width > 15 (d >= 7 with the default scoring): k_dn_align_wide; the reference runs its 16-bit aligner
+            ("c1_1k_150", 7, False, None, "d7"), ("w65_300", 9, False, None, "d9"), ("w64_400", 12, False, None, "d12"),
+            ("l400_250", 7, False, None, "d7"), ("handmade", 8, False, None, "d8")]
 
 
 @pytest.mark.parametrize("dn_filter", [0, 1])
@@ -349,7 +352,8 @@ def test_dn_golden(built, name, d, ncb, pen, tag, dn_filter):
 
 
 @pytest.mark.parametrize("dn_filter", [0, 1])
-@pytest.mark.parametrize("n,L,seed,mode_ab,d", [(4000, 100, 31, 0, 2), (3000, 60, 32, 1, 3), (2500, 400, 33, 0, 2), (2000, 150, 34, 1, 5)])
+@pytest.mark.parametrize("n,L,seed,mode_ab,d", [(4000, 100, 31, 0, 2), (3000, 60, 32, 1, 3), (2500, 400, 33, 0, 2), (2000, 150, 34, 1, 5),
+                                                (1500, 120, 35, 0, 8), (1200, 90, 36, 1, 10), (300, 70, 37, 0, 255)])
 def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab, d, dn_filter):
     fa = helpers.make_fasta(tmp_path / "s.fa", n, L, seed, mode_ab)
     db = HostDb(fa, check_dup_sequences=True)

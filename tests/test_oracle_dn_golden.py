@@ -11,7 +11,10 @@ from swarm_b200 import DnResult, HostDb, scoring
 CASES = [("handmade", 2, False, None, "d2"), ("c1_1k_150", 2, False, None, "d2"), ("short_600_20", 2, False, None, "d2"),
          ("short_600_20", 3, False, None, "d3"), ("tie_1500_60", 2, False, None, "d2"), ("tie_1500_60", 2, True, None, "d2n"),
          ("w65_300", 3, False, None, "d3"), ("w64_400", 4, False, None, "d4"), ("w32_400", 2, False, (3, 2, 5, 3), "d2pen"),
-         ("l400_250", 2, False, None, "d2")]
+         ("l400_250", 2, False, None, "d2"),
+         # d >= 7: the reference switches to its 16-bit SIMD aligner (src/algo.cc:96-120)
+         ("c1_1k_150", 7, False, None, "d7"), ("w65_300", 9, False, None, "d9"), ("w64_400", 12, False, None, "d12"),
+         ("l400_250", 7, False, None, "d7"), ("handmade", 8, False, None, "d8")]
 
 
 def test_scoring_conversion(built):
