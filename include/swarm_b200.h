@@ -178,7 +178,7 @@ double swb200_last_device_seconds(swb200_ctx *ctx);
 double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
- * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create, [6] packed sequences gathered into shared memory (tile join); [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
+ * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create, [6] packed sequences gathered into shared memory (tile join), [7] rounds of the last swb200_d1_cluster; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
  * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links. */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 

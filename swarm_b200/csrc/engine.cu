@@ -900,6 +900,13 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   run_cluster(c);
   c->toc(3);
   c->clustered = true;
+  {                                                           // rounds the relaxation took (stats[7]; persistent kernels only)
+    uint32_t rounds = 0;
+    if (c->cluster_kernel == 0 || c->cluster_kernel == 3)
+      CK(cudaMemcpyAsync(&rounds, reinterpret_cast<uint32_t *>(c->counters.p + 19), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats[7] = rounds;
+  }
   if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (parent) CK(cudaMemcpyAsync(parent, c->parent.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));

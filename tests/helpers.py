@@ -233,6 +233,31 @@ def have_ref() -> bool:
     return REF_BIN.exists() and os.access(REF_BIN, os.X_OK)
 
 
+def make_variant_fasta(path, n, L, seed, kmin=3, kmax=60):
+    """one abundant seed + n distinct variants, each kmin..kmax random edits (60 % substitutions, 20 % deletions, 20 %
+    insertions) away from it: related sequences far apart, the input for large-d tests"""
+    import random
+    rng = random.Random(seed)
+    root = "".join(rng.choice("ACGT") for _ in range(L))
+    recs, seen = [("seed", 100000, root)], {root}
+    while len(recs) <= n:
+        s = list(root)
+        for _ in range(rng.randint(kmin, kmax)):
+            r, p = rng.random(), rng.randrange(len(s))
+            if r < 0.6:
+                s[p] = rng.choice("ACGT")
+            elif r < 0.8:
+                del s[p]
+            else:
+                s.insert(p, rng.choice("ACGT"))
+        s = "".join(s)
+        if s not in seen and len(s) >= 20:
+            seen.add(s)
+            recs.append((f"m{len(recs)}", rng.choice([1, 1, 2, 5]), s))
+    Path(path).write_text("".join(f">{h}_{a}\n{t}\n" for h, a, t in recs))
+    return path
+
+
 def run_ref(fasta, *flags, outputs=("o",), threads=1):
     """run the unmodified reference binary; returns {flag: bytes}"""
     res = {}

@@ -369,6 +369,32 @@ def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab,
     if helpers.have_ref():
         r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
         res = DnResult(db, sw, gen, par, pd)
+        assert res.swarms_text() == r["o"]
+        # Unrelated sequences (random pairs ~45 differences apart, only linked at d = 255) have many co-optimal
+        # alignments, and the reference's SIMD aligner (src/search16.cc) and its own scalar one (src/nw.cc, which the
+        # oracle and the engine follow) then report different difference counts for ~2 % of such pairs; on related
+        # sequences they agree at any distance (test_dn_wide_related_sequences).  So the per-link columns are compared
+        # where links join related sequences.
+        if d <= 30:
+            assert res.stats_text() == r["s"] and res.structure_text() == r["i"]
+
+
+@pytest.mark.parametrize("d", [20, 60])
+def test_dn_wide_related_sequences(built, tmp_path, d):
+    """one seed + 600 variants 3..60 edits away, clustered at a d far beyond the register band (full-matrix
+    k_dn_align_wide): engine == oracle == reference, including every link's difference count"""
+    fa = helpers.make_variant_fasta(tmp_path / "v.fa", 600, 150, 5)
+    db = HostDb(fa, check_dup_sequences=True)
+    orc = Oracle(db)
+    osw, ogen, opar, opd = orc.dn_cluster(d)
+    eng = Engine(0)
+    eng.load(db)
+    sw, gen, par, pd = eng.dn_cluster(d)
+    eng.close()
+    assert np.array_equal(sw, osw) and np.array_equal(gen, ogen) and np.array_equal(par, opar) and np.array_equal(pd, opd)
+    if helpers.have_ref():
+        r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
+        res = DnResult(db, sw, gen, par, pd)
         assert res.swarms_text() == r["o"] and res.stats_text() == r["s"] and res.structure_text() == r["i"]
 
 

@@ -58,3 +58,18 @@ def test_dn_matches_reference(built, name, d, ncb, pen, tag):
     want = [l.split() for l in (GOLDEN / f"{name}.{tag}.o").read_text().splitlines()]
     flat = [h for l in want for h in l]
     assert [db.header(a) for a in orc.order] == flat
+
+
+@pytest.mark.parametrize("d", [20, 60, 255])
+def test_wide_d_related_sequences_match_reference(built, tmp_path, d):
+    """far beyond d = 6 the reference aligns with its 16-bit SIMD kernels; on RELATED sequences (variants of one seed,
+    3..60 edits away) the oracle's scalar aligner reports the same difference count for every link"""
+    if not helpers.have_ref():
+        pytest.skip("reference binary not built")
+    fa = helpers.make_variant_fasta(tmp_path / "v.fa", 500, 150, 5)
+    db = HostDb(fa, check_dup_sequences=True)
+    orc = Oracle(db)
+    sw, gen, par, pdiff = orc.dn_cluster(d)
+    res = DnResult(db, sw, gen, par, pdiff)
+    r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=2)
+    assert res.swarms_text() == r["o"] and res.stats_text() == r["s"] and res.structure_text() == r["i"]
