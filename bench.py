@@ -207,6 +207,49 @@ def build_weak_dataset(args, rank, world):
     return W, Ln, Ab, S
 
 
+def two_jobs_in_flight(make_engine, one_job, eng_a, res_a, make_result, steps, n, sync):
+    """2 x `steps` end-to-end jobs, two at a time: a second engine context and one host thread per context, so one job's
+    upload overlaps the other's kernels and download.  Informational (host wall clock); any failure is reported in the
+    returned dict instead of being raised, so it can never take the bench line down."""
+    import numpy as np
+    eng_b = None
+    try:
+        eng_b = make_engine()
+        res_b = make_result()
+        failed = []
+
+        def run(e, r, k):
+            try:
+                for _ in range(k):
+                    one_job(e, r)
+            except Exception as exc:
+                failed.append(repr(exc))
+
+        run(eng_b, res_b, 2)
+        sync()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=run, args=(eng_a, res_a, steps)), threading.Thread(target=run, args=(eng_b, res_b, steps))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        sync()
+        dt2 = time.perf_counter() - t0
+        if failed:
+            return {"error": failed[0]}
+        same = all(np.array_equal(res_a[k], res_b[k]) for k in res_a)
+        return {"value": 2 * steps * n / dt2, "unit": UNIT, "ms_per_job": 1e3 * dt2 / (2 * steps), "timing": "host wall clock",
+                "results_identical": bool(same)}
+    except Exception as exc:
+        return {"error": repr(exc)}
+    finally:
+        if eng_b is not None:
+            try:
+                eng_b.close()
+            except Exception:
+                pass
+
+
 def per_rank_rows(n, world):
     """rows the index pass of one rank reads: every rank scans the whole database (its tiles are a hash range)"""
     return n
@@ -384,48 +427,19 @@ def main():
     # informational: the same end-to-end call with TWO jobs in flight (two contexts on the GPU, one host thread each):
     # job B's upload runs while job A computes and downloads.  Host wall clock over 2 x K steps; not the headline e2e.
     two_jobs = None
-    eng_b = None
     if world == 1 and not args.fastidious:
-        try:
-            eng_b = Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, cluster_kernel=args.cluster_kernel,
-                           bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0)
-        except Exception:
-            eng_b = None
-    if eng_b is not None:
-        res_b = {k: pinned(n, torch.int32).view(np.uint32) for k in ("swarm_of", "generation", "parent")}
+        def make_engine():
+            return Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, cluster_kernel=args.cluster_kernel,
+                          bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0)
 
-        def job(e, r, k):
-            for _ in range(k):
-                e.load_db_compact(pw, stride, pl16, prab, prst)
-                e.d1_index()
-                e.d1_network()
-                e.d1_cluster(out=r)
+        def one_job(e, r):
+            e.load_db_compact(pw, stride, pl16, prab, prst)
+            e.d1_index()
+            e.d1_network()
+            e.d1_cluster(out=r)
 
-        failed = []
-
-        def guarded(e, r, k):
-            try:
-                job(e, r, k)
-            except Exception as exc:                       # informational leg: never take the bench line down with it
-                failed.append(repr(exc))
-
-        guarded(eng_b, res_b, 2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=guarded, args=(eng, res, args.steps)), threading.Thread(target=guarded, args=(eng_b, res_b, args.steps))]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        torch.cuda.synchronize()
-        dt2 = time.perf_counter() - t0
-        if failed:
-            two_jobs = {"error": failed[0]}
-        else:
-            same = all(np.array_equal(res[k], res_b[k]) for k in res)
-            two_jobs = {"value": 2 * args.steps * n / dt2, "unit": UNIT, "ms_per_job": 1e3 * dt2 / (2 * args.steps), "timing": "host wall clock",
-                        "results_identical": bool(same)}
-        eng_b.close()
+        two_jobs = two_jobs_in_flight(make_engine, one_job, eng, res, lambda: {k: pinned(n, torch.int32).view(np.uint32) for k in res},
+                                      args.steps, n, torch.cuda.synchronize)
 
     times = torch.tensor([dt, dt_e2e, wall, wall_e2e], dtype=torch.float64, device="cuda")
     stat_t = torch.tensor([st["variants"], st["filter_pass"], st["slots_visited"], st["exact_compares"], st["links"], st["rows_gathered"],
