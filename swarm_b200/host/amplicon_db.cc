@@ -16,6 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <atomic>
 #include <numeric>
 #include <thread>
@@ -573,15 +578,27 @@ std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, Ampl
 }
 
 std::string db_read_file(const std::string &path, const DbOptions &opt, AmpliconDb &db) {
-  std::FILE *f = (path == "-") ? stdin : std::fopen(path.c_str(), "rb");          // src/utils/input_output.cc:29-60
+  // a regular file is mapped, not copied: the ingest workers then fault their own ranges in, in parallel
+  if (path != "-") {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return "Unable to open input data file (" + path + ").\n";          // src/utils/input_output.cc:29-60
+    struct stat st;
+    if (::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void *map = ::mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE, fd, 0);
+      if (map != MAP_FAILED) {
+        ::madvise(map, static_cast<size_t>(st.st_size), MADV_WILLNEED);
+        std::string e = db_parse(static_cast<const char *>(map), static_cast<uint64_t>(st.st_size), opt, db);
+        ::munmap(map, static_cast<size_t>(st.st_size));
+        ::close(fd);
+        return e;
+      }
+    }
+    ::close(fd);                                                                   // a pipe, an empty file, ...: read it
+  }
+  std::FILE *f = (path == "-") ? stdin : std::fopen(path.c_str(), "rb");
   if (f == nullptr) return "Unable to open input data file (" + path + ").\n";
   std::vector<char> buf;
   size_t cap = 1u << 24, used = 0;
-  if (f != stdin && std::fseek(f, 0, SEEK_END) == 0) {
-    const long sz = std::ftell(f);
-    if (sz > 0) cap = static_cast<size_t>(sz) + 1;
-    std::rewind(f);
-  }
   buf.resize(cap);
   for (;;) {
     const size_t got = std::fread(buf.data() + used, 1, buf.size() - used, f);
