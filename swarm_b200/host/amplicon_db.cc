@@ -22,6 +22,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <numeric>
 #include <thread>
 #include <unordered_set>
@@ -320,6 +321,7 @@ void parse_range(const char *text, Range &R, uint32_t range_no) {
     if (text[pos] != '>') { R.ok = false; return; }
     const void *nl = std::memchr(text + pos, '\n', end - pos);
     uint64_t le = nl ? static_cast<uint64_t>(static_cast<const char *>(nl) - text) + 1 : end;
+    if (std::memchr(text + pos, '\0', le - pos) != nullptr) { R.ok = false; return; }   // NUL bytes: the serial parser's business
     ParEntry e{};
     e.range = range_no;
     e.header_pos = pos + 1;
@@ -410,27 +412,64 @@ bool all_distinct(uint32_t n, unsigned T, KeyOf &&key_of) {
   return !dup.load();
 }
 
+// sample sort: T-1 splitters from a sorted sample, one counting + one scattering pass over the workers' slices, then
+// every bucket is sorted by its own worker — no merge passes (the keys are unique, so the buckets are balanced)
 template <typename Rec, typename Less>
-void parallel_sort(std::vector<Rec> &v, unsigned T, Less less) {
+void parallel_sort(raw_vector<Rec> &v, unsigned T, Less less) {
   const size_t n = v.size();
   if (T <= 1 || n < (1u << 16)) { std::sort(v.begin(), v.end(), less); return; }
-  unsigned parts = 1;
-  while (parts * 2 <= T) parts *= 2;
-  std::vector<size_t> cut(parts + 1);
-  for (unsigned p = 0; p <= parts; ++p) cut[p] = n * p / parts;
-  run_workers(parts, [&](unsigned p) { std::sort(v.begin() + static_cast<int64_t>(cut[p]), v.begin() + static_cast<int64_t>(cut[p + 1]), less); });
-  for (unsigned width = 1; width < parts; width *= 2) {
-    const unsigned merges = parts / (2 * width);
-    run_workers(merges, [&](unsigned m) {
-      const size_t a = cut[2 * width * m], b = cut[2 * width * m + width], c = cut[2 * width * (m + 1)];
-      std::inplace_merge(v.begin() + static_cast<int64_t>(a), v.begin() + static_cast<int64_t>(b), v.begin() + static_cast<int64_t>(c), less);
-    });
+  const size_t per_bucket = 64, S = per_bucket * T;
+  std::vector<Rec> sample(S);
+  for (size_t i = 0; i < S; ++i) sample[i] = v[i * (n / S)];
+  std::sort(sample.begin(), sample.end(), less);
+  std::vector<Rec> split(T - 1);
+  for (unsigned b = 1; b < T; ++b) split[b - 1] = sample[b * per_bucket];
+  raw_vector<uint16_t> bucket(n);
+  std::vector<size_t> count(static_cast<size_t>(T) * T, 0);        // [worker][bucket]
+  run_workers(T, [&](unsigned t) {
+    const size_t lo = n * t / T, hi = n * (t + 1) / T;
+    size_t *c = count.data() + static_cast<size_t>(t) * T;
+    for (size_t i = lo; i < hi; ++i) {
+      const unsigned b = static_cast<unsigned>(std::upper_bound(split.begin(), split.end(), v[i], less) - split.begin());
+      bucket[i] = static_cast<uint16_t>(b);
+      ++c[b];
+    }
+  });
+  std::vector<size_t> start(static_cast<size_t>(T) * T), bucket_begin(T + 1, 0);
+  size_t run = 0;
+  for (unsigned b = 0; b < T; ++b) {
+    bucket_begin[b] = run;
+    for (unsigned t = 0; t < T; ++t) { start[static_cast<size_t>(t) * T + b] = run; run += count[static_cast<size_t>(t) * T + b]; }
   }
+  bucket_begin[T] = run;
+  raw_vector<Rec> out(n);
+  run_workers(T, [&](unsigned t) {
+    const size_t lo = n * t / T, hi = n * (t + 1) / T;
+    size_t *at = start.data() + static_cast<size_t>(t) * T;
+    for (size_t i = lo; i < hi; ++i) out[at[bucket[i]]++] = v[i];
+  });
+  run_workers(T, [&](unsigned b) {
+    std::sort(out.begin() + static_cast<int64_t>(bucket_begin[b]), out.begin() + static_cast<int64_t>(bucket_begin[b + 1]), less);
+  });
+  v.swap(out);
 }
 
 // returns false when the input is not plainly well-formed (the serial parser then decides and words the error)
+// SWARM_B200_INGEST_TIMES=1: stage times of the parallel ingest on stderr (diagnostic)
+struct StageClock {
+  bool on = std::getenv("SWARM_B200_INGEST_TIMES") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ingest] %-9s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
+
 bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db, unsigned T) {
-  if (size == 0 || std::memchr(text, '\0', size) != nullptr) return false;
+  StageClock clock;
+  if (size == 0) return false;
   // ranges start at a '>' that follows a line break
   std::vector<Range> ranges(T);
   {
@@ -447,20 +486,26 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
     }
   }
   run_workers(T, [&](unsigned t) { parse_range(text, ranges[t], t); });
+  clock.lap("pack");
   uint64_t n64 = 0;
   for (const Range &R : ranges) { if (!R.ok) return false; n64 += R.entries.size(); }
   if (n64 == 0 || n64 >= 0xFFFFFFF0ull) return false;
   const uint32_t n = static_cast<uint32_t>(n64);
-  std::vector<ParEntry> entries;
-  entries.reserve(n);
+  raw_vector<ParEntry> entries(n);
   db = AmpliconDb{};
-  for (Range &R : ranges) {
-    entries.insert(entries.end(), R.entries.begin(), R.entries.end());
-    std::vector<ParEntry>().swap(R.entries);
+  std::vector<uint64_t> first(T + 1, 0);
+  for (unsigned t = 0; t < T; ++t) {
+    const Range &R = ranges[t];
+    first[t + 1] = first[t] + R.entries.size();
     db.nucleotides += R.nucleotides;
     db.longest = std::max(db.longest, R.longest);
     db.longest_header = std::max(db.longest_header, R.longest_header);
   }
+  run_workers(T, [&](unsigned t) {
+    std::copy(ranges[t].entries.begin(), ranges[t].entries.end(), entries.begin() + static_cast<int64_t>(first[t]));
+    std::vector<ParEntry>().swap(ranges[t].entries);
+  });
+  clock.lap("merge");
   // abundance annotations and identifiers (src/db.cc:286-347,676-758): any irregular record ends the fast path
   std::atomic<bool> bad{false};
   run_workers(T, [&](unsigned t) {
@@ -484,6 +529,7 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
     }
   });
   if (bad.load()) return false;
+  clock.lap("abundance");
   auto words_of = [&](const ParEntry &e) { return ranges[e.range].packed.data() + e.word_pos; };
   auto label_of = [&](uint32_t i) {
     const ParEntry &e = entries[i];
@@ -500,10 +546,11 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
     if (!all_distinct(n, T, seq_of)) return false;
   }
   // order: abundance descending, then header ascending (src/db.cc:392-411)
+  clock.lap("distinct");
   // sort records carry the abundance and the first 8 header bytes (big-endian, zero padded: a shorter header that is
   // a prefix sorts first, like strcmp) so that almost every comparison is decided without touching the text
   struct SortRec { uint64_t abundance, prefix; uint32_t idx; };
-  std::vector<SortRec> order(n);
+  raw_vector<SortRec> order(n);
   auto less = [&](const SortRec &a, const SortRec &b) {
     if (a.abundance != b.abundance) return a.abundance > b.abundance;
     if (a.prefix != b.prefix) return a.prefix < b.prefix;
@@ -529,12 +576,14 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
       for (uint64_t i = lo; i < hi && sorted.load(std::memory_order_relaxed); ++i)
         if (less(order[i + 1], order[i])) sorted.store(false);
     });
+    clock.lap("sort keys");
     if (!sorted.load()) parallel_sort(order, T, less);
   }
+  clock.lap("sort");
   // gather into the SoA layout
   db.n = n;
   db.stride = std::max<uint32_t>(1, (db.longest + 31) / 32);
-  db.words.assign(static_cast<uint64_t>(n) * db.stride, 0);
+  db.words.resize(static_cast<uint64_t>(n) * db.stride);          // uninitialised: every row is written whole below
   db.len.resize(n); db.abundance.resize(n); db.ab_start.resize(n); db.ab_end.resize(n);
   db.header_off.resize(static_cast<uint64_t>(n) + 1);
   std::vector<uint64_t> part(T + 1, 0);
@@ -552,7 +601,10 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
     for (uint64_t i = lo; i < hi; ++i) {
       const ParEntry &e = entries[order[i].idx];
       db.len[i] = e.len; db.abundance[i] = e.abundance; db.ab_start[i] = e.ab_start; db.ab_end[i] = e.ab_end;
-      std::memcpy(db.words.data() + i * db.stride, words_of(e), static_cast<size_t>((e.len + 31) / 32) * 8);
+      const uint32_t nw = (e.len + 31) / 32;
+      uint64_t *row = db.words.data() + i * db.stride;
+      std::memcpy(row, words_of(e), static_cast<size_t>(nw) * 8);
+      std::fill(row + nw, row + db.stride, 0ull);
       db.header_off[i] = hp;
       std::memcpy(db.headers.data() + hp, text + e.header_pos, e.header_len);
       db.headers[hp + e.header_len] = '\0';
@@ -560,6 +612,7 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
     }
   });
   db.header_off[n] = part[T];
+  clock.lap("gather");
   return true;
 }
 

@@ -12,10 +12,23 @@
 // Parsing rules, limits and error messages follow SURVEY.md §A.1 / src/db.cc.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace swb {
+
+// std::vector that leaves trivially-constructible elements uninitialised on resize(): the big arrays of the database are
+// filled by the ingest workers, a value-initialising resize would first write them once more on one thread
+template <typename T>
+struct default_init_allocator : std::allocator<T> {
+  template <typename U> struct rebind { using other = default_init_allocator<U>; };
+  using std::allocator<T>::allocator;
+  template <typename U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <typename T> using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 struct DbOptions {
   bool usearch_abundance = false;   // -z  (src/db.cc:214-283)
@@ -29,10 +42,10 @@ struct AmpliconDb {
   uint32_t longest_header = 0;
   uint32_t stride = 0;              // 64-bit words per amplicon
   uint64_t nucleotides = 0;
-  std::vector<uint64_t> words;      // n * stride
+  raw_vector<uint64_t> words;       // n * stride
   std::vector<uint32_t> len;        // n
   std::vector<uint64_t> abundance;  // n
-  std::vector<char> headers;        // NUL-terminated, sorted order
+  raw_vector<char> headers;         // NUL-terminated, sorted order
   std::vector<uint64_t> header_off; // n + 1
   std::vector<int32_t> ab_start;    // abundance annotation [start, end) inside the header
   std::vector<int32_t> ab_end;
