@@ -338,9 +338,23 @@ void parse_range(const char *text, Range &R, uint32_t range_no) {
     const size_t first_word = R.packed.size();
     uint64_t buf = 0, length = 0;
     uint32_t nbuf = 0;
-    // the sequence runs to the next line that starts with '>' (a '>' elsewhere is an illegal character)
+    // the sequence runs to the next line that starts with '>' (a '>' elsewhere is an illegal character).  Line by line:
+    // 32 nucleotides at a time go into one word with no per-character branch (the codes of a block are OR-ed and looked
+    // at once); a block holding anything but nucleotides — a line break, '\r', an illegal byte — takes the slow lane.
     while (pos < end && text[pos] != '>') {
-      for (;;) {
+      const void *lf = std::memchr(text + pos, '\n', end - pos);
+      const uint64_t stop = lf ? static_cast<uint64_t>(static_cast<const char *>(lf) - text) + 1 : end;
+      while (pos < stop) {
+        if (nbuf == 0 && stop - pos >= 32) {
+          uint64_t word = 0;
+          uint32_t seen = 0;
+          for (uint32_t k = 0; k < 32; ++k) {
+            const uint32_t code = kNt.v[static_cast<unsigned char>(text[pos + k])];
+            seen |= code;
+            word |= static_cast<uint64_t>(code & 3u) << (2 * k);
+          }
+          if (seen < 4) { R.packed.push_back(word); length += 32; pos += 32; continue; }
+        }
         const uint8_t code = kNt.v[static_cast<unsigned char>(text[pos])];
         if (code < 4) {
           buf |= static_cast<uint64_t>(code) << (2 * nbuf);
@@ -348,7 +362,6 @@ void parse_range(const char *text, Range &R, uint32_t range_no) {
           if (++nbuf == 32) { R.packed.push_back(buf); buf = 0; nbuf = 0; }
         } else if (code == 5) { R.ok = false; return; }
         ++pos;
-        if (pos >= end || text[pos - 1] == '\n') break;
       }
     }
     if (length == 0 || length > kMaxSequenceLength) { R.ok = false; return; }
