@@ -87,6 +87,9 @@ int  swbh_d0_write_uclust(const swbh_db *db, const swbh_derep *r, int usearch_ab
                           char **out, uint64_t *out_len);
 int  swbh_d0_write_structure(const swbh_db *db, const swbh_derep *r, int usearch_abundance, char **out, uint64_t *out_len);
 int  swbh_d0_write_stats(const swbh_db *db, const swbh_derep *r, int usearch_abundance, char **out, uint64_t *out_len);
+/* first band half-width of the -u aligner (default 8; it doubles until the banded result provably equals the full
+ * matrix's; 0 = always the full matrix).  The records do not depend on it. */
+void swbh_uclust_band(int first_half_width);
 /* alignment scoring conversion (src/swarm.cc:466-483): penalties[3] = mismatch, gap open, gap extend */
 void swbh_scoring(int64_t match_reward, int64_t mismatch_penalty, int64_t gap_open, int64_t gap_extend, int64_t penalties[3]);
 

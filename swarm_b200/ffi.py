@@ -132,6 +132,8 @@ def host_lib():
         L.swbh_write_structure.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_seeds.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]
         L.swbh_write_uclust.argtypes = [vp, vp, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int64, C.c_int, C.POINTER(vp), _u64p]
+        L.swbh_uclust_band.argtypes = [C.c_int]
+        L.swbh_uclust_band.restype = None
         L.swbh_write_network.argtypes = [vp, _u64p, _u32p, C.c_int, C.c_int64, C.POINTER(vp), _u64p]
         L.swbh_dn_assemble.argtypes = [vp, _u32p, _u32p, _u32p, _u32p, C.POINTER(vp)]
         L.swbh_dn_write_stats.argtypes = [vp, vp, C.c_int, C.POINTER(vp), _u64p]

@@ -9,7 +9,8 @@
 // CIGAR depends on them: while tracing back from the lower-right corner an open gap is continued first, then a gap
 // along the database sequence ("I"), then along the query ("D"), then the diagonal.  It is restated here over
 // unpacked nucleotide bytes with the four decisions of a cell packed in one byte that is written once (the
-// reference ORs flags into a zeroed matrix and clears it again after every pair).  Pairs are independent, so the
+// reference ORs flags into a zeroed matrix and clears it again after every pair), inside a band that is widened until
+// the result provably equals the full matrix's (Aligner::align).  Pairs are independent, so the
 // swarms are cut into contiguous ranges of equal alignment work and aligned by `threads` workers (the reference's
 // `-t` — it aligns serially); the ranges' texts are concatenated in order, so the output does not depend on it.
 #include "../../include/swarm_b200_host.h"
@@ -17,6 +18,7 @@
 #include "result.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -26,6 +28,8 @@
 namespace swb { int give_text(const std::string &s, char **out, uint64_t *out_len); }
 
 namespace {
+
+std::atomic<uint32_t> g_first_band{8};      // swbh_uclust_band(): first band half-width of the -u aligner (0 = full matrix)
 
 constexpr uint8_t kUp = 1, kLeft = 2, kExtUp = 4, kExtLeft = 8;
 
@@ -41,25 +45,31 @@ struct Aligner {
     for (uint32_t i = 0; i < len; ++i) out[i] = static_cast<uint8_t>((w[i >> 5] >> ((i & 31u) * 2)) & 3u);
   }
 
-  // fills `ops` (reversed) and returns the number of alignment columns that are not matches
-  uint64_t align(const uint64_t *member, uint32_t dlen, const uint64_t *seed, uint32_t qlen) {
-    unpack(member, dlen, d);
-    unpack(seed, qlen, q);
-    cell.resize(static_cast<size_t>(dlen) * qlen);
-    h.resize(qlen); e.resize(qlen);
+  // One pass of the recurrence over the cells |column - row| <= w (everything outside counts as infinite), flags in
+  // `cell[row][column - row + w]`.  Returns the corner score, or kInf when the corner is outside the band.
+  static constexpr uint64_t kInf = 1ull << 60;
+  uint64_t fill(uint32_t dlen, uint32_t qlen, uint32_t w) {
     const uint64_t go = gap_open, ge = gap_ext;
-    for (uint32_t c = 0; c < qlen; ++c) { h[c] = go + (c + 1) * ge; e[c] = 2 * go + (c + 2) * ge; }   // src/nw.cc:71-75
+    const uint32_t nb = 2 * w + 1;
+    cell.resize(static_cast<size_t>(dlen) * nb);
+    h.resize(qlen); e.resize(qlen);
+    for (uint32_t c = 0; c < qlen; ++c) {                        // the boundary row (src/nw.cc:71-75), inside its band
+      h[c] = c <= w ? go + (c + 1) * ge : kInf;
+      e[c] = c <= w ? 2 * go + (c + 2) * ge : kInf;
+    }
     for (uint32_t r = 0; r < dlen; ++r) {
-      uint64_t up = 2 * go + (r + 2) * ge;                       // best score ending in a gap along the seed
-      uint64_t diag = r == 0 ? 0 : go + r * ge;                  // H of the previous row, previous column
-      uint8_t *row = cell.data() + static_cast<size_t>(r) * qlen;
+      const uint32_t c_lo = r > w ? r - w : 0, c_hi = std::min<uint64_t>(qlen - 1, static_cast<uint64_t>(r) + w);
+      if (c_lo > c_hi) return kInf;
+      uint64_t up, diag;
+      if (r <= w) { up = 2 * go + (r + 2) * ge; diag = r == 0 ? 0 : go + r * ge; }   // true left boundary (src/nw.cc:75-76)
+      else { up = kInf; diag = h[c_lo - 1]; }                    // cell (r, c_lo - 1) is outside the band
+      uint8_t *row = cell.data() + static_cast<size_t>(r) * nb + w - r;      // row[c] = cell[r][c - r + w]
       const uint8_t dn = d[r];
-      for (uint32_t c = 0; c < qlen; ++c) {
+      for (uint32_t c = c_lo; c <= c_hi; ++c) {
         const uint64_t h_above = h[c];
         uint64_t left = e[c];
         uint64_t best = diag + (dn == q[c] ? 0 : mismatch);
-        // the four decisions of the cell as flag arithmetic (no data-dependent branches: on real sequences they are
-        // unpredictable and cost more than the arithmetic)
+        // the four decisions of the cell as flag arithmetic (no data-dependent branches)
         uint32_t f = static_cast<uint32_t>(up < best);                                  // kUp
         best = std::min(best, std::min(up, left));
         f |= static_cast<uint32_t>(left == best) << 1;                                  // kLeft
@@ -74,13 +84,38 @@ struct Aligner {
         diag = h_above;
       }
     }
+    const uint32_t gap = qlen > dlen ? qlen - dlen : dlen - qlen;
+    return gap <= w ? h[qlen - 1] : kInf;
+  }
+
+  // fills `ops` (reversed) and returns the number of alignment columns that are not matches.
+  // The matrix is filled inside a band that is widened until the result is provably the full matrix's: k gap columns
+  // cost at least gap_open + k * gap_ext, so an alignment that costs less than gap_open + (w + 1) * gap_ext never
+  // leaves the diagonals +-w; if the banded corner score is below that, so is the optimum, every optimal path — and
+  // every predecessor that ties with or beats a step of one, which is what the flags record — lies inside the band,
+  // and the trace-back reads the flags the full matrix would hold (same argument as the device aligner, DESIGN.md
+  // §3.6).  Members of a swarm are a few edits from their seed: 150 x 17 cells instead of 150 x 150.
+  uint64_t align(const uint64_t *member, uint32_t dlen, const uint64_t *seed, uint32_t qlen) {
+    unpack(member, dlen, d);
+    unpack(seed, qlen, q);
+    const uint32_t full = std::max(dlen, qlen);
+    uint32_t w = first_band == 0 ? full : std::min(first_band, full);
+    for (;;) {
+      const uint64_t score = fill(dlen, qlen, w);
+      if (w >= full || score < gap_open + (static_cast<uint64_t>(w) + 1) * gap_ext) break;
+      // the banded score bounds the optimum from above: the band that makes THAT score provable ends the search in one
+      // more pass (a wider band can only lower the score); no score at all (corner outside the band): four times wider
+      const uint64_t need = score < kInf ? (score - gap_open) / gap_ext + 1 : 4ull * w;
+      w = static_cast<uint32_t>(std::min<uint64_t>(full, std::max<uint64_t>(need, static_cast<uint64_t>(w) + 1)));
+    }
+    const uint32_t nb = 2 * w + 1;
     // trace back (src/nw.cc:111-191)
     ops.clear();
     uint64_t matches = 0;
     uint32_t c = qlen, r = dlen;
     char op = 0;
     while (c > 0 && r > 0) {
-      const uint8_t f = cell[static_cast<size_t>(r - 1) * qlen + (c - 1)];
+      const uint8_t f = cell[static_cast<size_t>(r - 1) * nb + (c - 1) + w - (r - 1)];
       if (op == 'I' && (f & kExtLeft)) { --r; }
       else if (op == 'D' && (f & kExtUp)) { --c; }
       else if (f & kLeft) { --r; op = 'I'; }
@@ -92,6 +127,7 @@ struct Aligner {
     ops.append(r, 'I');
     return ops.size() - matches;
   }
+  uint32_t first_band = 8;
 };
 
 // run-length form of the alignment read from its far end (src/utils/cigar.cc:30-60: a count of 1 is not printed)
@@ -108,6 +144,8 @@ void append_cigar_reversed(std::string &out, const std::string &ops) {
 struct Unit { uint32_t swarm, cluster_no; };
 
 }  // namespace
+
+extern "C" void swbh_uclust_band(int first_half_width) { g_first_band.store(first_half_width < 0 ? 0u : static_cast<uint32_t>(first_half_width)); }
 
 extern "C" int swbh_write_uclust(const swbh_db *dbh, const swbh_result *r, int64_t differences, const int64_t penalties[3],
                                  int usearch, int64_t append, int threads, char **out, uint64_t *out_len) {
@@ -148,6 +186,7 @@ extern "C" int swbh_write_uclust(const swbh_db *dbh, const swbh_result *r, int64
   }
   auto run = [&](unsigned t) {
     Aligner A;
+    A.first_band = g_first_band.load();
     A.mismatch = static_cast<uint64_t>(penalties[0]); A.gap_open = static_cast<uint64_t>(penalties[1]); A.gap_ext = static_cast<uint64_t>(penalties[2]);
     std::string &s = text[t];
     char num[64];

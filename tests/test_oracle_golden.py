@@ -113,6 +113,37 @@ def test_uclust_cigar_known_answers(built):
             assert ref == lines
 
 
+def test_uclust_band_does_not_change_the_records(built, tmp_path):
+    """the -u aligner fills a band that doubles until the result is provably the full matrix's: every first band
+    (1, 2, 8, 64) must give the records of the full matrix (0) — members from 1 to 60 edits away from their seed,
+    unrelated sequences of other lengths, very short ones"""
+    import random
+    from swarm_b200.ffi import host_lib
+    rng = random.Random(11)
+    fa = helpers.make_variant_fasta(tmp_path / "v.fa", 300, 120, 8, kmin=1, kmax=60)
+    text = fa.read_text()
+    for k in range(60):                                    # unrelated sequences, lengths 1..260
+        L = rng.choice([1, 2, 3, 17, 64, 119, 120, 121, 260])
+        text += f">x{k}_1\n{''.join(rng.choice('ACGT') for _ in range(L))}\n"
+    db = HostDb(text=text.encode())
+    n = db.n
+    # one swarm: the most abundant amplicon is the seed of everything (alignment partners are then seed vs. member)
+    sw = np.zeros(n, np.uint32)
+    gen = np.ones(n, np.uint32); gen[0] = 0
+    par = np.zeros(n, np.uint32); par[0] = 0xFFFFFFFF
+    res = D1Result(db, sw, gen, par)
+    L = host_lib()
+    try:
+        L.swbh_uclust_band(0)
+        want = res.uclust_text(threads=4)
+        for w in (1, 2, 8, 64):
+            L.swbh_uclust_band(w)
+            assert res.uclust_text(threads=4) == want, w
+    finally:
+        L.swbh_uclust_band(8)
+    assert want.count(b"\nH\t") == n - 1
+
+
 def test_network_matches_reference(case):
     name, db, orc = case
     pairs = orc.links()
