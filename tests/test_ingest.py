@@ -138,3 +138,24 @@ def test_compact_form_of_the_database(built):
         assert np.array_equal(np.ctypeslib.as_array(pab, shape=(runs,)), rab)
         assert np.array_equal(np.ctypeslib.as_array(pst, shape=(runs + 1,)), rst)
         assert np.array_equal(np.repeat(rab, np.diff(rst.astype(np.int64))), db.abundance)
+
+
+def test_extreme_shapes(built):
+    """ranges that hold no record start (one 3 MB sequence wrapped at 80 columns), more workers than records, 200 k
+    one-nucleotide records, append-abundance (-a) with and without annotations: parallel == serial"""
+    rng = random.Random(4)
+    big = "".join(rng.choice("ACGT") for _ in range(3_000_000))
+    wrapped = "\n".join(big[i:i + 80] for i in range(0, len(big), 80))
+    cases = [
+        (f">big_7\n{wrapped}\n>small_3\nACGT\n".encode(), {}),
+        (f">only_1\n{big[:500]}".encode(), {}),
+        ("".join(f">t{i}_{1 + i % 3}\n{'ACGT'[i % 4]}{'ACGT'[(i // 4) % 4]}{'ACGT'[(i // 16) % 4]}\n" for i in range(200_000)).encode(), {}),
+        (b">a\nACGT\n>b_5\nACGA\n>c;size=3;\nAAAA\n", {"append_abundance": 2}),
+        (b">a;size=4;\nACGT\n>b\nACGA\n", {"append_abundance": 9, "usearch_abundance": True}),
+    ]
+    for text, kw in cases:
+        want = _parse(text, 1, **kw)
+        assert want[0] == "ok", want
+        for t in (2, 8, 32):
+            assert _parse(text, t, **kw) == want
+        assert _parse(text, 6, check_dup_sequences=True, **kw) == _parse(text, 1, check_dup_sequences=True, **kw)
