@@ -2,6 +2,7 @@
 #   swarm_b200/libswarm_b200.so       CUDA engine + C ABI (include/swarm_b200.h), sm_100a only
 #   swarm_b200/libswarm_b200_host.so  host mirror of the reference's FASTA/db/output layer (C++17)
 #   tools/libgen_amplicons.so         synthetic data generator (bench/test infrastructure)
+#   tools/libcanon.so                 canonical form + SHA-256 of a cluster file (bench/test infrastructure)
 #   oracle/liboracle.so, oracle/_ref/ CPU oracle + the reference itself (test infrastructure)
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
@@ -16,7 +17,7 @@ all: engine host tools oracle cli
 cli: bin/swarm_b200
 engine: swarm_b200/libswarm_b200.so
 host: swarm_b200/libswarm_b200_host.so
-tools: tools/libgen_amplicons.so
+tools: tools/libgen_amplicons.so tools/libcanon.so
 
 swarm_b200/libswarm_b200.so: $(ENGINE_SRC) $(ENGINE_DEP)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(ENGINE_SRC) -lcudart 2> swarm_b200/csrc/ptxas.log || (cat swarm_b200/csrc/ptxas.log; false)
@@ -32,6 +33,9 @@ bin/swarm_b200: swarm_b200/host/main.cc $(HOST_SRC) $(HOST_DEP) swarm_b200/libsw
 
 tools/libgen_amplicons.so: tools/gen_amplicons.c
 	gcc -O2 -std=c11 -fPIC -shared -Wall -o $@ $< -lm
+
+tools/libcanon.so: tools/canon.c
+	gcc -O2 -std=c11 -fPIC -shared -Wall -o $@ $<
 
 oracle:
 	$(MAKE) -C oracle all

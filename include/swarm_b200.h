@@ -55,10 +55,17 @@ const char *swb200_last_error(void);
 /* Tunables (call before swb200_d1_index).  key: "enum_mode" (SWB200_ENUM_*), "bloom_bytes_per_slot"
  * (1,2,4,8: filter size = table slots * this; reference uses 1, src/algod1.cc:1127),
  * "collect_stats" (0/1), "net_kernel" (0 auto, 1 first-generation kernel, 2 lean HALF kernel),
- * "join_kernel" (JOIN mode: 0 auto = radix-partitioned join in shared memory, d1_tilejoin.cuh; 1 = global hash
- * multimap, d1_join.cuh — same links), "tile_cmax" (test hook: cap on the entries a tile may hold in shared memory),
+ * "join_kernel" (JOIN mode: 0 auto = partitioned join over the tile store, d1_tilestore.cuh: one scatter pass writes
+ * entry + packed row into fixed-capacity tile slots, a tile is joined from shared memory after one TMA bulk copy;
+ * 1 = global hash multimap, d1_join.cuh, no length limit; 2 = r1's count / scan / scatter tile join, d1_tilejoin.cuh —
+ * same links), "tile_cmax" (test hook: cap on the records a tile slot holds; the rest takes the overflow path),
+ * "skew_fallback" (1 default: when the overflow path would cost more than ~32 pair tests per amplicon — dense data,
+ * huge groups sharing one K-mer — swb200_d1_network switches to the linear HALF enumeration, like the reference's
+ * cost model; 0 = always sweep),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "cluster_kernel" (0 fused label/generation relaxation of the frontier in one persistent cooperative kernel, 3 the same after counting-sorting the links by source, 2 one launch per round, 1 label propagation then BFS), "dn_filter" (0 auto,
+ * "cluster_kernel" (0 frontier relaxation over 8-slot out-rows in one persistent cooperative kernel, d1_frontier.cuh;
+ * 5 r1's persistent kernel over the whole link list every round; 3 the same after counting-sorting the links by
+ * source; 2 one launch per round; 1 label propagation then BFS — same result), "dn_filter" (0 auto,
  * 1 all-pairs q-gram filter),
  * "shard_rank"/"shard_world" (this context's share of the network build, SURVEY.md §8e: in JOIN mode the
  * K-mer table is sharded by hash range — every rank scans all lookups but builds and walks only its own
@@ -179,7 +186,8 @@ double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
  * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create, [6] packed sequences gathered into shared memory (tile join), [7] rounds of the last swb200_d1_cluster; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
- * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links. */
+ * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links; [16] tile-store records that
+ * overflowed their tile slot in the last index, [17] times the network fell back to the enumeration (skew_fallback). */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 
 /* Test hook: enumerate the microvariants of amplicon `seed` on the device exactly as the network

@@ -8,6 +8,8 @@
 #include "d1_fastidious_join.cuh"
 #include "d1_join.cuh"
 #include "d1_tilejoin.cuh"
+#include "d1_tilestore.cuh"
+#include "d1_frontier.cuh"
 #include "d1_cluster.cuh"
 #include "d1_dist.cuh"
 #include "dn_kernels.cuh"
@@ -140,8 +142,9 @@ struct swb200_ctx {
   bool too_long = false;             // longest sequence > 5 000 nt: d = 0 only
   bool db_pending = false;           // rows uploaded by load_db_shard, exchange + db_commit still due
   bool sorted_desc = false;          // abundances never increase with the id (the reference's order, src/db.cc:392-406)
-  int cluster_kernel = 0; // 0 fused key relaxation of the frontier, one persistent cooperative kernel; 3 the same over links first sorted by
-                          // source (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
+  int cluster_kernel = 0; // 0 frontier relaxation over out-rows, one persistent cooperative kernel (d1_frontier.cuh); 5 r1's persistent
+                          // kernel that walks the whole link list every round; 3 the same over links first sorted by source
+                          // (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
                           // 1 label propagation + BFS
   int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
@@ -153,8 +156,21 @@ struct swb200_ctx {
   uint32_t jK = 0;
   bool join_active = false;
   // partitioned (tile) join: d1_tilejoin.cuh
-  int join_kernel = 0;               // 0 auto (tile join when the rows fit shared memory), 1 = global hash multimap (d1_join.cuh)
+  int join_kernel = 0;               // 0 auto (tile store when a tile fits shared memory, d1_tilestore.cuh), 1 = global hash multimap
+                                     // (d1_join.cuh), 2 = r1's count / scan / scatter tile join (d1_tilejoin.cuh)
   bool tile_active = false;
+  // tile store (d1_tilestore.cuh): fat records in fixed-capacity tile slots
+  bool ts_active = false;
+  DevBuf<unsigned long long> ts_store, ts_ovf;
+  DevBuf<uint32_t> ts_cursor;        // [T] cursors, then [T] overflow chain heads
+  uint32_t ts_cap = 0, ts_tiles = 0, ts_lo = 0, ts_hi = 0;
+  uint64_t ts_ovf_cap = 0;
+  size_t ts_smem = 0;
+  unsigned long long ts_overflow = 0, ts_fallbacks = 0;
+  int skew_fallback = 1;             // dense data: abandon the quadratic overflow sweep for the linear enumeration (single GPU)
+  // frontier clustering (d1_frontier.cuh)
+  DevBuf<uint32_t> fr_deg, fr_adj;
+  DevBuf<uint2> fr_spill;
   DevBuf<uint32_t> tj_count, tj_cursor, tj_big;
   DevBuf<unsigned long long> tj_off, tj_entries;
   DevBuf<uint2> tj_plist_ent;
@@ -261,7 +277,7 @@ int swb200_create(swb200_ctx **out, int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
-    c->counters.alloc(32);
+    c->counters.alloc(64);
   } catch (const CudaFail &f) {
     delete c;
     return f.code;
@@ -280,6 +296,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
+  c->ts_store.release(); c->ts_ovf.release(); c->ts_cursor.release(); c->fr_deg.release(); c->fr_adj.release(); c->fr_spill.release();
   c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
   c->qgrams.release(); c->ediff.release(); c->dirs.release(); c->pdiff.release(); c->tasks.release();
@@ -297,11 +314,12 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "bloom_bytes_per_slot" && (v == 1 || v == 2 || v == 4 || v == 8)) c->bloom_bytes_per_slot = static_cast<int>(v);
   else if (k == "collect_stats") c->collect_stats = v != 0;
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
-  else if (k == "join_kernel" && v >= 0 && v <= 1) c->join_kernel = static_cast<int>(v);
+  else if (k == "join_kernel" && v >= 0 && v <= 2) c->join_kernel = static_cast<int>(v);
+  else if (k == "skew_fallback" && (v == 0 || v == 1)) c->skew_fallback = static_cast<int>(v);
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
-  else if (k == "cluster_kernel" && v >= 0 && v <= 3) c->cluster_kernel = static_cast<int>(v);
+  else if (k == "cluster_kernel" && v >= 0 && v <= 5) c->cluster_kernel = static_cast<int>(v);
   else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
@@ -322,7 +340,7 @@ static void db_alloc(swb200_ctx *c, uint32_t n, uint32_t stride_words) {
   // room for an in-place all-gather of equal shards of ceil(n / world) rows (swb200_load_db_shard)
   const size_t shard = (static_cast<size_t>(n) + c->shard_world - 1) / c->shard_world;
   const size_t rows = std::max<size_t>(c->n_padded, shard * c->shard_world);
-  c->words.alloc(rows * stride_words);
+  c->words.alloc(rows * stride_words + 2);            // + 16 bytes: the TMA row staging rounds its size up to 16 (d1_tilestore.cuh)
   c->len.alloc(rows);
   c->abundance.alloc(rows);
 }
@@ -502,14 +520,111 @@ static TileJoinParams tile_params(swb200_ctx *c) {
   return J;
 }
 
+// ---- tile store (d1_tilestore.cuh) ----------------------------------------------------------------------------------
+static TileStoreParams ts_params(swb200_ctx *c) {
+  TileStoreParams J{};
+  J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.ab_all = c->abundance.p;
+  J.n = c->n; J.row_first = 0; J.row_count = c->n;
+  J.stride = c->stride; J.K = c->jK;
+  uint32_t idb = 12;
+  while (idb < 32 && (1ull << idb) < c->n) ++idb;
+  J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0; J.ncb = c->ncb;
+  J.n_tiles = c->ts_tiles; J.t_lo = c->ts_lo; J.t_hi = c->ts_hi;
+  J.cap = c->ts_cap; J.rec_words = c->stride + 1;
+  J.store = c->ts_store.p; J.cursor = c->ts_cursor.p; J.ovf_head = c->ts_cursor.p + (c->ts_hi - c->ts_lo);
+  J.ovf = c->ts_ovf.p; J.ovf_count = c->counters.p + 32; J.ovf_cap = c->ts_ovf_cap;
+  J.ovf_abort = reinterpret_cast<uint32_t *>(c->counters.p + 34);
+  // dense data: past 32 pair tests per amplicon (and 10^8 in all) the linear enumeration wins — single GPU with the
+  // per-position tables on chip only; the tile_cmax test hook forces everything through the overflow path instead
+  J.ovf_budget = (c->skew_fallback && c->tj_cmax_override < 2 && !c->too_long)
+                     ? (static_cast<uint64_t>(c->n) * 16 + 50000000ull) : 0;
+  J.edges = c->edges.p; J.edge_count = c->counters.p; J.edge_cap = c->edges.n;
+  J.dup_flag = reinterpret_cast<uint32_t *>(c->counters.p + 8);
+  J.stats = c->collect_stats ? c->counters.p + 1 : nullptr;
+  J.appended = c->counters.p + 36;
+  return J;
+}
+
+// "Hashing sequences" for the tile store: geometry, buffers, ONE scatter pass.  No host synchronisation.
+static void index_tilestore(swb200_ctx *c) {
+  const uint32_t rec_bytes = 8 * (c->stride + 1);
+  uint32_t cap = std::min<uint32_t>(768, (36u * 1024u) / rec_bytes) & ~1u;
+  cap = std::max<uint32_t>(cap, 64);
+  const uint32_t fill = cap * 2 / 3;                       // mean records per tile: Poisson(512) never reaches 768
+  const uint64_t want_tiles = (static_cast<uint64_t>(c->n) * 2 + fill - 1) / fill;
+  c->ts_tiles = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(want_tiles, 0x7FFFFFFFull)));
+  if (c->tj_cmax_override >= 2) cap = std::max<uint32_t>(2, std::min(cap, c->tj_cmax_override) & ~1u);
+  c->ts_cap = cap;
+  const uint32_t per = (c->ts_tiles + c->shard_world - 1) / c->shard_world;
+  c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * c->shard_rank, c->ts_tiles));
+  c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
+  const uint32_t T = c->ts_hi - c->ts_lo;
+  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + kTsBuckets * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
+  c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * (c->stride + 1), 2) + 2);
+  c->ts_cursor.alloc(static_cast<size_t>(T) * 2 + 2);
+  if (c->ts_ovf_cap == 0 || c->tj_cmax_override >= 2)
+    c->ts_ovf_cap = std::max<uint64_t>(c->ts_ovf_cap, c->tj_cmax_override >= 2 ? static_cast<uint64_t>(c->n) * 2 / c->shard_world + (1u << 16)
+                                                                                : static_cast<uint64_t>(c->n) / 8 / c->shard_world + (1u << 16));
+  c->ts_ovf.alloc(c->ts_ovf_cap * (c->stride + 2));
+  CK(cudaMemsetAsync(c->counters.p, 0, 17 * 8, c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 32, 0, 5 * 8, c->stream));
+  CK(cudaMemsetAsync(c->ts_cursor.p, 0, static_cast<size_t>(T) * 4, c->stream));
+  CK(cudaMemsetAsync(c->ts_cursor.p + T, 0xFF, static_cast<size_t>(T) * 4, c->stream));
+  if (T) {
+    TileStoreParams J = ts_params(c);
+    const size_t smem = static_cast<size_t>(kTsRows) * c->stride * 8 + 16;
+    CK(cudaFuncSetAttribute(k_ts_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k_ts_scatter<<<(c->n + kTsRows - 1) / kTsRows, kTsRows, smem, c->stream>>>(J);
+    CK(cudaGetLastError());
+    c->launches += 1;
+  }
+}
+
+// "Hashing sequences" for the enumeration kernels: Zobrist hash of every amplicon, open-addressing table, blocked
+// Bloom filter, duplicate check.  Returns true when two amplicons are identical.
+static bool index_table(swb200_ctx *c) {
+  c->n_slots = table_slots(c->n);
+  c->n_filter_blocks = std::max<uint64_t>(1, c->n_slots * c->bloom_bytes_per_slot / 8);
+  if (c->n_filter_blocks > (1ull << 32)) c->n_filter_blocks = 1ull << 32;
+  c->slots.alloc(c->n_slots);
+  c->filter.alloc(c->n_filter_blocks);
+  c->hashes.alloc(c->n);
+  CK(cudaMemsetAsync(c->slots.p, 0xFF, c->n_slots * sizeof(Slot), c->stream));
+  CK(cudaMemsetAsync(c->filter.p, 0, c->n_filter_blocks * 8, c->stream));
+  CK(cudaMemsetAsync(c->counters.p, 0, 16 * 8, c->stream));
+  D1Params P = c->params();
+  const size_t zbytes = static_cast<size_t>(c->zlen) * 32;
+  CK(cudaFuncSetAttribute(k_d1_index, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
+  const int grid = std::min<int>(c->sm_count * 8, (c->n + 255) / 256);
+  k_d1_index<<<grid, 256, zbytes, c->stream>>>(P);
+  CK(cudaGetLastError());
+  k_d1_dupcheck<<<(c->n + 255) / 256, 256, 0, c->stream>>>(P);
+  CK(cudaGetLastError());
+  c->launches += 2;
+  uint32_t dup = 0;
+  CK(cudaMemcpyAsync(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return dup != 0;
+}
+
 int swb200_d1_index(swb200_ctx *c) {
   API_BEGIN(c)
   if (c->n == 0) { g_err = "d1_index: no database loaded"; return SWB200_EINVAL; }
   if (c->db_pending) { g_err = "d1_index: swb200_load_db_shard must be followed by the row exchange and swb200_db_commit"; return SWB200_EINVAL; }
-  if (c->too_long) { g_err = "sequences longer than 5,000 nt are not supported by the on-chip Zobrist table"; return SWB200_EUNSUPPORTED; }
-  c->join_active = c->tile_active = false;
+  c->join_active = c->tile_active = c->ts_active = false;
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
-  if (c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8 && c->join_kernel != 1 && c->stride <= 32 && c->max_len < 8192) {
+  const bool join = c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8;
+  if (join && c->join_kernel == 0 && c->stride <= 64 && c->max_len < 8192) {
+    // JOIN over the tile store (d1_tilestore.cuh): one scatter pass, fat records in fixed-capacity tile slots
+    c->tic();
+    index_tilestore(c);
+    c->toc(1);
+    c->indexed = true;
+    c->join_active = c->ts_active = true;
+    c->have_network = c->clustered = false;
+    return SWB200_OK;
+  }
+  if (join && c->join_kernel == 2 && c->stride <= 32 && c->max_len < 8192) {
     // JOIN, partitioned: two K-mer entries per amplicon appended to hash-range tiles (d1_tilejoin.cuh)
     c->tj_cmax = c->stride <= 6 ? 768 : (c->stride <= 14 ? 384 : 192);
     const uint64_t want_tiles = (static_cast<uint64_t>(c->n) * 2 + c->tj_cmax / 2 - 1) / (c->tj_cmax / 2);
@@ -591,27 +706,9 @@ int swb200_d1_index(swb200_ctx *c) {
     c->have_network = c->clustered = false;
     return SWB200_OK;
   }
-  c->n_slots = table_slots(c->n);
-  c->n_filter_blocks = std::max<uint64_t>(1, c->n_slots * c->bloom_bytes_per_slot / 8);
-  if (c->n_filter_blocks > (1ull << 32)) c->n_filter_blocks = 1ull << 32;
-  c->slots.alloc(c->n_slots);
-  c->filter.alloc(c->n_filter_blocks);
-  c->hashes.alloc(c->n);
+  if (c->too_long) { g_err = "sequences longer than 5,000 nt need enum_mode JOIN (the enumeration kernels keep per-position tables on chip)"; return SWB200_EUNSUPPORTED; }
   c->tic();
-  CK(cudaMemsetAsync(c->slots.p, 0xFF, c->n_slots * sizeof(Slot), c->stream));
-  CK(cudaMemsetAsync(c->filter.p, 0, c->n_filter_blocks * 8, c->stream));
-  CK(cudaMemsetAsync(c->counters.p, 0, 16 * 8, c->stream));
-  D1Params P = c->params();
-  const size_t zbytes = static_cast<size_t>(c->zlen) * 32;
-  CK(cudaFuncSetAttribute(k_d1_index, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(zbytes)));
-  const int grid = std::min<int>(c->sm_count * 8, (c->n + 255) / 256);
-  k_d1_index<<<grid, 256, zbytes, c->stream>>>(P);
-  CK(cudaGetLastError());
-  k_d1_dupcheck<<<(c->n + 255) / 256, 256, 0, c->stream>>>(P);
-  CK(cudaGetLastError());
-  c->launches += 2;
-  uint32_t dup = 0;
-  CK(cudaMemcpyAsync(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+  const bool dup = index_table(c);
   c->toc(1);
   c->indexed = true;
   c->have_network = c->clustered = false;
@@ -654,9 +751,25 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
   c->ncb = no_cluster_breaking ? 1 : 0;
   if (c->edges.n == 0) c->edges.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 4, 1u << 16));
   c->tic();
-  for (int attempt = 0; attempt < 2; ++attempt) {
+  for (int attempt = 0; attempt < 4; ++attempt) {
     CK(cudaMemsetAsync(c->counters.p, 0, 10 * 8, c->stream));
-    if (c->tile_active) {
+    if (c->ts_active) {
+      TileStoreParams J = ts_params(c);
+      const uint32_t T = c->ts_hi - c->ts_lo;
+      if (T) {
+        if (c->collect_stats) {
+          CK(cudaFuncSetAttribute(k_ts_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->ts_smem)));
+          k_ts_join<true><<<T, 256, c->ts_smem, c->stream>>>(J);
+          k_ts_big<true><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
+        } else {
+          CK(cudaFuncSetAttribute(k_ts_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->ts_smem)));
+          k_ts_join<false><<<T, 256, c->ts_smem, c->stream>>>(J);
+          k_ts_big<false><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
+        }
+        c->launches += 2;
+        CK(cudaGetLastError());
+      }
+    } else if (c->tile_active) {
       TileJoinParams J = tile_params(c);
       const uint32_t T = c->tj_hi - c->tj_lo;
       if (T) {
@@ -702,7 +815,7 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
       CK(cudaGetLastError());
     } else
     run_network(c);
-    unsigned long long host[6];
+    unsigned long long host[37];                                           // one read-back: links, stats, duplicate flag, overflow counters
     CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_edges = host[0];
@@ -710,11 +823,25 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
     c->stats[4] = c->n_edges;
     c->stats[6] = host[5];
     if (c->tile_active && c->collect_stats) c->stats[0] = c->tj_total;     // entries of this rank's tiles (2 per amplicon over all ranks)
-    if (c->join_active) {
-      uint32_t dup = 0;
-      CK(cudaMemcpy(&dup, c->counters.p + 8, 4, cudaMemcpyDeviceToHost));
-      if (dup) { c->toc(2); g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
+    if (c->ts_active) {
+      const unsigned long long *ov = host + 32;                            // [0] overflow records [1] their pair tests [2] abort flag
+      c->ts_overflow = ov[0];
+      if (c->collect_stats) c->stats[0] = host[36];                        // records appended to this rank's tiles (2 per amplicon over all ranks)
+      if (ov[0] > c->ts_ovf_cap) {                                         // the overflow list itself overflowed: grow it, index again
+        c->ts_ovf_cap = ov[0] + ov[0] / 8 + 1024;
+        index_tilestore(c);
+        continue;
+      }
+      if (static_cast<uint32_t>(ov[2])) {
+        // dense data: a few K-mers are shared by so many amplicons that the pairwise sweep of their tiles is quadratic;
+        // the enumeration kernels are linear in the data, like the reference (src/algod1.cc:606-670)
+        c->ts_active = c->join_active = false;
+        c->ts_fallbacks++;
+        if (index_table(c)) { c->toc(2); g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
+        continue;
+      }
     }
+    if (c->join_active && static_cast<uint32_t>(host[8])) { c->toc(2); g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
     if (c->n_edges <= c->edges.n) break;
     c->edges.alloc(c->n_edges + c->n_edges / 8);    // link list overflowed: grow and redo (dense data)
   }
@@ -793,6 +920,40 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
+  if (c->cluster_kernel == 0 || c->cluster_kernel == 4) {
+    // frontier relaxation over 8-slot out-rows, one persistent cooperative kernel (d1_frontier.cuh)
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_frontier, 256, 0));
+    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+    FrontierParams F{};
+    F.edges = c->edges.p; F.m = m; F.n = n;
+    F.key = c->key.p; F.parent = c->parent.p; F.label = c->label.p; F.generation = c->generation.p;
+    F.nwords = (n + 31) / 32;
+    c->cl_bits.alloc(static_cast<size_t>(F.nwords) * 3);
+    c->fr_deg.alloc(n); c->fr_adj.alloc(static_cast<size_t>(n) * kFrSlots);
+    if (c->fr_spill.n < m) c->fr_spill.alloc(std::max<uint64_t>(m + m / 8, 1));      // worst case: one hub owns every link
+    F.bits = c->cl_bits.p; F.deg = c->fr_deg.p; F.adj = c->fr_adj.p;
+    F.spill = c->fr_spill.p; F.spill_n = c->counters.p + 35; F.spill_cap = c->fr_spill.n;
+    F.flags = reinterpret_cast<uint32_t *>(c->counters.p + 17); F.rounds_out = reinterpret_cast<uint32_t *>(c->counters.p + 19);
+    if (std::getenv("SWB200_CLUSTER_TS")) {                    // profiling aid: phase timestamps of the persistent kernel on stderr
+      c->cl_ts.alloc(64);
+      CK(cudaMemsetAsync(c->cl_ts.p, 0, 64 * 8, c->stream));
+      F.ts = c->cl_ts.p;
+    }
+    void *args[] = {&F};
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_frontier), dim3(grid), dim3(256), args, 0, c->stream));
+    c->launches++;
+    if (F.ts) {
+      unsigned long long h[64];
+      CK(cudaMemcpyAsync(h, c->cl_ts.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      std::fprintf(stderr, "[cluster_frontier n=%u m=%llu] us (init, build + round 0, rounds ..., parents + unpack):", n, static_cast<unsigned long long>(m));
+      for (int i = 1; i < 64 && h[i]; ++i) std::fprintf(stderr, " %.1f", (h[i] - h[i - 1]) * 1e-3);
+      std::fprintf(stderr, "\n");
+    }
+    return;
+  }
   if (c->cluster_kernel == 3 && m < 0xFFFFFFF0ull) {
     // links counting-sorted by source + frontier relaxation, one persistent cooperative kernel (d1_cluster.cuh)
     int occ = 1;
@@ -828,7 +989,7 @@ static void run_cluster(swb200_ctx *c) {
     }
     return;
   }
-  if (c->cluster_kernel == 0 || c->cluster_kernel == 3) {
+  if (c->cluster_kernel == 5 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
     auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;
@@ -902,7 +1063,7 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
   c->clustered = true;
   {                                                           // rounds the relaxation took (stats[7]; persistent kernels only)
     uint32_t rounds = 0;
-    if (c->cluster_kernel == 0 || c->cluster_kernel == 3)
+    if (c->cluster_kernel == 0 || c->cluster_kernel >= 3)
       CK(cudaMemcpyAsync(&rounds, reinterpret_cast<uint32_t *>(c->counters.p + 19), 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->stats[7] = rounds;
@@ -1342,6 +1503,8 @@ int swb200_get_stats(swb200_ctx *c, uint64_t *out, int n) {
   for (int i = 0; i < n && i < 8; ++i) out[i] = c->stats[i];
   for (int i = 8; i < n && i < 12; ++i) out[i] = c->fstats[i - 8];
   for (int i = 12; i < n && i < 16; ++i) out[i] = c->dnstats[i - 12];
+  if (n > 16) out[16] = c->ts_overflow;
+  if (n > 17) out[17] = c->ts_fallbacks;
   return SWB200_OK;
 }
 

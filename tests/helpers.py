@@ -276,3 +276,71 @@ def run_ref(fasta, *flags, outputs=("o",), threads=1):
             res[o] = open(f, "rb").read() if os.path.exists(f) else b""
         res["log"] = open(os.path.join(td, "log"), "rb").read() if os.path.exists(os.path.join(td, "log")) else b""
     return res
+
+
+# ---- parity at BASELINE scale: SHA-256 of the reference's outputs (tests/golden/scale_hashes.json, written by
+# tests/golden/make_scale_hashes.py in the build container, where /root/reference compiles).  A case = generator
+# arguments + reference flags; bench.py and the slow GPU tests rebuild the same FASTA and compare hashes.
+SCALE_CASES = {
+    # name: (n, L, seed, ab_mode, reference flags, reference threads)
+    "c2": (10_000_000, 150, 42, 0, (), 8),                     # BASELINE configs[1]
+    "c3": (10_000_000, 150, 42, 0, ("-f",), 1),                # configs[2]; -t 1: the reference's light pass races
+    "c4": (1_000_000, 400, 42, 0, ("-d", "2"), 8),             # configs[3]
+    "tie1m": (1_000_000, 150, 42, 1, (), 8),                   # tie-heavy: 70 % of the abundances are 1
+    "tie1m_f": (1_000_000, 150, 42, 1, ("-f",), 1),
+    "c2_1m": (1_000_000, 150, 42, 0, (), 8),                   # the same generator stream at the size the GPU test suite uses
+    "c3_1m": (1_000_000, 150, 42, 0, ("-f",), 1),
+    "c4_100k": (100_000, 400, 42, 0, ("-d", "2"), 8),
+}
+SCALE_HASHES = GOLDEN / "scale_hashes.json"
+
+_canon = None
+
+
+def canon_lib():
+    global _canon
+    if _canon is None:
+        L = C.CDLL(str(ROOT / "tools" / "libcanon.so"))
+        L.canon_sha256.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+        L.canon_sha256.restype = C.c_int64
+        L.sha256_hex.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p]
+        L.sha256_hex.restype = None
+        _canon = L
+    return _canon
+
+
+def canon_sha256(text: bytes) -> str:
+    """SHA-256 of the canonical form (ids sorted inside each line, lines sorted)"""
+    b = C.create_string_buffer(65)
+    if canon_lib().canon_sha256(text, len(text), b) < 0:
+        raise MemoryError("canon_sha256")
+    return b.value.decode()
+
+
+def sha256_hex(data: bytes) -> str:
+    b = C.create_string_buffer(65)
+    canon_lib().sha256_hex(data, len(data), b)
+    return b.value.decode()
+
+
+def scale_fasta(name: str) -> str:
+    n, L, seed, ab_mode, _flags, _t = SCALE_CASES[name]
+    path = f"/dev/shm/swb200_{n}x{L}_s{seed}" + ("_tie" if ab_mode else "") + ".fa"
+    if not os.path.exists(path):
+        make_fasta(path + ".tmp", n, L, seed, ab_mode)
+        os.replace(path + ".tmp", path)
+    return path
+
+
+def scale_hashes() -> dict:
+    import json
+    return json.loads(SCALE_HASHES.read_text()) if SCALE_HASHES.exists() else {}
+
+
+def output_hashes(o: bytes, s: bytes | None = None, i: bytes | None = None) -> dict:
+    h = {"o_canonical_sha256": canon_sha256(o), "o_sha256": sha256_hex(o), "swarms": o.count(b"\n")}
+    if s is not None:
+        h["s_sha256"] = sha256_hex(s)
+    if i is not None:
+        h["i_sha256"] = sha256_hex(i)
+    return h
