@@ -1,0 +1,30 @@
+#!/bin/bash
+# One parametrised runner for the GPU box (under gpurun): scripts/gpu_run.sh TAG step [step ...]
+#   steps: box | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
+# Everything lands in gpurun_out/TAG_*.
+cd "$(dirname "$0")/.." || exit 1
+mkdir -p gpurun_out
+TAG=$1; shift
+O=gpurun_out
+for step in "$@"; do
+  name=${step%%:*}; arg=""; [[ "$step" == *:* ]] && arg=${step#*:}
+  case $name in
+    box) (nvidia-smi; nvidia-smi topo -m; lscpu | head -20; free -g) > $O/${TAG}_box.txt 2>&1 ;;
+    tests) if [ -n "$arg" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -k "$arg" > $O/${TAG}_tests.log 2>&1; else timeout 2400 python -m pytest tests -x -q -m gpu > $O/${TAG}_tests.log 2>&1; fi
+           echo "== tests rc=$?"; tail -5 $O/${TAG}_tests.log ;;
+    scale) timeout 1500 python -m pytest tests/test_gpu_scale.py -x -q -m gpu > $O/${TAG}_scale.log 2>&1; echo "== scale rc=$?"; tail -5 $O/${TAG}_scale.log ;;
+    bench) timeout 1500 python bench.py $arg > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "== bench rc=$?"; tail -c 2500 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err ;;
+    probe) timeout 900 python scripts/probe.py $arg > $O/${TAG}_probe.log 2>&1; echo "== probe rc=$?"; cat $O/${TAG}_probe.log ;;
+    ts) SWB200_CLUSTER_TS=1 timeout 600 python scripts/probe.py 10000000 default= > $O/${TAG}_ts.log 2>&1; grep -E "cluster_frontier|cluster_dist" $O/${TAG}_ts.log | tail -3 ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv \
+                python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_launches.out 2>&1
+              python scripts/ncu_summary.py launches $O/${TAG}_launches.csv > $O/${TAG}_launches.txt; head -20 $O/${TAG}_launches.txt ;;
+    full) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
+          timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
+            python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_full_$k.out 2>&1
+          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -40 $O/${TAG}_$k.txt ;;
+    sanitize) bash scripts/gpu_sanitize.sh ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+ls -la $O | tail -20

@@ -344,3 +344,43 @@ def output_hashes(o: bytes, s: bytes | None = None, i: bytes | None = None) -> d
     if i is not None:
         h["i_sha256"] = sha256_hex(i)
     return h
+
+
+def engine_case_outputs(name: str, device: int = 0, db=None, **opt):
+    """the CUDA engine (through the C ABI) on SCALE_CASES[name]: returns the digests of its -o / -s / -i texts, computed
+    exactly like tests/golden/make_scale_hashes.py computes the reference's"""
+    from swarm_b200 import D1Result, DnResult, Engine, HostDb, scoring
+    n, L, seed, ab_mode, flags, _t = SCALE_CASES[name]
+    d = int(flags[flags.index("-d") + 1]) if "-d" in flags else 1
+    own_db = db is None
+    if own_db:
+        db = HostDb(scale_fasta(name), check_dup_sequences=d > 1)
+    eng = Engine(device, **opt)
+    try:
+        eng.load(db)
+        if d == 1:
+            eng.d1_index()
+            eng.d1_network()
+            sw, gen, par = eng.d1_cluster()
+            gc = None
+            if "-f" in flags:
+                gc, _nl, _nh = eng.d1_fastidious(boundary=3)
+            res = D1Result(db, sw, gen, par, graft_cand=gc, boundary=3)
+        else:
+            sw, gen, par, pd = eng.dn_cluster(d, penalties=scoring())
+            res = DnResult(db, sw, gen, par, pd)
+        h = output_hashes(res.swarms_text(), res.stats_text(), res.structure_text())
+        res.close()
+    finally:
+        eng.close()
+        if own_db:
+            db.close()
+    return h
+
+
+def compare_case(name: str, got: dict) -> list:
+    """keys on which `got` differs from the committed reference digests of case `name` ([] = parity)"""
+    want = scale_hashes().get(name)
+    if want is None:
+        return ["no golden digests for " + name]
+    return [k for k in ("o_canonical_sha256", "o_sha256", "s_sha256", "i_sha256", "swarms") if got.get(k) != want.get(k)]

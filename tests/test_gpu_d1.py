@@ -189,6 +189,31 @@ def test_join_dense_group(built, tmp_path, group):
         assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
 
 
+def test_skew_fallback_to_enumeration(built):
+    """dense data: 9 000 amplicons share both K-mers, so the two tiles that hold them overflow by 8 k records each and
+    the pairwise sweep would cost 8e7 pair tests: swb200_d1_network abandons the join for the linear HALF enumeration
+    (the reference is linear in density, src/algod1.cc:606-670).  Same links, same swarms; with the fallback disabled the
+    sweep itself must give them too."""
+    rng = np.random.default_rng(11)
+    cen = rng.integers(0, 4, 200)
+    seqs = {"".join("ACGT"[b] for b in cen)}
+    while len(seqs) < 9000:
+        s = cen.copy()
+        for p in rng.integers(66, 134, 2 if rng.random() < 0.97 else 1):
+            s[p] = (s[p] + int(rng.integers(1, 4))) % 4
+        seqs.add("".join("ACGT"[b] for b in s))
+    text = "".join(f">d{i}_{1 + (i * 7919) % 50}\n{s}\n" for i, s in enumerate(sorted(seqs))).encode()
+    db = HostDb(text=text)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    for opt, fallbacks in (({}, 1), ({"skew_fallback": 0}, 0)):
+        links, sw, gen, par, _rp, _col, stats = run_engine(db, ENUM_JOIN, **opt)
+        assert stats["skew_fallbacks"] == fallbacks and stats["tile_overflow"] > 15000
+        assert np.array_equal(links, orc.links())
+        assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
+
+
 def test_duplicates_rejected(built):
     db = HostDb(text=b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>c_1\nACGTACGA\n")
     eng = Engine(0, enum_mode=ENUM_HALF)
