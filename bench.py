@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark: amplicons clustered per second at d=1 (BASELINE.json).
+"""bench.py — headline benchmark: amplicons clustered per second (BASELINE.json), CUDA engine vs the reference's CPU code.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--amplicons 10000000] [--length 150]
-    python bench.py --impl reference ...        # the reference's own CPU implementation, same metric
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--amplicons N] [--length L]
+    python bench.py --impl reference ...        # the reference's own CPU implementation, same metric, same config
 
-A "step" is one pass of the d=1 hot path (index -> network -> cluster) over one synthetic amplicon
-set (BASELINE.md §3.2 generator, seed 42).  N=1 workload = BASELINE.json configs[1]: 10 M x 150 bp.
+A "step" is one pass of the hot path over one synthetic amplicon set (BASELINE.md §3.2 generator, seed 42):
+  c2 (default)  10 M x 150 bp, d=1: index -> network -> cluster                      BASELINE configs[1]
+  c3            the same + the --fastidious graft search                              configs[2]
+  c4            1 M x 400 bp, d=2: q-gram vectors, candidates, exact aligner, cluster configs[3]
+  c5            --gpus 8: 8 x 12.5 M = 100 M x 150 bp, d=1, ONE job                   configs[4]
   value : whole-job amplicons/s with the packed database already resident in HBM (device path only)
-  e2e   : the same metric through the C ABI with HOST buffers: swb200_load_db_compact (H2D from pinned host
-          memory: packed words, u16 lengths, abundance runs — 420 MB instead of swb200_load_db's 520 MB at 10 M)
-          + index + network + cluster + D2H of the three result arrays, every step
-  roofline     : the network kernel, algorithmic bytes per launch (SURVEY.md §8d formula) / CUDA-event time
-  cpu_baseline : oracle/_ref/swarm_timed (the unmodified reference + phase timers) on a bounded sample
-N>1 (torchrun, one rank per GPU), weak scaling: ONE clustering job of N x --amplicons amplicons.  Every GPU holds
-the whole packed database (e2e: each rank uploads its own rows over PCIe, the rest arrives by NCCL all-gather over
-NVLink), the join tiles are sharded by hash range, the directed links are exchanged with an NCCL all-gather(v),
-clustering runs replicated; device time = CUDA events on the engine's stream, max over ranks.
+  e2e   : the same metric through the C ABI with HOST buffers: upload from pinned host memory + the step + D2H of the result
+          arrays into pinned host memory, every step
+  roofline     : the dominant kernel of the step (largest CUDA-event time): algorithmic bytes per launch / its time; all
+                 phases under roofline.phases
+  cpu_baseline : oracle/_ref/swarm_timed (the unmodified reference + phase timers) on the host cores
+  parity       : UNTIMED leg.  N=1: the engine's -o/-s/-i texts, hashed, against the committed digests of the reference's
+                 outputs on the same input (tests/golden/scale_hashes.json); N>1: every rank's rows against the single-GPU
+                 engine run on the gathered database by rank 0.
+N>1 (torchrun, one rank per GPU), weak scaling: ONE clustering job of N x --amplicons amplicons (see swarm_b200/multi.py).
 """
 import argparse
 import json
@@ -32,15 +35,16 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-METRIC = "amplicons clustered/s (device-timed) at d=1"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the network kernel(s) at 10 M x 150 bp, from the committed
-# ncu --set full captures: tile = k_tile_join (1.945+0.071 GB), profiles/r1k_*;
-# JOIN multimap = k_join_candidates (2.954+0.320 GB) + k_join_verify (5.897+0.071 GB), profiles/r1h_*;
-# HALF (lean kernel) = 2.639+0.028 GB per 4 M seeds scaled to 10 M, profiles/r1d_*
-TRAFFIC = {"tile": 2.016e9, "join": 9.242e9, "half": 6.67e9, "full": None}
 UNIT = "amplicons/s"
-
-
+CONFIGS = {
+    # name: (amplicons per GPU, length, d, fastidious, BASELINE label, scale-hash case, metric)
+    "c2": (10_000_000, 150, 1, False, "BASELINE configs[1]", "c2", "amplicons clustered/s (device-timed) at d=1"),
+    "c3": (10_000_000, 150, 1, True, "BASELINE configs[2]", "c3", "amplicons clustered/s (device-timed) at d=1 --fastidious"),
+    "c4": (1_000_000, 400, 2, False, "BASELINE configs[3]", "c4", "amplicons clustered/s (device-timed) at d=2"),
+    "c5": (12_500_000, 150, 1, False, "BASELINE configs[4]", None, "amplicons clustered/s (device-timed) at d=1"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 M x 150 bp from the committed ncu --set full captures
+TRAFFIC = {}          # kernel -> (bytes, profiles/ file); filled in from profiles/traffic.json when present
 JSON_FD = 1
 
 
@@ -57,7 +61,8 @@ def env_int(k, d):
 def make_dataset(n, L, seed, path):
     import helpers
     if not Path(path).exists():
-        helpers.make_fasta(path, n, L, seed)
+        helpers.make_fasta(path + ".tmp%d" % os.getpid(), n, L, seed)
+        os.replace(path + ".tmp%d" % os.getpid(), path)
     return path
 
 
@@ -69,6 +74,7 @@ class ClockSampler:
         self.stop = False
         self.index = index
         self.t = None
+        self.p = None
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -107,152 +113,120 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, rank, world):
-    """--impl reference: the reference's own CPU implementation (oracle/_ref/swarm_timed = unmodified
-    reference sources + a timing-only progress shim) on the host cores, bounded sample of the workload."""
+# ---- the reference's CPU implementation (oracle/_ref/swarm_timed = unmodified reference sources + a timing-only progress shim)
+REF_PHASES = {
+    1: ("Hashing sequences", "Building network", "Clustering"),
+    "f": ("Hashing sequences", "Building network", "Clustering", "Adding light swarm amplicons to Bloom filter",
+          "Checking heavy swarm amplicons against Bloom filter", "Grafting light swarms on heavy swarms"),
+    2: ("Find qgram vects", "Clustering"),
+}
+
+
+def run_reference(fa, d, fastidious, threads):
+    """one run of the reference binary; returns (sum of the hot-path phases in s, per-phase dict)"""
+    binp = ROOT / "oracle" / "_ref" / "swarm_timed"
+    with tempfile.NamedTemporaryFile(suffix=".pt", delete=False) as tf:
+        pt = tf.name
+    cmd = [str(binp), "-t", str(threads), "-l", os.devnull, "-o", os.devnull]
+    if d != 1:
+        cmd += ["-d", str(d)]
+    if fastidious:
+        cmd += ["-f"]
+    subprocess.run(cmd + [fa], check=True, env=dict(os.environ, SWARM_PHASE_TIMES=pt), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ph = {}
+    for line in open(pt):
+        k, v = line.rstrip("\n").split("\t")
+        ph[k.strip().rstrip(":")] = ph.get(k.strip().rstrip(":"), 0.0) + float(v)
+    os.unlink(pt)
+    want = REF_PHASES["f" if fastidious else (1 if d == 1 else 2)]
+    used = {k: v for k, v in ph.items() if any(k.startswith(w) for w in want)}
+    return sum(used.values()), used
+
+
+def reference_sample(args, cfg, full):
+    """(sample size, same_config): the whole workload when one run takes a few tens of seconds, else a bounded prefix of
+    the same generator stream"""
+    n_gpu, L, d, fast, *_ = cfg
+    n = args.amplicons
+    if args.cpu_sample:
+        return min(args.cpu_sample, n), args.cpu_sample >= n
+    if d == 1 and not fast:
+        cap = 10_000_000                                  # ~5 s of phases, ~20 s whole process at 16 threads
+    elif d == 1:
+        cap = 10_000_000 if full else 1_000_000           # -f: a minute or more at 10 M
+    else:
+        cap = 100_000                                     # d=2 at 1 M x 400 bp: ~20 min (BASELINE.md §2)
+    return min(cap, n), cap >= n
+
+
+def reference_arm(args, cfg, rank, world):
+    """--impl reference: the reference's own CPU code on the host cores, same metric and config.  Rank 0 only."""
     if rank != 0:
         return
-    import helpers  # noqa: F401
+    n_gpu, L, d, fast, label, _case, metric = cfg
     binp = ROOT / "oracle" / "_ref" / "swarm_timed"
     if not binp.exists():
         emit({"impl": "reference", "unavailable": "oracle/_ref/swarm_timed was not built (needs /root/reference at build time)"})
         return
-    sample = args.cpu_sample
-    fa = make_dataset(sample, args.length, args.seed, f"/dev/shm/swb200_ref_{sample}x{args.length}_s{args.seed}.fa")
+    sample, same = reference_sample(args, cfg, True)
+    fa = make_dataset(sample, L, args.seed, f"/dev/shm/swb200_{sample}x{L}_s{args.seed}.fa")
     threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-    times = []
-    for it in range(args.warmup + args.steps):
-        with tempfile.NamedTemporaryFile(suffix=".pt", delete=False) as tf:
-            pt = tf.name
-        env = dict(os.environ, SWARM_PHASE_TIMES=pt)
-        subprocess.run([str(binp), "-t", str(threads), "-l", os.devnull, "-o", os.devnull, fa], check=True, env=env,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        ph = {}
-        for line in open(pt):
-            k, v = line.rstrip("\n").split("\t")
-            ph[k.strip().rstrip(":")] = float(v)
-        os.unlink(pt)
-        t = ph["Hashing sequences"] + ph["Building network"] + ph["Clustering"]
-        if it >= args.warmup:
+    # bounded repeats: one run of the full 10 M workload is ~20 s of wall time (FASTA parse + sort included, untimed)
+    warm, runs = min(args.warmup, 1), max(1, min(args.steps, 3))
+    if fast or d != 1:
+        warm, runs = 0, 1
+    times, phases = [], None
+    for it in range(warm + runs):
+        t, phases = run_reference(fa, d, fast, threads)
+        if it >= warm:
             times.append(t)
     ms = 1e3 * sum(times) / len(times)
     val = sample / (ms * 1e-3)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{args.amplicons} x {args.length} bp synthetic amplicons, d=1 (BASELINE configs[1])",
-                       "sample": f"first {sample} amplicons of the same seeded generator stream",
-                       "phases_timed": "Hashing sequences + Building network + Clustering (reference's own phases)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
-                             "sample": f"{sample} x {args.length} bp, -t {threads}, phases hash+network+cluster"},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit(line)
+    wl = f"{args.amplicons} x {L} bp synthetic amplicons, d={d}" + (" --fastidious" if fast else "") + f" ({label})"
+    emit({"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": world, "steps": runs, "warmup": warm,
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+          "config": {"workload": wl, "same_config": bool(same),
+                     "sample": ("the whole workload" if same else f"first {sample} amplicons of the same seeded generator stream"),
+                     "phases_timed": " + ".join(phases) + " (the reference's own phases, steady_clock)",
+                     "requested_steps_warmup": [args.steps, args.warmup]},
+          "phases_s": phases,
+          "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                           "sample": f"{sample} x {L} bp, -t {threads}, {runs} run(s)"},
+          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
-def cpu_baseline(args):
-    binp = ROOT / "oracle" / "_ref" / "swarm_timed"
-    if not binp.exists():
+def cpu_baseline(args, cfg):
+    n_gpu, L, d, fast, *_ = cfg
+    if not (ROOT / "oracle" / "_ref" / "swarm_timed").exists():
         return None
-    sample = args.cpu_sample
-    fa = make_dataset(sample, args.length, args.seed, f"/dev/shm/swb200_ref_{sample}x{args.length}_s{args.seed}.fa")
+    sample, same = reference_sample(args, cfg, False)
+    fa = make_dataset(sample, L, args.seed, f"/dev/shm/swb200_{sample}x{L}_s{args.seed}.fa")
     threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-    with tempfile.NamedTemporaryFile(suffix=".pt", delete=False) as tf:
-        pt = tf.name
-    env = dict(os.environ, SWARM_PHASE_TIMES=pt)
-    subprocess.run([str(binp), "-t", str(threads), "-l", os.devnull, "-o", os.devnull, fa], check=True, env=env,
-                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    ph = {}
-    for line in open(pt):
-        k, v = line.rstrip("\n").split("\t")
-        ph[k.strip().rstrip(":")] = float(v)
-    os.unlink(pt)
-    t = ph["Hashing sequences"] + ph["Building network"] + ph["Clustering"]
+    t, phases = run_reference(fa, d, fast, threads)
     return {"value": sample / t, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": f"first {sample} of the workload's amplicons, reference binary -t {threads}, phases hash+network+cluster = {t:.3f} s"}
+            "sample": ("the whole workload" if same else f"first {sample} of the workload's amplicons") +
+                      f", reference binary -t {threads}, phases {' + '.join(phases)} = {t:.3f} s"}
 
 
-def build_weak_dataset(args, rank, world):
-    """N>1: ONE clustering job of world x args.amplicons amplicons.  Every rank generates and parses its own set
-    (generator seed + rank: independent random centroids, so the union has no duplicate sequences), the packed rows
-    are gathered on every GPU and put into the reference's database order — abundance descending (src/db.cc:392-406;
-    ties in rank/header order, a stable sort) — with torch (setup only, not timed, not part of the product)."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from swarm_b200 import HostDb
-    fa = f"/dev/shm/swb200_{args.amplicons}x{args.length}_s{args.seed + rank}.fa"
-    make_dataset(args.amplicons, args.length, args.seed + rank, fa)
-    db = HostDb(fa)
-    stride = torch.tensor([db.stride, db.n], dtype=torch.int64, device="cuda")
-    mx = stride.clone()
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    assert int(mx[1]) == db.n == args.amplicons, "every rank must hold the same number of amplicons"
-    S = int(mx[0])
-    w = torch.zeros((db.n, S), dtype=torch.int64, device="cuda")
-    w[:, : db.stride] = torch.from_numpy(db.words.view(np.int64).reshape(db.n, db.stride)).cuda()
-    ln = torch.from_numpy(db.len.view(np.int32)).cuda()
-    ab = torch.from_numpy(db.abundance.view(np.int64)).cuda()
-    db.close()
-    W = torch.empty((world * args.amplicons, S), dtype=torch.int64, device="cuda")
-    Ln = torch.empty(world * args.amplicons, dtype=torch.int32, device="cuda")
-    Ab = torch.empty(world * args.amplicons, dtype=torch.int64, device="cuda")
-    dist.all_gather_into_tensor(W, w)
-    dist.all_gather_into_tensor(Ln, ln)
-    dist.all_gather_into_tensor(Ab, ab)
-    del w, ln, ab
-    order = torch.sort(Ab, descending=True, stable=True).indices
-    W, Ln, Ab = W[order].contiguous(), Ln[order].contiguous(), Ab[order].contiguous()
-    del order
-    torch.cuda.synchronize()
-    return W, Ln, Ab, S
+def load_traffic():
+    p = ROOT / "profiles" / "traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
 
 
-def two_jobs_in_flight(make_engine, one_job, eng_a, res_a, make_result, steps, n, sync):
-    """2 x `steps` end-to-end jobs, two at a time: a second engine context and one host thread per context, so one job's
-    upload overlaps the other's kernels and download.  Informational (host wall clock); any failure is reported in the
-    returned dict instead of being raised, so it can never take the bench line down."""
-    import numpy as np
-    eng_b = None
-    try:
-        eng_b = make_engine()
-        res_b = make_result()
-        failed = []
-
-        def run(e, r, k):
-            try:
-                for _ in range(k):
-                    one_job(e, r)
-            except Exception as exc:
-                failed.append(repr(exc))
-
-        run(eng_b, res_b, 2)
-        sync()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=run, args=(eng_a, res_a, steps)), threading.Thread(target=run, args=(eng_b, res_b, steps))]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        sync()
-        dt2 = time.perf_counter() - t0
-        if failed:
-            return {"error": failed[0]}
-        same = all(np.array_equal(res_a[k], res_b[k]) for k in res_a)
-        return {"value": 2 * steps * n / dt2, "unit": UNIT, "ms_per_job": 1e3 * dt2 / (2 * steps), "timing": "host wall clock",
-                "results_identical": bool(same)}
-    except Exception as exc:
-        return {"error": repr(exc)}
-    finally:
-        if eng_b is not None:
-            try:
-                eng_b.close()
-            except Exception:
-                pass
-
-
-def per_rank_rows(n, world):
-    """rows the index pass of one rank reads: every rank scans the whole database (its tiles are a hash range)"""
-    return n
+def roofline_block(peak, peaks_found, phases, traffic_key):
+    """phases: {name: {"kernel": .., "bytes": algorithmic bytes per launch, "s": CUDA-event seconds, ...}} -> roofline object for
+    the phase with the largest time, all phases attached"""
+    out = {}
+    for k, v in phases.items():
+        if v["s"] > 0:
+            out[k] = dict(v, achieved=v["bytes"] / v["s"] / 1e9, frac=v["bytes"] / v["s"] / 1e9 / peak, ms=1e3 * v["s"])
+            out[k].pop("s")
+    top = max(out, key=lambda k: out[k]["ms"])
+    tr = load_traffic().get(traffic_key + ":" + top) if traffic_key else None
+    return {"bound": "hbm", "achieved": out[top]["achieved"], "peak": peak, "unit": "GB/s", "frac": out[top]["frac"],
+            "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+            "kernel": out[top]["kernel"], "phase": top, "bytes_per_launch": out[top]["bytes"],
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks_found else "fallback 6650 GB/s", "phases": out}
 
 
 def main():
@@ -261,279 +235,228 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--amplicons", type=int, default=10_000_000, help="amplicons per GPU (the job has gpus x this many)")
-    ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE configuration (default c2; c5 needs --gpus 8)")
+    ap.add_argument("--amplicons", type=int, default=0, help="amplicons per GPU (the job has gpus x this many); default: the config's")
+    ap.add_argument("--length", type=int, default=0)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--enum-mode", type=int, default=2, help="0 full microvariant enumeration, 1 half, 2 pigeonhole join (default)")
-    ap.add_argument("--join-kernel", type=int, default=0, help="JOIN: 0 partitioned join in shared memory (default), 1 global hash multimap")
+    ap.add_argument("--join-kernel", type=int, default=0, help="JOIN: 0 tile store (default), 1 global hash multimap, 2 r1 tile join")
     ap.add_argument("--cluster-kernel", type=int, default=0)
     ap.add_argument("--multi", default="dist", choices=["dist", "replicated"],
-                    help="N>1 clustering: dist = sharded by amplicon range, exchange over peer memory inside the kernel (default); "
+                    help="N>1 clustering: dist = sharded by amplicon, exchange over peer memory inside the kernel (default); "
                          "replicated = links all-gathered with NCCL, every GPU clusters everything")
-    ap.add_argument("--bloom-bytes", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fastidious", action="store_true", help="BASELINE configs[2]: add the --fastidious graft search to every step")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity leg (profiling runs)")
+    ap.add_argument("--fastidious", action="store_true", help="alias of --config c3")
     args = ap.parse_args()
+    if args.config is None:
+        args.config = "c3" if args.fastidious else "c2"
+    cfg = CONFIGS[args.config]
+    args.amplicons = args.amplicons or cfg[0]
+    args.length = args.length or cfg[1]
+    cfg = (args.amplicons, args.length) + cfg[2:]
+    n_gpu, L, d, fast, label, case, metric = cfg
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    # the contract is ONE JSON line on stdout: everything any library prints there meanwhile (NCCL's version banner ...) goes to stderr
+    # the contract is ONE JSON line on stdout: everything any library prints there meanwhile (NCCL's banner / NCCL_DEBUG lines ...)
+    # goes to stderr, where the driver can still read it
     global JSON_FD
     sys.stdout.flush()
     JSON_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, cfg, rank, world)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
-    from swarm_b200 import Engine, HostDb
-    from swarm_b200.ffi import dist_row_ids
-    from swarm_b200.multi import all_gather_db, engine_stream, exchange_engine_links, setup_dist_clustering, shard_rows
+    import helpers
+    from swarm_b200 import D1Result, DnResult, Engine, HostDb, scoring
+    from swarm_b200.ffi import compact_form
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        if not os.environ.get("BENCH_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION/INFO prints to stdout; the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if args.fastidious and world > 1:
-        raise SystemExit("bench.py: --fastidious is a single-GPU configuration (BASELINE configs[2])")
+        if fast or d != 1:
+            raise SystemExit("bench.py: c3 and c4 are single-GPU configurations (BASELINE configs[2], [3])")
+    if args.config == "c5" and world != 8:
+        raise SystemExit("bench.py: c5 is 8 x 12.5 M amplicons: launch with --gpus 8 under torchrun")
 
-    eng = Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, cluster_kernel=args.cluster_kernel,
-                 bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0, shard_rank=rank, shard_world=world)
+    def pinned(count, dtype):
+        return torch.empty(count, dtype=dtype, pin_memory=True).numpy()
 
-    def pinned(n, dtype):
-        return torch.empty(n, dtype=dtype, pin_memory=True).numpy()
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    P_ = 8 * ((L + 31) // 32)
 
-    if world == 1:
-        fa = f"/dev/shm/swb200_{args.amplicons}x{args.length}_s{args.seed}.fa"
-        make_dataset(args.amplicons, args.length, args.seed, fa)
-        db = HostDb(fa)
-        n, stride = db.n, db.stride
-        first, count = 0, n
-        # pinned host copies: what a host application hands to swb200_load_db
-        pw, pl, pa = pinned(n * stride, torch.int64).view(np.uint64), pinned(n, torch.int32).view(np.uint32), pinned(n, torch.int64).view(np.uint64)
-        pw[:], pl[:], pa[:] = db.words, db.len, db.abundance
-        db.close()
-        eng.load_db(pw, stride, pl, pa)
-        # the compact form of the same database (u16 lengths, abundance runs): what the end-to-end path uploads
-        from swarm_b200.ffi import compact_form
-        l16, rab, rst = compact_form(pl, pa)
-        pl16, prab, prst = pinned(n, torch.int16).view(np.uint16), pinned(rab.shape[0], torch.int64).view(np.uint64), pinned(rst.shape[0], torch.int32).view(np.uint32)
-        pl16[:], prab[:], prst[:] = l16, rab, rst
-    else:
-        W, Ln, Ab, stride = build_weak_dataset(args, rank, world)
-        n = W.shape[0]
-        first, count = shard_rows(n, rank, world)
-        # this rank's rows of the sorted database, in pinned host memory: what its host process hands to swb200_load_db_shard
-        pw, pl, pa = pinned(count * stride, torch.int64).view(np.uint64), pinned(count, torch.int32).view(np.uint32), pinned(count, torch.int64).view(np.uint64)
-        pw[:] = W[first:first + count].reshape(-1).cpu().numpy().view(np.uint64)
-        pl[:] = Ln[first:first + count].cpu().numpy().view(np.uint32)
-        pa[:] = Ab[first:first + count].cpu().numpy().view(np.uint64)
-        eng.load_db_device(W.data_ptr(), stride, Ln.data_ptr(), Ab.data_ptr(), n)
-        del W, Ln, Ab
-        torch.cuda.empty_cache()
-    dist_mode = world > 1 and args.multi == "dist"
-    # the rows of the result this rank hands back to its host: its upload range, or (dist) its block-cyclic share
-    own_ids = dist_row_ids(n, rank, world) if dist_mode else np.arange(first, first + count, dtype=np.uint32)
-    res = {k: pinned(own_ids.shape[0], torch.int32).view(np.uint32) for k in ("swarm_of", "generation", "parent")}
-    res_gc = pinned(own_ids.shape[0], torch.int32).view(np.uint32)
-    h2d = (pw.nbytes + pl16.nbytes + prab.nbytes + prst.nbytes) if world == 1 else (pw.nbytes + pl.nbytes + pa.nbytes)
-    d2h = (4 if args.fastidious else 3) * 4 * own_ids.shape[0]
+    if world > 1:
+        from bench_multi import run_multi
+        run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, bool(peaks))
+        return
+
+    # ---------------------------------------------------------------- single GPU
+    fa = f"/dev/shm/swb200_{args.amplicons}x{L}_s{args.seed}.fa"
+    make_dataset(args.amplicons, L, args.seed, fa)
+    db = HostDb(fa, check_dup_sequences=d > 1)
+    n, stride = db.n, db.stride
+    eng = Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, cluster_kernel=args.cluster_kernel, collect_stats=0)
+    # pinned host copies: what a host application hands to the C ABI
+    pw, pl, pa = pinned(n * stride, torch.int64).view(np.uint64), pinned(n, torch.int32).view(np.uint32), pinned(n, torch.int64).view(np.uint64)
+    pw[:], pl[:], pa[:] = db.words, db.len, db.abundance
+    eng.load_db(pw, stride, pl, pa)
+    # the compact form of the same database (u16 lengths, abundance runs): what the end-to-end path uploads
+    l16, rab, rst = compact_form(pl, pa)
+    pl16, prab, prst = pinned(n, torch.int16).view(np.uint16), pinned(rab.shape[0], torch.int64).view(np.uint64), pinned(rst.shape[0], torch.int32).view(np.uint32)
+    pl16[:], prab[:], prst[:] = l16, rab, rst
+    keys = ("swarm_of", "generation", "parent")
+    res = {k: pinned(n, torch.int32).view(np.uint32) for k in keys}
+    res_x = pinned(n, torch.int32).view(np.uint32)             # graft candidates (c3) / differences to the parent (c4)
+    h2d = pw.nbytes + pl16.nbytes + prab.nbytes + prst.nbytes
+    d2h = (4 if (fast or d != 1) else 3) * 4 * n
+    pen = scoring()
+    from swarm_b200.multi import engine_stream
     ext = engine_stream(eng)
-    if dist_mode:
-        setup_dist_clustering(eng, n)
 
     def device_step():
-        eng.d1_index()
-        eng.d1_network()
-        if dist_mode:
-            eng.d1_cluster_dist(None)
-            return
-        exchange_engine_links(eng)
-        eng.d1_cluster(want=())
-        if args.fastidious:
-            eng.d1_fastidious(want=False)
+        if d == 1:
+            eng.d1_index()
+            eng.d1_network()
+            eng.d1_cluster(want=())
+            if fast:
+                eng.d1_fastidious(want=False)
+        else:
+            eng.dn_cluster(d, penalties=pen, want=False)
 
     def e2e_step():
-        if world == 1:
-            eng.load_db_compact(pw, stride, pl16, prab, prst)
+        eng.load_db_compact(pw, stride, pl16, prab, prst)
+        if d == 1:
+            eng.d1_index()
+            eng.d1_network()
+            eng.d1_cluster(out=res)
+            if fast:
+                eng.d1_fastidious(out=res_x)
         else:
-            eng.load_db_shard(pw, stride, pl, pa, n, first)
-            all_gather_db(eng, n, stride)
-        eng.d1_index()
-        eng.d1_network()
-        if dist_mode:
-            return eng.d1_cluster_dist(res)
-        exchange_engine_links(eng)
-        if world == 1:
-            r = eng.d1_cluster(out=res)
-        else:
-            eng.d1_cluster(want=())
-            r = eng.d1_get_cluster(first, count, res)
-        if args.fastidious:
-            eng.d1_fastidious(out=res_gc)
-        return r
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+            eng.dn_cluster(d, penalties=pen, out=dict(res, pdiff=res_x))
 
     def timed(step, k):
-        """K steps bracketed by barrier + synchronize on both sides; device time from CUDA events on the engine's stream"""
+        """K steps bracketed by synchronize on both sides; device time from CUDA events on the engine's stream"""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         ev0.record(ext)
-        out = None
         for _ in range(k):
-            out = step()
+            step()
         ev1.record(ext)
-        sync_all()
-        return ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0, out
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) * 1e-3, time.perf_counter() - t0
 
     for _ in range(args.warmup):
         device_step()
     launches0 = eng.stats()["launches"]
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    phase = {1: [], 2: [], 3: [], 4: []}
+    sampler.start()
+    phase_ids = (1, 2, 3, 4) if d == 1 else (6,)
+    phase = {p: [] for p in phase_ids}
 
     def device_step_logged():
         device_step()
         for p in phase:
             phase[p].append(eng.phase_seconds(p))
 
-    dt, wall, _ = timed(device_step_logged, args.steps)
+    dt, wall = timed(device_step_logged, args.steps)
     launches = eng.stats()["launches"] - launches0
-    eng.set_option("collect_stats", 1)      # one extra, untimed pass with the counting kernel variant
+    eng.set_option("collect_stats", 1)      # one extra, untimed pass with the counting kernel variants
     device_step()
     st = eng.stats()
     eng.set_option("collect_stats", 0)
-    # e2e: host buffers in, host arrays out, every step
     for _ in range(min(args.warmup, 3)):
         e2e_step()
-    dt_e2e, wall_e2e, (sw, gen, par) = timed(e2e_step, args.steps)
-    clocks = sampler.finish() if rank == 0 else None
+    dt_e2e, wall_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.finish()
 
-    # informational: the same end-to-end call with TWO jobs in flight (two contexts on the GPU, one host thread each):
-    # job B's upload runs while job A computes and downloads.  Host wall clock over 2 x K steps; not the headline e2e.
-    two_jobs = None
-    if world == 1 and not args.fastidious:
-        def make_engine():
-            return Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, cluster_kernel=args.cluster_kernel,
-                          bloom_bytes_per_slot=args.bloom_bytes, collect_stats=0)
-
-        def one_job(e, r):
-            e.load_db_compact(pw, stride, pl16, prab, prst)
-            e.d1_index()
-            e.d1_network()
-            e.d1_cluster(out=r)
-
-        two_jobs = two_jobs_in_flight(make_engine, one_job, eng, res, lambda: {k: pinned(n, torch.int32).view(np.uint32) for k in res},
-                                      args.steps, n, torch.cuda.synchronize)
-
-    times = torch.tensor([dt, dt_e2e, wall, wall_e2e], dtype=torch.float64, device="cuda")
-    stat_t = torch.tensor([st["variants"], st["filter_pass"], st["slots_visited"], st["exact_compares"], st["links"], st["rows_gathered"],
-                           int((sw == own_ids).sum())], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stat_t, op=dist.ReduceOp.SUM)
-    dt, dt_e2e, wall, wall_e2e = (float(x) for x in times)
-    cnt = [int(x) for x in stat_t]
-
-    if rank == 0:
-        peaks = {}
-        pk = ROOT / "MEASURED_PEAKS.json"
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        net_s = sum(phase[2]) / len(phase[2])
-        mode = {0: "full", 1: "half", 2: "join"}[args.enum_mode]
-        tile = args.enum_mode == 2 and args.join_kernel == 0
-        P_ = 8 * ((args.length + 31) // 32)
-        V, fp_, s_, c_, e_, rows_ = (x / n for x in cnt[:6])
-        if tile:
-            # partitioned join (k_tile_join): 2 entries of 8 B read, one packed row per entry that has a same-key partner,
-            # 2 abundances per tie candidate (bounded by the links), links written; pairs are decided from shared memory
-            b1_counted = 16 + P_ * rows_ + 8 * e_ + 16 * e_
-            kernel = "k_tile_join"
-        elif args.enum_mode == 2:
-            b1_counted = P_ + 16 + 8 * s_ + 16 * fp_ + (2 * P_ + 16) * c_ + 8 * e_
-            kernel = "k_join_candidates + k_join_verify (network phase)"
+    # ---- parity (untimed): the engine's output files, hashed, vs the reference's digests for this input
+    parity = None
+    if not args.no_parity:
+        hashes = helpers.scale_hashes()
+        cand = [k for k, v in hashes.items() if (v["n"], v["length"], v["seed"], v["ab_mode"]) == (n, L, args.seed, 0)
+                and v["flags"] == " ".join((["-f"] if fast else []) + (["-d", str(d)] if d != 1 else []))]
+        if d == 1:
+            r = D1Result(db, res["swarm_of"], res["generation"], res["parent"], graft_cand=res_x if fast else None, boundary=3)
         else:
-            # SURVEY.md §8d: B1 = P + 16 + 8 V + 16 s + (P+8) c + 8 e with the implementation's own counters
-            b1_counted = P_ + 16 + 8 * V + 16 * s_ + (P_ + 8) * c_ + 8 * e_
-            kernel = {0: "k_d1_network<FULL>", 1: "k_d1_network_half"}[args.enum_mode]
-        # the other two phases of the step, same accounting (algorithmic bytes / CUDA-event time of the phase):
-        #   index (k_tile_partition x2 + k_tile_scan): both passes read row + length + abundance, pass 2 writes two 8-byte
-        #     entries, each pass one 4-byte counter update per piece;
-        #   cluster (k_cluster_persistent): key + parent initialised, the 8-byte link list re-read every round, the
-        #     parent pass (link + two keys), label + generation written.  Relaxation traffic (two keys per ACTIVE link) is not
-        #     counted — a lower bound.
-        rounds_ = int(st.get("cluster_rounds", 0))
-        idx_s, clu_s = sum(phase[1]) / len(phase[1]), sum(phase[3]) / len(phase[3])
-        phases_roof = None
-        if tile and not dist_mode:
-            idx_bytes = per_rank_rows(n, world) * (2 * (P_ + 12) + 16 + 16)
-            clu_bytes = n * (8 + 4 + 8 + 8) + rounds_ * 8 * cnt[4] + 24 * cnt[4]
-            phases_roof = {"index": {"bytes": idx_bytes, "achieved": idx_bytes / idx_s / 1e9, "frac": idx_bytes / idx_s / 1e9 / peak},
-                           "cluster": {"bytes": clu_bytes, "rounds": rounds_, "achieved": clu_bytes / clu_s / 1e9, "frac": clu_bytes / clu_s / 1e9 / peak,
-                                       "note": "bound by random 8-byte key accesses in L2 and a grid barrier per round, not by HBM"}}
-        b1_survey = 8400.0 if args.length == 150 else (P_ + 16 + 8 * (7 * args.length + 4))
-        per_rank = n / world                      # units one launch of the dominant kernel processes on one GPU
-        achieved = per_rank * b1_counted / net_s / 1e9
-        traffic = TRAFFIC.get("tile" if tile else mode) if (args.amplicons == 10_000_000 and world == 1 and args.length == 150) else None
-        line = {
-            "metric": METRIC, "value": n * args.steps / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"{n} x {args.length} bp synthetic amplicons, d=1" + (" --fastidious, BASELINE configs[2]" if args.fastidious else
-                                   (", BASELINE configs[1]" if world == 1 else f" — ONE job, {args.amplicons} amplicons per GPU (BASELINE configs[4] shape)")),
-                       "enum_mode": mode, "join_kernel": "tile" if tile else ("multimap" if args.enum_mode == 2 else None),
-                       "l2": "inputs larger than L2 (packed database %.0f MB per GPU + %.0f MB of join entries), no flush needed" % (n * (P_ + 12) / 1e6, 16 * n / world / 1e6),
-                       "timing": "CUDA events on the engine's stream around the K steps, barrier + synchronize on both sides, max over ranks",
-                       "wall_ms_per_step": 1e3 * wall / args.steps,
-                       "parallelism": ("single GPU" if world == 1 else
-                                       f"database replicated, join tiles sharded by hash range over {world} GPUs, " +
-                                       ("clustering sharded by amplicon range, links and label updates exchanged by the kernel over NVLink peer memory"
-                                        if dist_mode else "links all-gathered (NCCL over NVLink), clustering replicated"))},
-            "phases_ms": {"index": 1e3 * sum(phase[1]) / len(phase[1]), "network": 1e3 * net_s,
-                          "cluster": 1e3 * sum(phase[3]) / len(phase[3]),
-                          "fastidious": (1e3 * sum(phase[4]) / len(phase[4])) if args.fastidious else None},
-            "e2e": {"value": n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "ms_per_step": 1e3 * dt_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
-                    "two_jobs_in_flight": two_jobs,
-                    "api": ("swb200_load_db_compact" if world == 1 else "swb200_load_db_shard + all-gather") + " -> d1_index -> d1_network -> d1_cluster(host arrays)"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic,
-                         "traffic_source": "profiles/r1k_*_full_set_10M.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-                         "kernel": kernel, "bytes_per_amplicon_counted": b1_counted,
-                         "bytes_per_amplicon_survey_formula_full_enumeration": b1_survey,
-                         "phases": phases_roof,
-                         "achieved_if_counted_as_full_enumeration": per_rank * b1_survey / net_s / 1e9,
-                         "note": "the partitioned join is bound by instruction issue (ncu: 57 % issue slots, 16 % of DRAM bandwidth), not by HBM: it moves ~8x fewer bytes than the multimap join and ~80x fewer than the reference's enumeration" if tile else None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
-            "counters_per_amplicon": {"variants": V, "filter_pass": fp_, "slots_visited": s_, "exact_compares": c_, "links": e_,
-                                      "rows_gathered": rows_},
-            "swarms": cnt[6],
+            r = DnResult(db, res["swarm_of"], res["generation"], res["parent"], res_x)
+        got = helpers.output_hashes(r.swarms_text(), r.stats_text(), r.structure_text())
+        r.close()
+        if cand:
+            diff = helpers.compare_case(cand[0], got)
+            parity = {"ok": diff == [], "vs": f"tests/golden/scale_hashes.json[{cand[0]}]: SHA-256 of the reference's -o (raw + canonical, BASELINE.md §3.4), -s and -i files "
+                                              f"on the same FASTA ({hashes[cand[0]]['reference']}, -t {hashes[cand[0]]['reference_threads']})",
+                      "differs": diff, "swarms": got["swarms"], "o_canonical_sha256": got["o_canonical_sha256"],
+                      "from": "the host arrays of the last end-to-end step"}
+        else:
+            parity = {"ok": None, "vs": "no committed reference digest for this input size", "swarms": got["swarms"],
+                      "o_canonical_sha256": got["o_canonical_sha256"]}
+
+    # ---- roofline: algorithmic bytes per launch of every phase (DESIGN.md §3), time = CUDA events inside the timed region
+    cnt = {k: st[k] for k in st}
+    m_links = eng.n_links if d == 1 else st["dn_links"]
+    avg = {p: sum(v) / len(v) for p, v in phase.items()}
+    if d == 1:
+        e_ = m_links
+        ph = {
+            "index": {"kernel": "k_ts_scatter", "s": avg[1], "bytes": n * (P_ + 12) + 2 * n * (8 + P_),
+                      "formula": "per amplicon: packed row + length + abundance read, two fat records (8-byte entry + row) written"},
+            "network": {"kernel": "k_ts_join (+ k_ts_big, idle on this data)", "s": avg[2], "bytes": 2 * n * (8 + P_) + 8 * e_,
+                        "formula": "every tile record (entry + row) read once by TMA, links written"},
+            "cluster": {"kernel": "k_cluster_frontier", "s": avg[3], "bytes": n * 32 + e_ * 36, "rounds": st["cluster_rounds"],
+                        "formula": "per amplicon: key/degree/parent initialised, key read + label/generation written; per link: list read, "
+                                   "row slot written, key relaxed, parent pass (row + key read, parent written); frontier traffic of the later rounds not counted"},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
-        emit(line)
+        if args.join_kernel != 0 or args.enum_mode != 2 or args.cluster_kernel != 0:
+            for k in ph:
+                ph[k]["kernel"] += " (non-default kernel options: byte formula of the default kernels)"
+        if fast:
+            ph["fastidious"] = {"kernel": "k_fj_insert + k_fj_candidates + k_fj_verify", "s": avg[4],
+                                "bytes": 8 * st["fast_light_variants"] + 32 * st["fast_heavy_variants"] + (2 * P_ + 8) * st["fast_tag_matches"],
+                                "formula": "8 B per stored light piece + one 32-byte bucket per heavy lookup + two rows per candidate (counted)"}
+        step_bytes = sum(v["bytes"] for v in ph.values())
+    else:
+        ph = {"dn": {"kernel": "k_dn_qgrams + k_dn_candidates_join + k_dn_align + clustering", "s": avg[6],
+                     "bytes": 128 * st["dn_qgram_comparisons"] + 2 * P_ * st["dn_alignments"],
+                     "formula": "128 B x q-gram comparisons + (P_q + P_t) x alignments (SURVEY.md §8d), both counted"}}
+        step_bytes = ph["dn"]["bytes"]
+    roof = roofline_block(peak, bool(peaks), ph, args.config if n == CONFIGS[args.config][0] else None)
+    roof["step"] = {"bytes": step_bytes, "achieved": step_bytes / (dt / args.steps) / 1e9, "frac": step_bytes / (dt / args.steps) / 1e9 / peak}
+
+    wl = f"{n} x {L} bp synthetic amplicons, d={d}" + (" --fastidious" if fast else "") + f", {label}"
+    line = {
+        "metric": metric, "value": n * args.steps / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": wl, "seed": args.seed,
+                   "kernels": {"enum_mode": args.enum_mode, "join_kernel": args.join_kernel, "cluster_kernel": args.cluster_kernel},
+                   "l2": "inputs larger than L2 (packed database %.0f MB + %.0f MB tile store), no flush needed" % (n * (P_ + 12) / 1e6, 2 * n * (8 + P_) * 1.5 / 1e6),
+                   "timing": "CUDA events on the engine's stream around the K steps, synchronize on both sides",
+                   "wall_ms_per_step": 1e3 * wall / args.steps, "parallelism": "single GPU"},
+        "phases_ms": {k: v["ms"] for k, v in roof["phases"].items()},
+        "e2e": {"value": n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * dt_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
+                "api": "swb200_load_db_compact -> " + ("d1_index -> d1_network -> d1_cluster" + (" -> d1_fastidious" if fast else "") if d == 1 else "dn_cluster") + " (host arrays)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "parity": parity,
+        "counters": {"links": m_links, **{k: cnt[k] for k in ("variants", "exact_compares", "rows_gathered", "cluster_rounds", "tile_overflow", "skew_fallbacks")}},
+        "swarms": int((res["swarm_of"] == np.arange(n, dtype=np.uint32)).sum()),
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, cfg)
+    emit(line)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parametrised runner for the GPU box (under gpurun): scripts/gpu_run.sh TAG step [step ...]
-#   steps: box | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
+#   steps: box | fullp:<kernel regex>[:skip] (ncu --set full of one launch under scripts/probe.py) | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
 # Everything lands in gpurun_out/TAG_*.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
@@ -23,6 +23,10 @@ for step in "$@"; do
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_full_$k.out 2>&1
           python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -40 $O/${TAG}_$k.txt ;;
+    fullp) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
+          timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
+            python scripts/probe.py 10000000 default= > $O/${TAG}_fullp_$k.out 2>&1
+          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -45 $O/${TAG}_$k.txt ;;
     sanitize) bash scripts/gpu_sanitize.sh ;;
     *) echo "unknown step $step" ;;
   esac

@@ -11,7 +11,7 @@ import helpers  # noqa: E402
 from swarm_b200 import Engine, HostDb  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-variants = sys.argv[2:] or ["default=", "r1=join_kernel:2,cluster_kernel:5"]
+variants = sys.argv[2:] or ["default=", "fat=tile_rows:1", "r1=join_kernel:2", "frontier=cluster_kernel:4"]
 fa = f"/dev/shm/swb200_{n}x150_s42.fa"
 if not Path(fa).exists():
     helpers.make_fasta(fa, n, 150, 42)

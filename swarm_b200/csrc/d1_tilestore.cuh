@@ -49,7 +49,8 @@ struct TileStoreParams {
   uint32_t stride, K, id_bits;
   int sorted_desc, ncb;
   uint32_t n_tiles, t_lo, t_hi;     // global tile count; this context's tiles
-  uint32_t cap, rec_words;          // records per tile slot; words per record = 1 + stride
+  uint32_t cap, rec_words;          // records per tile slot; words per record: 1 + stride (FAT: entry + packed row) or 1 (slim: the
+                                    // join gathers the rows it needs from `words`, which must then hold every amplicon)
   unsigned long long *store;        // (t_hi - t_lo) * cap * rec_words
   uint32_t *cursor;                 // records appended per local tile (beyond cap: overflow list)
   unsigned long long *ovf;          // overflow records: `local tile | previous overflow record of the tile << 32`, then the record
@@ -102,7 +103,7 @@ __device__ __forceinline__ void ts_append(const TileStoreParams &J, uint32_t t, 
     for (uint32_t k = 1; k + 1 < J.rec_words; k += 2) d2[(k + 1) >> 1] = make_ulonglong2(row[k], row[k + 1]);
   } else {
     dst[0] = e;
-    for (uint32_t k = 0; k < J.stride; ++k) dst[1 + k] = row[k];
+    for (uint32_t k = 0; k + 1 < J.rec_words; ++k) dst[1 + k] = row[k];
   }
 }
 
@@ -221,30 +222,51 @@ __device__ __forceinline__ void ts_stage_links(const TileStoreParams &J, uint2 *
   }
 }
 
-// "Building network": one CTA per tile
-template <bool STATS>
+// asynchronous 8-byte global -> shared copy (SASS LDGSTS): the row gather of the slim join, no register staging
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// "Building network": one CTA per tile.
+//  (1) the tile's records arrive with ONE TMA bulk copy (FAT: entry + packed row each; slim: 8-byte entries);
+//  (2) counting sort of the record INDICES by the low 10 key bits (shared-memory atomics give the rank, one block scan the
+//      offsets): same-key records become neighbours, so the threads of a warp walk runs of similar length — r2a's
+//      hash-chain walk had one lane per warp busy for 40 steps while the average was 2.3 (ncu: 45 % of 0.9 G instructions);
+//  (3) thread s pairs its record with the later records of its bucket run; same-key, length-compatible pairs are queued,
+//      equal lengths from the bottom of the queue, lengths one apart from the top (qn = eq count | ne count << 16); a full
+//      queue suspends the walk until its pairs have been decided;
+//  (4) slim only: the packed rows of the records that are in a pair are gathered from the database, once, asynchronously
+//      (LDGSTS), 1.3 rows per amplicon;
+//  (5) the pairs are decided converged, one per thread: Hamming distance for equal lengths, the shifted comparison for
+//      lengths one apart (the lane-parallel check_variant, src/variants.cc:118-165).
+template <bool FAT, bool STATS>
 __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   extern __shared__ __align__(128) unsigned char ts_smem[];
+  const uint32_t rw = J.rec_words, stride = J.stride;
   unsigned long long *recs = reinterpret_cast<unsigned long long *>(ts_smem);          // cap * rec_words
-  uint32_t *head = reinterpret_cast<uint32_t *>(recs + static_cast<size_t>(J.cap) * J.rec_words);
-  uint32_t *queue = head + kTsBuckets;                                                  // kTsQueue pairs: i | j << 16
+  uint64_t *rows = reinterpret_cast<uint64_t *>(recs + static_cast<size_t>(J.cap) * rw);   // slim: cap * stride gathered rows
+  uint32_t *boff = reinterpret_cast<uint32_t *>(rows + (FAT ? 0 : static_cast<size_t>(J.cap) * stride));   // kTsBuckets + 2
+  uint32_t *queue = boff + kTsBuckets + 2;                                              // kTsQueue pairs: i | j << 16
   uint2 *out = reinterpret_cast<uint2 *>(queue + kTsQueue);                             // kTsOut links
-  uint16_t *nxt = reinterpret_cast<uint16_t *>(out + kTsOut);                           // cap chain links
+  uint16_t *order = reinterpret_cast<uint16_t *>(out + kTsOut);                         // cap: record indices, sorted by bucket
+  uint8_t *need = reinterpret_cast<uint8_t *>(order + J.cap);                           // slim: cap row states (0 unused, 1 wanted, 2 here)
   __shared__ uint64_t bar;
   __shared__ uint32_t qn, out_n;
   __shared__ unsigned long long out_base;
+  __shared__ uint32_t warp_tot[8];
 
   const uint32_t t = blockIdx.x, tid = threadIdx.x, lane = tid & 31u;
   const uint32_t c = min(J.cursor[t], J.cap);
   if (c < 2) return;
-  const uint32_t rw = J.rec_words, stride = J.stride;
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
     qn = 0;
     out_n = 0;
   }
-  for (uint32_t b = tid; b < kTsBuckets; b += 256) head[b] = kTsNil;
+  for (uint32_t b = tid; b < kTsBuckets + 2; b += 256) boff[b] = 0;
+  if (!FAT) for (uint32_t i = tid; i < c; i += 256) need[i] = 0;
   __syncthreads();
   if (tid == 0) {
     const uint32_t bytes = (c * rw * 8u + 15u) & ~15u;
@@ -254,80 +276,110 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   mbar_wait(&bar, 0);
 
   const uint32_t kshift = J.id_bits + 20;
-  // hash chains: nxt[i] = the entry that was at the head of i's bucket before i
-  for (uint32_t i = tid; i < c; i += 256) {
-    const uint32_t b = static_cast<uint32_t>(recs[static_cast<size_t>(i) * rw] >> kshift) & (kTsBuckets - 1);
-    nxt[i] = static_cast<uint16_t>(atomicExch(&head[b], i));
+  uint32_t rank[3], bk[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t i = tid + k * 256;
+    if (i < c) {
+      bk[k] = static_cast<uint32_t>(recs[static_cast<size_t>(i) * rw] >> kshift) & (kTsBuckets - 1);
+      rank[k] = atomicAdd(&boff[bk[k]], 1u);
+    }
+  }
+  __syncthreads();
+  tj_block_scan<4>(boff, kTsBuckets, warp_tot, tid);            // boff[b] = first sorted position of bucket b, boff[kTsBuckets] = c
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t i = tid + k * 256;
+    if (i < c) order[boff[bk[k]] + rank[k]] = static_cast<uint16_t>(i);
   }
   __syncthreads();
 
   const uint32_t K = J.K;
   const uint64_t kmask1 = K >= 64 ? ~0ull : (K > 32 ? (1ull << (2 * (K - 32))) - 1 : 0ull);
   const uint64_t kmask0 = K >= 32 ? ~0ull : (1ull << (2 * K)) - 1;
-  unsigned long long st_p = 0, st_s = 0, st_x = 0;
-  // resumable walk: entry i = tid, tid + 256, ...; j runs down i's chain.  Same-key, length-compatible pairs are queued —
-  // equal lengths from the bottom of the queue, lengths one apart from the top (qn = eq count | ne count << 16) — and a
-  // full queue suspends the walk until the pairs have been decided.
-  uint32_t i = tid, j = i < c ? nxt[i] : kTsNil;
-  unsigned long long ei = i < c ? recs[static_cast<size_t>(i) * rw] : 0ull;
+  unsigned long long st_p = 0, st_s = 0, st_x = 0, st_r = 0;
+  // resumable walk over the sorted positions s = tid, tid + 256, ...: q runs from s + 1 to the end of s's bucket run
+  uint32_t s = tid, q = 0, hi = 0, is = 0;
+  unsigned long long es = 0;
+  if (s < c) {
+    is = order[s];
+    es = recs[static_cast<size_t>(is) * rw];
+    hi = boff[(static_cast<uint32_t>(es >> kshift) & (kTsBuckets - 1)) + 1];
+    q = s + 1;
+  }
   for (;;) {
     bool more = false;
-    while (i < c) {
-      if (j == kTsNil) {
-        i += 256;
-        if (i < c) { j = nxt[i]; ei = recs[static_cast<size_t>(i) * rw]; }
+    while (s < c) {
+      if (q >= hi) {
+        s += 256;
+        if (s < c) {
+          is = order[s];
+          es = recs[static_cast<size_t>(is) * rw];
+          hi = boff[(static_cast<uint32_t>(es >> kshift) & (kTsBuckets - 1)) + 1];
+          q = s + 1;
+        }
         continue;
       }
-      const unsigned long long ej = recs[static_cast<size_t>(j) * rw];
+      const uint32_t iq = order[q];
+      const unsigned long long eq = recs[static_cast<size_t>(iq) * rw];
       if (STATS) st_s++;
-      if (ts_compatible(J, ei, ej)) {
-        const bool ne = ts_len(J, ei) != ts_len(J, ej);
+      if (ts_compatible(J, es, eq)) {
+        const bool ne = ts_len(J, es) != ts_len(J, eq);
         const uint32_t old = atomicAdd(&qn, ne ? 0x10000u : 1u);
         const uint32_t n_eq = old & 0xFFFFu, n_ne = old >> 16;
         if (n_eq + n_ne >= kTsQueue) { more = true; break; }       // full: this pair is retried in the next pass
-        queue[ne ? kTsQueue - 1 - n_ne : n_eq] = i | (j << 16);
+        queue[ne ? kTsQueue - 1 - n_ne : n_eq] = is | (iq << 16);
+        if (!FAT) { if (need[is] == 0) need[is] = 1; if (need[iq] == 0) need[iq] = 1; }
         if (STATS) st_p++;
       }
-      j = nxt[j];
+      ++q;
     }
     more = __syncthreads_or(more);
-    uint32_t n_eq = qn & 0xFFFFu, n_ne = qn >> 16;
-    if (n_eq + n_ne > kTsQueue) {                                   // the pushes that found the queue full did not write
-      // the writers are exactly the first kTsQueue arrivals; their split is not recorded, so count what was written:
-      // eq slots fill from 0 up, ne slots from the top down, kTsQueue in total -> every slot of the queue is valid and
-      // the boundary is wherever the eq run ends.  Recover it from the ne flag of the pairs themselves.
-      n_eq = kTsQueue; n_ne = 0;                                    // decide all kTsQueue slots with the general classifier
+    if (!FAT) {                                                     // gather the rows the queued pairs need and do not have yet
+      for (uint32_t i = tid; i < c; i += 256)
+        if (need[i] == 1) {
+          const uint64_t *w = J.words + static_cast<uint64_t>(ts_id(J, recs[static_cast<size_t>(i) * rw]) - J.row_first) * stride;
+          uint64_t *r = rows + static_cast<size_t>(i) * stride;
+          for (uint32_t x = 0; x < stride; ++x) cp_async_8(r + x, w + x);
+          need[i] = 2;
+          if (STATS) st_r++;
+        }
+      cp_async_wait_all();
+      __syncthreads();
     }
-    const bool mixed = (qn & 0xFFFFu) + (qn >> 16) > kTsQueue;
-    // equal lengths: Hamming distance
-    for (uint32_t p0 = 0; p0 < n_eq; p0 += 256) {
+    // the first kTsQueue pushes wrote their slots (equal lengths upwards from 0, unequal downwards from the top); when more
+    // arrived, every slot is valid but the boundary between the two kinds is not recorded: decide all with either classifier
+    const uint32_t raw_eq = qn & 0xFFFFu, raw_ne = qn >> 16;
+    const bool mixed = raw_eq + raw_ne > kTsQueue;
+    const uint32_t n_eq = mixed ? kTsQueue : raw_eq, n_ne = mixed ? 0u : raw_ne;
+    for (uint32_t p0 = 0; p0 < n_eq; p0 += 256) {                  // equal lengths: Hamming distance
       const uint32_t p = p0 + tid;
       uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
       uint32_t nl = 0;
       if (p < n_eq) {
         const uint32_t pr = queue[p], a = pr & 0xFFFFu, b = pr >> 16;
         const unsigned long long ea = recs[static_cast<size_t>(a) * rw], eb = recs[static_cast<size_t>(b) * rw];
+        const uint64_t *ra = FAT ? ts_u64(recs + static_cast<size_t>(a) * rw + 1) : rows + static_cast<size_t>(a) * stride;
+        const uint64_t *rb = FAT ? ts_u64(recs + static_cast<size_t>(b) * rw + 1) : rows + static_cast<size_t>(b) * stride;
         bool pfx_eq;
         int cls;
-        if (!mixed || ts_len(J, ea) == ts_len(J, eb))
-          cls = ts_classify_eq(ts_u64(recs + static_cast<size_t>(a) * rw + 1), ts_u64(recs + static_cast<size_t>(b) * rw + 1), stride, kmask0, kmask1, pfx_eq);
-        else
-          cls = tj_classify(ts_u64(recs + static_cast<size_t>(a) * rw + 1), ts_len(J, ea), ts_u64(recs + static_cast<size_t>(b) * rw + 1), ts_len(J, eb), stride, kmask0, kmask1, pfx_eq);
+        if (!mixed || ts_len(J, ea) == ts_len(J, eb)) cls = ts_classify_eq(ra, rb, stride, kmask0, kmask1, pfx_eq);
+        else cls = tj_classify(ra, ts_len(J, ea), rb, ts_len(J, eb), stride, kmask0, kmask1, pfx_eq);
         nl = ts_links<STATS>(J, ea, eb, cls, pfx_eq, st_x, l0, l1);
       }
       ts_stage_links(J, out, &out_n, nl, l0, l1, lane);
     }
-    // lengths one apart: shifted comparison
-    for (uint32_t p0 = 0; p0 < n_ne; p0 += 256) {
+    for (uint32_t p0 = 0; p0 < n_ne; p0 += 256) {                  // lengths one apart: shifted comparison
       const uint32_t p = p0 + tid;
       uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
       uint32_t nl = 0;
       if (p < n_ne) {
         const uint32_t pr = queue[kTsQueue - 1 - p], a = pr & 0xFFFFu, b = pr >> 16;
         const unsigned long long ea = recs[static_cast<size_t>(a) * rw], eb = recs[static_cast<size_t>(b) * rw];
+        const uint64_t *ra = FAT ? ts_u64(recs + static_cast<size_t>(a) * rw + 1) : rows + static_cast<size_t>(a) * stride;
+        const uint64_t *rb = FAT ? ts_u64(recs + static_cast<size_t>(b) * rw + 1) : rows + static_cast<size_t>(b) * stride;
         bool pfx_eq;
-        const int cls = tj_classify(ts_u64(recs + static_cast<size_t>(a) * rw + 1), ts_len(J, ea), ts_u64(recs + static_cast<size_t>(b) * rw + 1), ts_len(J, eb), stride,
-                                    kmask0, kmask1, pfx_eq);
+        const int cls = tj_classify(ra, ts_len(J, ea), rb, ts_len(J, eb), stride, kmask0, kmask1, pfx_eq);
         nl = ts_links<STATS>(J, ea, eb, cls, pfx_eq, st_x, l0, l1);
       }
       ts_stage_links(J, out, &out_n, nl, l0, l1, lane);
@@ -348,19 +400,21 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   if (STATS) {
     unsigned long long st_e = 0;
     for (uint32_t k = tid; k < c; k += 256) st_e++;
+    if (FAT) st_r = st_e;
 #pragma unroll
     for (int mm = 16; mm >= 1; mm >>= 1) {
       st_e += __shfl_xor_sync(kFull, st_e, mm);
       st_p += __shfl_xor_sync(kFull, st_p, mm);
       st_s += __shfl_xor_sync(kFull, st_s, mm);
       st_x += __shfl_xor_sync(kFull, st_x, mm);
+      st_r += __shfl_xor_sync(kFull, st_r, mm);
     }
     if (lane == 0) {
       atomicAdd(&J.stats[0], st_e);
       atomicAdd(&J.stats[1], st_p);
       atomicAdd(&J.stats[2], st_s);
       atomicAdd(&J.stats[3], st_x);
-      atomicAdd(&J.stats[4], st_e);
+      atomicAdd(&J.stats[4], st_r);
     }
   }
 }
@@ -368,7 +422,7 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
 // overflow records: against the records in their tile's slot (one warp per record, lanes over the slot), then against the
 // earlier overflow records of the same tile (one thread per record, down the tile's chain).  Rows are read from global
 // memory.  Exact; O(overflow x records of the tile).
-template <bool STATS>
+template <bool FAT, bool STATS>
 __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
   __shared__ PairStage stage[8];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -400,7 +454,9 @@ __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
         if (ts_compatible(J, ex, rec[0])) {
           if (STATS) st_p++;
           bool pfx_eq;
-          const int cls = tj_classify(ts_u64(ox + 2), ts_len(J, ex), ts_u64(rec + 1), ts_len(J, rec[0]), J.stride, kmask0, kmask1, pfx_eq);
+          const uint64_t *rx = FAT ? ts_u64(ox + 2) : J.words + static_cast<uint64_t>(ts_id(J, ex) - J.row_first) * J.stride;
+          const uint64_t *ry = FAT ? ts_u64(rec + 1) : J.words + static_cast<uint64_t>(ts_id(J, rec[0]) - J.row_first) * J.stride;
+          const int cls = tj_classify(rx, ts_len(J, ex), ry, ts_len(J, rec[0]), J.stride, kmask0, kmask1, pfx_eq);
           mine = ts_links<STATS>(J, ex, rec[0], cls, pfx_eq, st_x, l0, l1);
         }
       }
@@ -422,7 +478,9 @@ __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
         if (ts_compatible(J, ex, oy[1])) {
           if (STATS) st_p++;
           bool pfx_eq;
-          const int cls = tj_classify(ts_u64(ox + 2), ts_len(J, ex), ts_u64(oy + 2), ts_len(J, oy[1]), J.stride, kmask0, kmask1, pfx_eq);
+          const uint64_t *rx = FAT ? ts_u64(ox + 2) : J.words + static_cast<uint64_t>(ts_id(J, ex) - J.row_first) * J.stride;
+          const uint64_t *ry = FAT ? ts_u64(oy + 2) : J.words + static_cast<uint64_t>(ts_id(J, oy[1]) - J.row_first) * J.stride;
+          const int cls = tj_classify(rx, ts_len(J, ex), ry, ts_len(J, oy[1]), J.stride, kmask0, kmask1, pfx_eq);
           mine = ts_links<STATS>(J, ex, oy[1], cls, pfx_eq, st_x, l0, l1);
         }
         y = static_cast<uint32_t>(oy[0] >> 32);

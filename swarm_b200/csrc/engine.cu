@@ -161,6 +161,7 @@ struct swb200_ctx {
   bool tile_active = false;
   // tile store (d1_tilestore.cuh): fat records in fixed-capacity tile slots
   bool ts_active = false;
+  int ts_fat = 0;                    // 1: records carry their packed row (the sharded-database multi-GPU layout); 0: 8-byte entries, rows gathered
   DevBuf<unsigned long long> ts_store, ts_ovf;
   DevBuf<uint32_t> ts_cursor;        // [T] cursors, then [T] overflow chain heads
   uint32_t ts_cap = 0, ts_tiles = 0, ts_lo = 0, ts_hi = 0;
@@ -316,6 +317,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "net_kernel" && v >= 0 && v <= 2) c->net_kernel = static_cast<int>(v);
   else if (k == "join_kernel" && v >= 0 && v <= 2) c->join_kernel = static_cast<int>(v);
   else if (k == "skew_fallback" && (v == 0 || v == 1)) c->skew_fallback = static_cast<int>(v);
+  else if (k == "tile_rows" && (v == 0 || v == 1)) c->ts_fat = static_cast<int>(v);
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
@@ -530,7 +532,7 @@ static TileStoreParams ts_params(swb200_ctx *c) {
   while (idb < 32 && (1ull << idb) < c->n) ++idb;
   J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0; J.ncb = c->ncb;
   J.n_tiles = c->ts_tiles; J.t_lo = c->ts_lo; J.t_hi = c->ts_hi;
-  J.cap = c->ts_cap; J.rec_words = c->stride + 1;
+  J.cap = c->ts_cap; J.rec_words = c->ts_fat ? c->stride + 1 : 1;
   J.store = c->ts_store.p; J.cursor = c->ts_cursor.p; J.ovf_head = c->ts_cursor.p + (c->ts_hi - c->ts_lo);
   J.ovf = c->ts_ovf.p; J.ovf_count = c->counters.p + 32; J.ovf_cap = c->ts_ovf_cap;
   J.ovf_abort = reinterpret_cast<uint32_t *>(c->counters.p + 34);
@@ -547,7 +549,8 @@ static TileStoreParams ts_params(swb200_ctx *c) {
 
 // "Hashing sequences" for the tile store: geometry, buffers, ONE scatter pass.  No host synchronisation.
 static void index_tilestore(swb200_ctx *c) {
-  const uint32_t rec_bytes = 8 * (c->stride + 1);
+  const uint32_t rw = c->ts_fat ? c->stride + 1 : 1;
+  const uint32_t rec_bytes = 8 * (c->stride + 1);                // shared memory per record either way: entry + row
   uint32_t cap = std::min<uint32_t>(768, (36u * 1024u) / rec_bytes) & ~1u;
   cap = std::max<uint32_t>(cap, 64);
   const uint32_t fill = cap * 2 / 3;                       // mean records per tile: Poisson(512) never reaches 768
@@ -559,13 +562,13 @@ static void index_tilestore(swb200_ctx *c) {
   c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * c->shard_rank, c->ts_tiles));
   c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
   const uint32_t T = c->ts_hi - c->ts_lo;
-  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + kTsBuckets * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
-  c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * (c->stride + 1), 2) + 2);
+  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 3 + 15) & ~size_t(15));
+  c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * rw, 2) + 2);
   c->ts_cursor.alloc(static_cast<size_t>(T) * 2 + 2);
   if (c->ts_ovf_cap == 0 || c->tj_cmax_override >= 2)
     c->ts_ovf_cap = std::max<uint64_t>(c->ts_ovf_cap, c->tj_cmax_override >= 2 ? static_cast<uint64_t>(c->n) * 2 / c->shard_world + (1u << 16)
                                                                                 : static_cast<uint64_t>(c->n) / 8 / c->shard_world + (1u << 16));
-  c->ts_ovf.alloc(c->ts_ovf_cap * (c->stride + 2));
+  c->ts_ovf.alloc(c->ts_ovf_cap * (rw + 1));
   CK(cudaMemsetAsync(c->counters.p, 0, 17 * 8, c->stream));
   CK(cudaMemsetAsync(c->counters.p + 32, 0, 5 * 8, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p, 0, static_cast<size_t>(T) * 4, c->stream));
@@ -757,15 +760,13 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
       TileStoreParams J = ts_params(c);
       const uint32_t T = c->ts_hi - c->ts_lo;
       if (T) {
-        if (c->collect_stats) {
-          CK(cudaFuncSetAttribute(k_ts_join<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->ts_smem)));
-          k_ts_join<true><<<T, 256, c->ts_smem, c->stream>>>(J);
-          k_ts_big<true><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
-        } else {
-          CK(cudaFuncSetAttribute(k_ts_join<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->ts_smem)));
-          k_ts_join<false><<<T, 256, c->ts_smem, c->stream>>>(J);
-          k_ts_big<false><<<c->sm_count * 4, 256, 0, c->stream>>>(J);
-        }
+        auto launch = [&](auto join, auto big) {
+          CK(cudaFuncSetAttribute(join, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->ts_smem)));
+          join<<<T, 256, c->ts_smem, c->stream>>>(J);
+          big<<<c->sm_count * 4, 256, 0, c->stream>>>(J);
+        };
+        if (c->ts_fat) { if (c->collect_stats) launch(k_ts_join<true, true>, k_ts_big<true, true>); else launch(k_ts_join<true, false>, k_ts_big<true, false>); }
+        else { if (c->collect_stats) launch(k_ts_join<false, true>, k_ts_big<false, true>); else launch(k_ts_join<false, false>, k_ts_big<false, false>); }
         c->launches += 2;
         CK(cudaGetLastError());
       }
@@ -920,7 +921,7 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
-  if (c->cluster_kernel == 0 || c->cluster_kernel == 4) {
+  if (c->cluster_kernel == 4) {
     // frontier relaxation over 8-slot out-rows, one persistent cooperative kernel (d1_frontier.cuh)
     int occ = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_frontier, 256, 0));
@@ -989,7 +990,7 @@ static void run_cluster(swb200_ctx *c) {
     }
     return;
   }
-  if (c->cluster_kernel == 5 || c->cluster_kernel == 3) {
+  if (c->cluster_kernel == 0 || c->cluster_kernel == 5 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
     auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;

@@ -510,8 +510,10 @@ class Engine:
         self._ck(engine_lib().swb200_d1_fastidious(self._h, int(boundary), _ptr(gc, _u32p), C.byref(nl), C.byref(nh)))
         return gc, nl.value, nh.value
 
-    def dn_cluster(self, d, no_cluster_breaking=False, penalties=(18, 24, 13)):
-        outs = [np.empty(self.n, dtype=np.uint32) for _ in range(4)]
+    def dn_cluster(self, d, no_cluster_breaking=False, penalties=(18, 24, 13), want=True, out=None):
+        """out: optional dict of caller-owned uint32 arrays (swarm_of, generation, parent, pdiff); want=False: no download"""
+        keys = ("swarm_of", "generation", "parent", "pdiff")
+        outs = [((out[k] if out and k in out else np.empty(self.n, dtype=np.uint32)) if want else None) for k in keys]
         pen = (C.c_int64 * 3)(*penalties)
         self._ck(engine_lib().swb200_dn_cluster(self._h, int(d), int(bool(no_cluster_breaking)), pen,
                                                *[_ptr(a, _u32p) for a in outs]))

@@ -146,9 +146,11 @@ def seqs_of(db, i):
 
 
 @pytest.mark.gpu
-def test_long_sequences_are_dereplicated_but_not_clustered(built):
-    """the clustering kernels keep per-position tables on chip (<= 5 000 nt); d = 0 has no such limit"""
-    from swarm_b200 import Engine, EngineError
+def test_long_sequences(built):
+    """sequences beyond 5 000 nt (the reference accepts up to 67 108 861 nt, src/db.cc:439-442): dereplicated (d = 0) and
+    clustered at d = 1 by the JOIN path, whose global-memory multimap has no length limit; only the enumeration kernels
+    (per-position tables on chip) and the d > 1 aligner refuse them"""
+    from swarm_b200 import ENUM_HALF, ENUM_JOIN, Engine, EngineError
     rng = np.random.default_rng(3)
     a = "".join(rng.choice(list("ACGT"), 6000))
     b = a[:5999] + ("A" if a[5999] != "A" else "C")
@@ -159,10 +161,50 @@ def test_long_sequences_are_dereplicated_but_not_clustered(built):
     for got, exp in zip((rep, mass, size, singles), Oracle(db).derep()):
         assert np.array_equal(got, exp)
     assert k == 3 and rep.tolist() == [0, 1, 2, 0]          # order: x_3, y_2, w_1, z_1 (abundance, then header)
-    with pytest.raises(EngineError):
-        eng.d1_index()
+    eng.d1_index()
+    with pytest.raises(EngineError) as e:                   # x and z are identical: the reference's duplicate fatal
+        eng.d1_network()
+    assert e.value.status == 3
     with pytest.raises(EngineError):
         eng.dn_cluster(2)
+    eng.close()
+    # a swarm of 9 000-nt amplicons: centroid, one-edit variants (substitution / deletion / insertion anywhere), two-edit ones
+    cen = list(rng.choice(list("ACGT"), 9000))
+    recs, seen = [("c_100", "".join(cen))], {"".join(cen)}
+    for i in range(60):
+        s = list(cen)
+        for _ in range(1 + (i % 3 == 2)):
+            p, r = int(rng.integers(0, len(s))), rng.random()
+            if r < 0.6:
+                s[p] = "ACGT"[("ACGT".index(s[p]) + int(rng.integers(1, 4))) % 4]
+            elif r < 0.8:
+                del s[p]
+            else:
+                s.insert(p, "ACGT"[int(rng.integers(0, 4))])
+        s = "".join(s)
+        if s not in seen:
+            seen.add(s)
+            recs.append((f"v{i}_{1 + i % 7}", s))
+    db2 = HostDb(text="".join(f">{h}\n{s}\n" for h, s in recs).encode())
+    orc = Oracle(db2)
+    orc.network()
+    orc.cluster()
+    eng = Engine(0, enum_mode=ENUM_JOIN, collect_stats=1)
+    eng.load(db2)
+    eng.d1_index()
+    eng.d1_network()
+    links = eng.d1_export_links()
+    links = links[np.lexsort((links[:, 1], links[:, 0]))]
+    sw, gen, par = eng.d1_cluster()
+    eng.close()
+    assert np.array_equal(links, orc.links()) and len(links) > 30
+    assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent)
+    eng = Engine(0, enum_mode=ENUM_HALF)
+    eng.load(db2)
+    with pytest.raises(EngineError) as e:
+        eng.d1_index()
+    assert e.value.status == 5
+    eng.close()
 
 
 @pytest.mark.gpu

@@ -129,9 +129,10 @@ def test_lean_half_kernel_matches_first_kernel(built, name):
     assert s1["variants"] == s2["variants"] and s1["filter_pass"] == s2["filter_pass"]
 
 
-# JOIN flavours: tile store (default), the same with 8-record tile slots (most records take the overflow path of
-# k_ts_big), the global hash multimap of d1_join.cuh, and r1's count/scan/scatter tile join (normal and tiny tiles)
-JOIN_FLAVOURS = [{}, {"tile_cmax": 8}, {"join_kernel": 1}, {"join_kernel": 2}, {"join_kernel": 2, "tile_cmax": 8}]
+# JOIN flavours: tile store (default: 8-byte entries, rows gathered), the same with 8-record tile slots (most records take
+# the overflow path of k_ts_big), both again with fat records (entry + packed row, the sharded-database layout), the global hash multimap of d1_join.cuh, and r1's count/scan/scatter tile join (normal and tiny tiles)
+JOIN_FLAVOURS = [{}, {"tile_cmax": 8}, {"tile_rows": 1}, {"tile_rows": 1, "tile_cmax": 8}, {"join_kernel": 1}, {"join_kernel": 2},
+                 {"join_kernel": 2, "tile_cmax": 8}]
 
 
 @pytest.mark.parametrize("flavour", JOIN_FLAVOURS)
@@ -240,7 +241,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc.network()
     orc.cluster()
     for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1, "cluster_kernel": 2}), (ENUM_HALF, {"net_kernel": 2, "cluster_kernel": 3}), (ENUM_JOIN, {}),
-                      (ENUM_JOIN, {"cluster_kernel": 5})):
+                      (ENUM_JOIN, {"cluster_kernel": 4, "tile_rows": 1})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)
