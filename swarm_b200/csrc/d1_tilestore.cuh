@@ -32,7 +32,7 @@
 namespace swb {
 
 constexpr uint32_t kTsBuckets = 1024;     // hash-chain heads per tile
-constexpr uint32_t kTsQueue = 2048;       // pairs queued per pass of the join
+constexpr uint32_t kTsQueue = 1536;       // pairs queued per pass of the join
 constexpr uint32_t kTsOut = 512;          // links staged per tile before one global atomicAdd
 constexpr uint32_t kTsNil = 0xFFFFu;
 constexpr uint32_t kTsRows = 256;         // rows one CTA of the scatter pass stages
@@ -188,18 +188,20 @@ __device__ __forceinline__ uint32_t ts_links(const TileStoreParams &J, unsigned 
   return nl;
 }
 
-// equal lengths: 0 / 1 / 2+ differing positions; pfx_eq = the first K nucleotides agree
+// equal lengths: 0 / 1 / 2+ differing positions; pfx_eq = the first K nucleotides agree.  One substitution changes one
+// word: count the differing words (a select per word), popcount only the single survivor.
 __device__ __forceinline__ int ts_classify_eq(const uint64_t *x, const uint64_t *y, uint32_t stride, uint64_t kmask0, uint64_t kmask1, bool &pfx_eq) {
-  uint32_t ham = 0;
-  uint64_t d0 = 0, d1 = 0;
+  uint32_t nzw = 0;
+  uint64_t d0 = 0, d1 = 0, dw = 0;
   for (uint32_t k = 0; k < stride; ++k) {
     const uint64_t a = x[k] ^ y[k];
     if (k == 0) d0 = a;
     if (k == 1) d1 = a;
-    ham += __popcll((a | (a >> 1)) & 0x5555555555555555ull);
+    if (a != 0) { ++nzw; dw = a; }
   }
   pfx_eq = (d0 & kmask0) == 0 && (d1 & kmask1) == 0;
-  return ham > 1 ? 2 : static_cast<int>(ham);
+  if (nzw != 1) return nzw ? 2 : 0;
+  return __popcll((dw | (dw >> 1)) & 0x5555555555555555ull) == 1 ? 1 : 2;
 }
 
 // warp-collective: lanes contribute nl (0..2) links; staged in the tile's shared-memory buffer, spilled to the global list
@@ -231,15 +233,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // "Building network": one CTA per tile.
 //  (1) the tile's records arrive with ONE TMA bulk copy (FAT: entry + packed row each; slim: 8-byte entries);
 //  (2) counting sort of the record INDICES by the low 10 key bits (shared-memory atomics give the rank, one block scan the
-//      offsets): same-key records become neighbours, so the threads of a warp walk runs of similar length — r2a's
-//      hash-chain walk had one lane per warp busy for 40 steps while the average was 2.3 (ncu: 45 % of 0.9 G instructions);
-//  (3) thread s pairs its record with the later records of its bucket run; same-key, length-compatible pairs are queued,
-//      equal lengths from the bottom of the queue, lengths one apart from the top (qn = eq count | ne count << 16); a full
-//      queue suspends the walk until its pairs have been decided;
-//  (4) slim only: the packed rows of the records that are in a pair are gathered from the database, once, asynchronously
-//      (LDGSTS), 1.3 rows per amplicon;
-//  (5) the pairs are decided converged, one per thread: Hamming distance for equal lengths, the shifted comparison for
-//      lengths one apart (the lane-parallel check_variant, src/variants.cc:118-165).
+//      offsets): same-key records become neighbours; a 32-bit descriptor `key19 | len13` per sorted position is all the
+//      pairing needs;
+//  (3) slim only: the packed rows of the records whose bucket run holds at least two records are requested from the
+//      database now, asynchronously (LDGSTS), and arrive while the pairs are being enumerated;
+//  (4) pairs: sorted position s is paired with the later positions of its bucket run.  The runs are short on average (2.3)
+//      and long for dense groups (40+), so the enumeration is load-balanced inside each warp: the 32 run lengths of a
+//      block of positions are prefix-summed with shuffles and lane l takes pair p0 + l, locating its source position by a
+//      5-step shuffle search (r2a walked a chain per lane: one lane busy for 40 steps, ncu: 45 % of 0.9 G instructions).
+//      Same-key, length-compatible pairs are queued — equal lengths from the bottom, lengths one apart from the top — with
+//      one shared-memory atomic per warp; a full queue suspends the enumeration until its pairs have been decided;
+//  (5) the pairs are decided converged, one per thread: differing-word count then one popcount for equal lengths, the
+//      shifted comparison for lengths one apart (the lane-parallel check_variant, src/variants.cc:118-165).
 template <bool FAT, bool STATS>
 __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   extern __shared__ __align__(128) unsigned char ts_smem[];
@@ -247,26 +252,26 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   unsigned long long *recs = reinterpret_cast<unsigned long long *>(ts_smem);          // cap * rec_words
   uint64_t *rows = reinterpret_cast<uint64_t *>(recs + static_cast<size_t>(J.cap) * rw);   // slim: cap * stride gathered rows
   uint32_t *boff = reinterpret_cast<uint32_t *>(rows + (FAT ? 0 : static_cast<size_t>(J.cap) * stride));   // kTsBuckets + 2
-  uint32_t *queue = boff + kTsBuckets + 2;                                              // kTsQueue pairs: i | j << 16
+  uint32_t *sdesc = boff + kTsBuckets + 2;                                              // cap descriptors, by sorted position
+  uint32_t *queue = sdesc + J.cap;                                                      // kTsQueue pairs: s | q << 16 (sorted positions)
   uint2 *out = reinterpret_cast<uint2 *>(queue + kTsQueue);                             // kTsOut links
-  uint16_t *order = reinterpret_cast<uint16_t *>(out + kTsOut);                         // cap: record indices, sorted by bucket
-  uint8_t *need = reinterpret_cast<uint8_t *>(order + J.cap);                           // slim: cap row states (0 unused, 1 wanted, 2 here)
+  uint16_t *order = reinterpret_cast<uint16_t *>(out + kTsOut);                         // cap: record index of every sorted position
   __shared__ uint64_t bar;
-  __shared__ uint32_t qn, out_n;
+  __shared__ uint32_t qn, qok, out_n;
   __shared__ unsigned long long out_base;
   __shared__ uint32_t warp_tot[8];
 
-  const uint32_t t = blockIdx.x, tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t t = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t c = min(J.cursor[t], J.cap);
   if (c < 2) return;
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
     qn = 0;
+    qok = 0;
     out_n = 0;
   }
   for (uint32_t b = tid; b < kTsBuckets + 2; b += 256) boff[b] = 0;
-  if (!FAT) for (uint32_t i = tid; i < c; i += 256) need[i] = 0;
   __syncthreads();
   if (tid == 0) {
     const uint32_t bytes = (c * rw * 8u + 15u) & ~15u;
@@ -276,13 +281,14 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   mbar_wait(&bar, 0);
 
   const uint32_t kshift = J.id_bits + 20;
-  uint32_t rank[3], bk[3];
+  uint32_t rank[3], desc[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint32_t i = tid + k * 256;
     if (i < c) {
-      bk[k] = static_cast<uint32_t>(recs[static_cast<size_t>(i) * rw] >> kshift) & (kTsBuckets - 1);
-      rank[k] = atomicAdd(&boff[bk[k]], 1u);
+      const unsigned long long e = recs[static_cast<size_t>(i) * rw];
+      desc[k] = (static_cast<uint32_t>(e >> kshift) << 13) | ts_len(J, e);             // key bits 0..18 | length
+      rank[k] = atomicAdd(&boff[(desc[k] >> 13) & (kTsBuckets - 1)], 1u);
     }
   }
   __syncthreads();
@@ -290,91 +296,106 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const uint32_t i = tid + k * 256;
-    if (i < c) order[boff[bk[k]] + rank[k]] = static_cast<uint16_t>(i);
+    if (i < c) {
+      const uint32_t pos = boff[(desc[k] >> 13) & (kTsBuckets - 1)] + rank[k];
+      order[pos] = static_cast<uint16_t>(i);
+      sdesc[pos] = desc[k];
+    }
   }
   __syncthreads();
+  unsigned long long st_p = 0, st_s = 0, st_x = 0, st_r = 0;
+  if (!FAT) {                                                     // rows of the records that have a bucket mate: on their way
+    for (uint32_t sp = tid; sp < c; sp += 256) {
+      const uint32_t b = (sdesc[sp] >> 13) & (kTsBuckets - 1);
+      if (boff[b + 1] - boff[b] >= 2u) {
+        const uint32_t i = order[sp];
+        const uint64_t *w = J.words + static_cast<uint64_t>(ts_id(J, recs[static_cast<size_t>(i) * rw]) - J.row_first) * stride;
+        uint64_t *r = rows + static_cast<size_t>(i) * stride;
+        for (uint32_t x = 0; x < stride; ++x) cp_async_8(r + x, w + x);
+        if (STATS) st_r++;
+      }
+    }
+  }
 
   const uint32_t K = J.K;
   const uint64_t kmask1 = K >= 64 ? ~0ull : (K > 32 ? (1ull << (2 * (K - 32))) - 1 : 0ull);
   const uint64_t kmask0 = K >= 32 ? ~0ull : (1ull << (2 * K)) - 1;
-  unsigned long long st_p = 0, st_s = 0, st_x = 0, st_r = 0;
-  // resumable walk over the sorted positions s = tid, tid + 256, ...: q runs from s + 1 to the end of s's bucket run
-  uint32_t s = tid, q = 0, hi = 0, is = 0;
-  unsigned long long es = 0;
-  if (s < c) {
-    is = order[s];
-    es = recs[static_cast<size_t>(is) * rw];
-    hi = boff[(static_cast<uint32_t>(es >> kshift) & (kTsBuckets - 1)) + 1];
-    q = s + 1;
-  }
-  for (;;) {
-    bool more = false;
-    while (s < c) {
-      if (q >= hi) {
-        s += 256;
-        if (s < c) {
-          is = order[s];
-          es = recs[static_cast<size_t>(is) * rw];
-          hi = boff[(static_cast<uint32_t>(es >> kshift) & (kTsBuckets - 1)) + 1];
-          q = s + 1;
+  const uint32_t nblk = (c + 31u) >> 5, lt = (1u << lane) - 1u;
+  uint32_t blk = warp, p0 = 0;                                    // resumable: block of 32 sorted positions, first pair of the step
+  for (bool first = true;; first = false) {
+    bool fail = false;
+    while (blk < nblk && !fail) {
+      const uint32_t sp = (blk << 5) + lane;
+      const uint32_t ds = sp < c ? sdesc[sp] : 0u;
+      const uint32_t cnt = sp < c ? boff[((ds >> 13) & (kTsBuckets - 1)) + 1] - sp - 1u : 0u;
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += v;
+      }
+      const uint32_t T = __shfl_sync(kFull, incl, 31);
+      for (; p0 < T; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        uint32_t lo = 0;                                          // lanes whose pairs all come before p
+#pragma unroll
+        for (uint32_t step = 16; step >= 1; step >>= 1) {
+          const uint32_t v = __shfl_sync(kFull, incl, (lo + step - 1) & 31u);
+          if (v <= p) lo += step;
         }
-        continue;
+        const uint32_t src = lo & 31u;
+        const uint32_t d_src = __shfl_sync(kFull, ds, src), excl_src = __shfl_sync(kFull, incl - cnt, src);
+        const uint32_t ss = (blk << 5) + src, q = ss + 1u + (p - excl_src);
+        bool ok = p < T;
+        const uint32_t dq = ok ? sdesc[q] : 0u;
+        const uint32_t ls = d_src & 0x1FFFu, lq = dq & 0x1FFFu;
+        if (STATS && ok) st_s++;
+        ok = ok && ((d_src ^ dq) >> 13) == 0 && ls + 1u >= lq && lq + 1u >= ls;
+        const bool ne = ls != lq;
+        const uint32_t m_eq = __ballot_sync(kFull, ok && !ne), m_ne = __ballot_sync(kFull, ok && ne);
+        if (m_eq | m_ne) {
+          const uint32_t k_eq = __popc(m_eq), k_ne = __popc(m_ne);
+          uint32_t old = 0;
+          if (lane == 0) old = atomicAdd(&qn, k_eq | (k_ne << 16));
+          old = __shfl_sync(kFull, old, 0);
+          const uint32_t o_eq = old & 0xFFFFu, o_ne = old >> 16;
+          if (o_eq + o_ne + k_eq + k_ne > kTsQueue) { fail = true; break; }       // full: this step is retried in the next pass
+          if (lane == 0) atomicAdd(&qok, k_eq | (k_ne << 16));
+          if (ok && !ne) queue[o_eq + __popc(m_eq & lt)] = ss | (q << 16);
+          if (ok && ne) queue[kTsQueue - 1u - o_ne - __popc(m_ne & lt)] = ss | (q << 16);
+          if (STATS && ok) st_p++;
+        }
       }
-      const uint32_t iq = order[q];
-      const unsigned long long eq = recs[static_cast<size_t>(iq) * rw];
-      if (STATS) st_s++;
-      if (ts_compatible(J, es, eq)) {
-        const bool ne = ts_len(J, es) != ts_len(J, eq);
-        const uint32_t old = atomicAdd(&qn, ne ? 0x10000u : 1u);
-        const uint32_t n_eq = old & 0xFFFFu, n_ne = old >> 16;
-        if (n_eq + n_ne >= kTsQueue) { more = true; break; }       // full: this pair is retried in the next pass
-        queue[ne ? kTsQueue - 1 - n_ne : n_eq] = is | (iq << 16);
-        if (!FAT) { if (need[is] == 0) need[is] = 1; if (need[iq] == 0) need[iq] = 1; }
-        if (STATS) st_p++;
-      }
-      ++q;
+      if (!fail) { blk += 8; p0 = 0; }
     }
-    more = __syncthreads_or(more);
-    if (!FAT) {                                                     // gather the rows the queued pairs need and do not have yet
-      for (uint32_t i = tid; i < c; i += 256)
-        if (need[i] == 1) {
-          const uint64_t *w = J.words + static_cast<uint64_t>(ts_id(J, recs[static_cast<size_t>(i) * rw]) - J.row_first) * stride;
-          uint64_t *r = rows + static_cast<size_t>(i) * stride;
-          for (uint32_t x = 0; x < stride; ++x) cp_async_8(r + x, w + x);
-          need[i] = 2;
-          if (STATS) st_r++;
-        }
+    const bool more = __syncthreads_or(fail);
+    if (!FAT && first) {
       cp_async_wait_all();
       __syncthreads();
     }
-    // the first kTsQueue pushes wrote their slots (equal lengths upwards from 0, unequal downwards from the top); when more
-    // arrived, every slot is valid but the boundary between the two kinds is not recorded: decide all with either classifier
-    const uint32_t raw_eq = qn & 0xFFFFu, raw_ne = qn >> 16;
-    const bool mixed = raw_eq + raw_ne > kTsQueue;
-    const uint32_t n_eq = mixed ? kTsQueue : raw_eq, n_ne = mixed ? 0u : raw_ne;
-    for (uint32_t p0 = 0; p0 < n_eq; p0 += 256) {                  // equal lengths: Hamming distance
-      const uint32_t p = p0 + tid;
+    // every push before the first failure wrote its slots: equal lengths [0, n_eq), lengths one apart (top - n_ne, top]
+    const uint32_t n_eq = qok & 0xFFFFu, n_ne = qok >> 16;
+    for (uint32_t q0 = 0; q0 < n_eq; q0 += 256) {
+      const uint32_t p = q0 + tid;
       uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
       uint32_t nl = 0;
       if (p < n_eq) {
-        const uint32_t pr = queue[p], a = pr & 0xFFFFu, b = pr >> 16;
+        const uint32_t pr = queue[p], a = order[pr & 0xFFFFu], b = order[pr >> 16];
         const unsigned long long ea = recs[static_cast<size_t>(a) * rw], eb = recs[static_cast<size_t>(b) * rw];
         const uint64_t *ra = FAT ? ts_u64(recs + static_cast<size_t>(a) * rw + 1) : rows + static_cast<size_t>(a) * stride;
         const uint64_t *rb = FAT ? ts_u64(recs + static_cast<size_t>(b) * rw + 1) : rows + static_cast<size_t>(b) * stride;
         bool pfx_eq;
-        int cls;
-        if (!mixed || ts_len(J, ea) == ts_len(J, eb)) cls = ts_classify_eq(ra, rb, stride, kmask0, kmask1, pfx_eq);
-        else cls = tj_classify(ra, ts_len(J, ea), rb, ts_len(J, eb), stride, kmask0, kmask1, pfx_eq);
+        const int cls = ts_classify_eq(ra, rb, stride, kmask0, kmask1, pfx_eq);
         nl = ts_links<STATS>(J, ea, eb, cls, pfx_eq, st_x, l0, l1);
       }
       ts_stage_links(J, out, &out_n, nl, l0, l1, lane);
     }
-    for (uint32_t p0 = 0; p0 < n_ne; p0 += 256) {                  // lengths one apart: shifted comparison
-      const uint32_t p = p0 + tid;
+    for (uint32_t q0 = 0; q0 < n_ne; q0 += 256) {
+      const uint32_t p = q0 + tid;
       uint2 l0 = make_uint2(0, 0), l1 = make_uint2(0, 0);
       uint32_t nl = 0;
       if (p < n_ne) {
-        const uint32_t pr = queue[kTsQueue - 1 - p], a = pr & 0xFFFFu, b = pr >> 16;
+        const uint32_t pr = queue[kTsQueue - 1u - p], a = order[pr & 0xFFFFu], b = order[pr >> 16];
         const unsigned long long ea = recs[static_cast<size_t>(a) * rw], eb = recs[static_cast<size_t>(b) * rw];
         const uint64_t *ra = FAT ? ts_u64(recs + static_cast<size_t>(a) * rw + 1) : rows + static_cast<size_t>(a) * stride;
         const uint64_t *rb = FAT ? ts_u64(recs + static_cast<size_t>(b) * rw + 1) : rows + static_cast<size_t>(b) * stride;
@@ -386,7 +407,7 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
     }
     __syncthreads();
     if (!more) break;
-    if (tid == 0) qn = 0;
+    if (tid == 0) { qn = 0; qok = 0; }
     __syncthreads();
   }
   const uint32_t m = min(out_n, kTsOut);

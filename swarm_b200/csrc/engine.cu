@@ -562,7 +562,7 @@ static void index_tilestore(swb200_ctx *c) {
   c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * c->shard_rank, c->ts_tiles));
   c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
   const uint32_t T = c->ts_hi - c->ts_lo;
-  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 3 + 15) & ~size_t(15));
+  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + static_cast<size_t>(cap) * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
   c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * rw, 2) + 2);
   c->ts_cursor.alloc(static_cast<size_t>(T) * 2 + 2);
   if (c->ts_ovf_cap == 0 || c->tj_cmax_override >= 2)
