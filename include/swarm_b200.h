@@ -59,6 +59,10 @@ const char *swb200_last_error(void);
  * entry + packed row into fixed-capacity tile slots, a tile is joined from shared memory after one TMA bulk copy;
  * 1 = global hash multimap, d1_join.cuh, no length limit; 2 = r1's count / scan / scatter tile join, d1_tilejoin.cuh —
  * same links), "tile_cmax" (test hook: cap on the records a tile slot holds; the rest takes the overflow path),
+ * "tile_rows" (0 default: a tile record is the 8-byte entry and the join gathers the packed rows it needs from the
+ * database; 1: a record carries its packed row — the layout of the sharded multi-GPU job), "tile_cap" (tuning: records per
+ * tile slot), "index_exchange" (1 default: after swb200_dist_setup every rank hashes only its own rows and routes the
+ * records to the tile owners over the peer buffers; 0: every rank scans the whole replicated database),
  * "skew_fallback" (1 default: when the overflow path would cost more than ~32 pair tests per amplicon — dense data,
  * huge groups sharing one K-mer — swb200_d1_network switches to the linear HALF enumeration, like the reference's
  * cost model; 0 = always sweep),
@@ -94,6 +98,17 @@ int  swb200_load_db_compact(swb200_ctx *ctx, const uint64_t *words, uint32_t str
  * that is already in device memory (device pointers, copied). */
 int  swb200_load_db_shard(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
                           const uint64_t *abundance, uint32_t n_total, uint32_t first, uint32_t count);
+/* SHARDED database (BASELINE configs[4], SURVEY.md §8e "hash-sharded"): this context keeps only the rows [first, first+count)
+ * of the job's sorted database — no rank holds all packed sequences.  run_start (n_runs + 1 entries, as in
+ * swb200_load_db_compact) describes the abundance runs of the WHOLE database: it is how a rank decides whether two amplicon ids
+ * have equal abundances (src/algod1.cc:580-583) without the other ranks' rows.  Requires swb200_dist_setup, option
+ * "tile_rows" = 1 (records carry their packed row to the rank that owns their tile) and, when the ranks' shards differ in
+ * their shortest / longest sequence, the options "job_min_len" / "job_max_len" (set before this call; every rank must derive
+ * the same piece length).  Then swb200_d1_index (the index exchange runs inside it, over the peer buffers),
+ * swb200_d1_network and swb200_d1_cluster_dist; the single-GPU entry points answer SWB200_EUNSUPPORTED. */
+int  swb200_load_db_rows(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
+                         const uint64_t *abundance, uint32_t n_total, uint32_t first, uint32_t count,
+                         const uint32_t *run_start, uint32_t n_runs);
 int  swb200_db_device(swb200_ctx *ctx, void **d_words, void **d_len, void **d_abundance);
 int  swb200_db_commit(swb200_ctx *ctx);
 int  swb200_load_db_device(swb200_ctx *ctx, const void *d_words, uint32_t stride_words, const void *d_len,

@@ -47,6 +47,7 @@ struct TileStoreParams {
   uint32_t n;                       // amplicons of the whole job
   uint32_t row_first, row_count;
   uint32_t stride, K, id_bits;
+  uint64_t kmask0, kmask1;          // the first K nucleotides of a packed row: masks of words 0 and 1
   int sorted_desc, ncb;
   uint32_t n_tiles, t_lo, t_hi;     // global tile count; this context's tiles
   uint32_t cap, rec_words;          // records per tile slot; words per record: 1 + stride (FAT: entry + packed row) or 1 (slim: the
@@ -188,6 +189,16 @@ __device__ __forceinline__ uint32_t ts_links(const TileStoreParams &J, unsigned 
   return nl;
 }
 
+// shared-memory atomic add issued by ONE lane the caller has already elected: plain `atomicAdd` makes the compiler wrap the
+// instruction in its own warp aggregation (vote / find-leader / popc / shuffle, ~20 instructions) every time
+__device__ __forceinline__ uint32_t atoms_add(uint32_t *p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t *p, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 // equal lengths: 0 / 1 / 2+ differing positions; pfx_eq = the first K nucleotides agree.  One substitution changes one
 // word: count the differing words (a select per word), popcount only the single survivor.
 __device__ __forceinline__ int ts_classify_eq(const uint64_t *x, const uint64_t *y, uint32_t stride, uint64_t kmask0, uint64_t kmask1, bool &pfx_eq) {
@@ -210,7 +221,7 @@ __device__ __forceinline__ void ts_stage_links(const TileStoreParams &J, uint2 *
   const uint32_t tot = __popc(b1) + __popc(b2);
   if (tot == 0) return;
   uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(out_n, tot);
+  if (lane == 0) base = atoms_add(out_n, tot);
   base = __shfl_sync(kFull, base, 0);
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t i0 = base + __popc(b1 & lt), i1 = base + __popc(b1) + __popc(b2 & lt);
@@ -317,9 +328,7 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
     }
   }
 
-  const uint32_t K = J.K;
-  const uint64_t kmask1 = K >= 64 ? ~0ull : (K > 32 ? (1ull << (2 * (K - 32))) - 1 : 0ull);
-  const uint64_t kmask0 = K >= 32 ? ~0ull : (1ull << (2 * K)) - 1;
+  const uint64_t kmask0 = J.kmask0, kmask1 = J.kmask1;
   const uint32_t nblk = (c + 31u) >> 5, lt = (1u << lane) - 1u;
   uint32_t blk = warp, p0 = 0;                                    // resumable: block of 32 sorted positions, first pair of the step
   for (bool first = true;; first = false) {
@@ -356,11 +365,11 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
         if (m_eq | m_ne) {
           const uint32_t k_eq = __popc(m_eq), k_ne = __popc(m_ne);
           uint32_t old = 0;
-          if (lane == 0) old = atomicAdd(&qn, k_eq | (k_ne << 16));
+          if (lane == 0) old = atoms_add(&qn, k_eq | (k_ne << 16));
           old = __shfl_sync(kFull, old, 0);
           const uint32_t o_eq = old & 0xFFFFu, o_ne = old >> 16;
           if (o_eq + o_ne + k_eq + k_ne > kTsQueue) { fail = true; break; }       // full: this step is retried in the next pass
-          if (lane == 0) atomicAdd(&qok, k_eq | (k_ne << 16));
+          if (lane == 0) reds_add(&qok, k_eq | (k_ne << 16));
           if (ok && !ne) queue[o_eq + __popc(m_eq & lt)] = ss | (q << 16);
           if (ok && ne) queue[kTsQueue - 1u - o_ne - __popc(m_ne & lt)] = ss | (q << 16);
           if (STATS && ok) st_p++;
@@ -455,9 +464,8 @@ __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *J.ovf_abort = 1u;
     return;
   }
-  const uint32_t K = J.K, rw = J.rec_words;
-  const uint64_t kmask1 = K >= 64 ? ~0ull : (K > 32 ? (1ull << (2 * (K - 32))) - 1 : 0ull);
-  const uint64_t kmask0 = K >= 32 ? ~0ull : (1ull << (2 * K)) - 1;
+  const uint32_t rw = J.rec_words;
+  const uint64_t kmask0 = J.kmask0, kmask1 = J.kmask1;
   unsigned long long st_s = 0, st_p = 0, st_x = 0;
   const uint64_t nwarps = static_cast<uint64_t>(gridDim.x) * 8;
   for (uint64_t x = static_cast<uint64_t>(blockIdx.x) * 8 + warp; x < n_ovf; x += nwarps) {

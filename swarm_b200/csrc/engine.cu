@@ -10,6 +10,7 @@
 #include "d1_tilejoin.cuh"
 #include "d1_tilestore.cuh"
 #include "d1_frontier.cuh"
+#include "d1_tsroute.cuh"
 #include "d1_cluster.cuh"
 #include "d1_dist.cuh"
 #include "dn_kernels.cuh"
@@ -161,6 +162,7 @@ struct swb200_ctx {
   bool tile_active = false;
   // tile store (d1_tilestore.cuh): fat records in fixed-capacity tile slots
   bool ts_active = false;
+  uint32_t ts_cap_opt = 0;           // tuning: records per tile slot (0 = derived from the record size)
   int ts_fat = 0;                    // 1: records carry their packed row (the sharded-database multi-GPU layout); 0: 8-byte entries, rows gathered
   DevBuf<unsigned long long> ts_store, ts_ovf;
   DevBuf<uint32_t> ts_cursor;        // [T] cursors, then [T] overflow chain heads
@@ -168,6 +170,17 @@ struct swb200_ctx {
   uint64_t ts_ovf_cap = 0;
   size_t ts_smem = 0;
   unsigned long long ts_overflow = 0, ts_fallbacks = 0;
+  // multi-GPU index exchange (d1_tsroute.cuh) and sharded database
+  bool db_sharded = false;           // this context holds only the rows [row_first, row_first + row_count) of the job's database
+  uint32_t row_first = 0, row_count = 0;
+  DevBuf<uint32_t> run_start_d;      // abundance runs of the WHOLE database (equal-abundance test without the abundance array)
+  uint32_t n_runs = 0;
+  uint32_t job_min_len = 0, job_max_len = 0;   // length range of the whole job (every rank must use the same piece length K)
+  int dist_grid_div = 1;             // test hook: several ranks share ONE GPU, each persistent kernel takes 1/div of the SMs
+  int index_exchange = 1;            // after swb200_dist_setup: hash only this rank's rows, route the records to the tile owners
+  unsigned long long idx_epoch = 0;
+  DevBuf<unsigned long long> ts_route_cnt;     // [16] sender counters, then done_ctas[2] + err[2] as 32-bit words
+  uint64_t dist_buffer_bytes = 0;
   int skew_fallback = 1;             // dense data: abandon the quadratic overflow sweep for the linear enumeration (single GPU)
   // frontier clustering (d1_frontier.cuh)
   DevBuf<uint32_t> fr_deg, fr_adj;
@@ -297,6 +310,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
+  c->run_start_d.release(); c->ts_route_cnt.release();
   c->ts_store.release(); c->ts_ovf.release(); c->ts_cursor.release(); c->fr_deg.release(); c->fr_adj.release(); c->fr_spill.release();
   c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
@@ -318,6 +332,11 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "join_kernel" && v >= 0 && v <= 2) c->join_kernel = static_cast<int>(v);
   else if (k == "skew_fallback" && (v == 0 || v == 1)) c->skew_fallback = static_cast<int>(v);
   else if (k == "tile_rows" && (v == 0 || v == 1)) c->ts_fat = static_cast<int>(v);
+  else if (k == "index_exchange" && (v == 0 || v == 1)) c->index_exchange = static_cast<int>(v);
+  else if (k == "dist_grid_div" && v >= 1 && v <= 16) c->dist_grid_div = static_cast<int>(v);
+  else if (k == "job_min_len" && v >= 0 && v < (1ll << 32)) c->job_min_len = static_cast<uint32_t>(v);
+  else if (k == "job_max_len" && v >= 0 && v < (1ll << 32)) c->job_max_len = static_cast<uint32_t>(v);
+  else if (k == "tile_cap" && v >= 0 && v <= 768) c->ts_cap_opt = static_cast<uint32_t>(v);
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
@@ -332,6 +351,9 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
 // device buffers for a database of n amplicons with `stride_words` words per row
 static void db_alloc(swb200_ctx *c, uint32_t n, uint32_t stride_words) {
   c->indexed = c->have_network = c->clustered = false;
+  c->db_sharded = false;
+  c->row_first = 0;
+  c->row_count = n;
   // seeds per TMA batch: even, <= kMaxBatch, batch*stride*8 bytes <= 2 KB per buffer
   uint32_t batch = 256 / stride_words;
   batch = std::max<uint32_t>(2, std::min<uint32_t>(kMaxBatch, batch & ~1u));
@@ -349,8 +371,8 @@ static void db_alloc(swb200_ctx *c, uint32_t n, uint32_t stride_words) {
 
 // after the rows are on the device: padding, length range, order check, Zobrist table
 static int db_finalize(swb200_ctx *c) {
-  const uint32_t n = c->n, stride_words = c->stride;
-  if (c->n_padded > n)
+  const uint32_t n = c->db_sharded ? c->row_count : c->n, stride_words = c->stride;      // rows present in this context
+  if (!c->db_sharded && c->n_padded > n)
     CK(cudaMemsetAsync(c->words.p + static_cast<size_t>(n) * stride_words, 0,
                        static_cast<size_t>(c->n_padded - n) * stride_words * 8, c->stream));
   // Zobrist table: zlen = longest + 2 positions (two insertions, src/db.cc:652), 4 values each,
@@ -379,6 +401,8 @@ static int db_finalize(swb200_ctx *c) {
   c->toc(0);
   c->max_len = c->minmax[0];
   c->min_len = ~c->minmax[1];
+  if (c->job_max_len) c->max_len = std::max(c->max_len, c->job_max_len);      // multi-GPU: the job's range, identical on every rank
+  if (c->job_min_len) c->min_len = std::min(c->min_len, c->job_min_len);
   c->sorted_desc = c->unsorted == 0;
   return SWB200_OK;
 }
@@ -476,6 +500,34 @@ int swb200_load_db_shard(swb200_ctx *c, const uint64_t *words, uint32_t stride_w
   API_END()
 }
 
+// Sharded database (BASELINE configs[4]): this context keeps ONLY the rows [first, first + count) of the job's sorted database;
+// the abundance runs of the whole database (tiny: one entry per distinct abundance) are replicated so that any rank can
+// tell whether two amplicon ids have equal abundances.
+int swb200_load_db_rows(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint32_t *len, const uint64_t *abundance,
+                        uint32_t n_total, uint32_t first, uint32_t count, const uint32_t *run_start, uint32_t n_runs) {
+  API_BEGIN(c)
+  if (n_total == 0 || stride_words == 0 || count == 0 || static_cast<uint64_t>(first) + count > n_total || !words || !len || !abundance ||
+      !run_start || n_runs == 0 || run_start[0] != 0 || run_start[n_runs] != n_total || n_total >= 0xFFFFFFF0u) {
+    g_err = "load_db_rows: bad argument";
+    return SWB200_EINVAL;
+  }
+  c->indexed = c->have_network = c->clustered = false;
+  c->n = n_total; c->stride = stride_words; c->batch = 2; c->n_padded = n_total;
+  c->db_sharded = true; c->row_first = first; c->row_count = count;
+  c->words.alloc(static_cast<size_t>(count) * stride_words + 2);
+  c->len.alloc(count);
+  c->abundance.alloc(count);
+  c->run_start_d.alloc(static_cast<size_t>(n_runs) + 1);
+  c->n_runs = n_runs;
+  c->tic();
+  db_upload(c, c->words.p, words, static_cast<size_t>(count) * stride_words * 8);
+  db_upload(c, c->len.p, len, static_cast<size_t>(count) * 4);
+  db_upload(c, c->abundance.p, abundance, static_cast<size_t>(count) * 8);
+  db_upload(c, c->run_start_d.p, run_start, (static_cast<size_t>(n_runs) + 1) * 4);
+  return db_finalize(c);
+  API_END()
+}
+
 int swb200_load_db_device(swb200_ctx *c, const void *d_words, uint32_t stride_words, const void *d_len, const void *d_abundance,
                           uint32_t n) {
   API_BEGIN(c)
@@ -525,9 +577,12 @@ static TileJoinParams tile_params(swb200_ctx *c) {
 // ---- tile store (d1_tilestore.cuh) ----------------------------------------------------------------------------------
 static TileStoreParams ts_params(swb200_ctx *c) {
   TileStoreParams J{};
-  J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p; J.ab_all = c->abundance.p;
-  J.n = c->n; J.row_first = 0; J.row_count = c->n;
+  J.words = c->words.p; J.len = c->len.p; J.abundance = c->abundance.p;
+  J.ab_all = c->db_sharded ? nullptr : c->abundance.p; J.run_start = c->run_start_d.p; J.n_runs = c->n_runs;
+  J.n = c->n; J.row_first = c->row_first; J.row_count = c->row_count;
   J.stride = c->stride; J.K = c->jK;
+  J.kmask1 = c->jK >= 64 ? ~0ull : (c->jK > 32 ? (1ull << (2 * (c->jK - 32))) - 1 : 0ull);
+  J.kmask0 = c->jK >= 32 ? ~0ull : (1ull << (2 * c->jK)) - 1;
   uint32_t idb = 12;
   while (idb < 32 && (1ull << idb) < c->n) ++idb;
   J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0; J.ncb = c->ncb;
@@ -553,31 +608,78 @@ static void index_tilestore(swb200_ctx *c) {
   const uint32_t rec_bytes = 8 * (c->stride + 1);                // shared memory per record either way: entry + row
   uint32_t cap = std::min<uint32_t>(768, (36u * 1024u) / rec_bytes) & ~1u;
   cap = std::max<uint32_t>(cap, 64);
+  if (c->ts_cap_opt >= 64) cap = std::min(cap, c->ts_cap_opt & ~1u);
   const uint32_t fill = cap * 2 / 3;                       // mean records per tile: Poisson(512) never reaches 768
   const uint64_t want_tiles = (static_cast<uint64_t>(c->n) * 2 + fill - 1) / fill;
   c->ts_tiles = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(want_tiles, 0x7FFFFFFFull)));
   if (c->tj_cmax_override >= 2) cap = std::max<uint32_t>(2, std::min(cap, c->tj_cmax_override) & ~1u);
   c->ts_cap = cap;
-  const uint32_t per = (c->ts_tiles + c->shard_world - 1) / c->shard_world;
-  c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * c->shard_rank, c->ts_tiles));
+  const uint32_t own_world = (c->dist_world > 1 && c->index_exchange) ? c->dist_world : static_cast<uint32_t>(c->shard_world);
+  const uint32_t own_rank = (c->dist_world > 1 && c->index_exchange) ? c->dist_rank : static_cast<uint32_t>(c->shard_rank);
+  const uint32_t per = (c->ts_tiles + own_world - 1) / own_world;
+  c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * own_rank, c->ts_tiles));
   c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
   const uint32_t T = c->ts_hi - c->ts_lo;
   c->ts_smem = static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + static_cast<size_t>(cap) * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
   c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * rw, 2) + 2);
   c->ts_cursor.alloc(static_cast<size_t>(T) * 2 + 2);
   if (c->ts_ovf_cap == 0 || c->tj_cmax_override >= 2)
-    c->ts_ovf_cap = std::max<uint64_t>(c->ts_ovf_cap, c->tj_cmax_override >= 2 ? static_cast<uint64_t>(c->n) * 2 / c->shard_world + (1u << 16)
-                                                                                : static_cast<uint64_t>(c->n) / 8 / c->shard_world + (1u << 16));
+    c->ts_ovf_cap = std::max<uint64_t>(c->ts_ovf_cap, c->tj_cmax_override >= 2 ? static_cast<uint64_t>(c->n) * 2 / own_world + (1u << 16)
+                                                                                : static_cast<uint64_t>(c->n) / 8 / own_world + (1u << 16));
   c->ts_ovf.alloc(c->ts_ovf_cap * (rw + 1));
   CK(cudaMemsetAsync(c->counters.p, 0, 17 * 8, c->stream));
   CK(cudaMemsetAsync(c->counters.p + 32, 0, 5 * 8, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p, 0, static_cast<size_t>(T) * 4, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p + T, 0xFF, static_cast<size_t>(T) * 4, c->stream));
-  if (T) {
+  const bool exchange = c->dist_world > 1 && c->index_exchange;
+  if (exchange) {
+    // multi-GPU: hash only this rank's rows, route every record to the owner of its tile over NVLink (d1_tsroute.cuh)
+    TsRouteParams R{};
+    R.J = ts_params(c);
+    R.rank = c->dist_rank; R.world = c->dist_world;
+    R.tiles_per_rank = per;
+    for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
+    R.rec_words = c->ts_fat ? c->stride + 1 : 2;
+    R.inbox_cap = (c->dist_buffer_bytes - kDistCtlBytes) / (static_cast<uint64_t>(R.world) * R.rec_words * 8);
+    c->ts_route_cnt.alloc(kDistMaxWorld + 4);
+    R.counters = c->ts_route_cnt.p;
+    R.done_ctas = reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld);
+    R.err = R.done_ctas + 4;
+    R.epoch = ++c->idx_epoch;
+    if (R.epoch == 1) CK(cudaMemsetAsync(c->ts_route_cnt.p, 0, (kDistMaxWorld + 4) * 8, c->stream));
+    else CK(cudaMemsetAsync(c->ts_route_cnt.p, 0, kDistMaxWorld * 8, c->stream));
+    if (!c->db_sharded) {                                      // replicated database: this rank hashes an equal share of the rows
+      const uint32_t share = (c->n + R.world - 1) / R.world;
+      R.J.row_first = std::min<uint64_t>(static_cast<uint64_t>(share) * R.rank, c->n);
+      R.J.row_count = std::min<uint32_t>(share, c->n - R.J.row_first);
+      R.J.words += static_cast<size_t>(R.J.row_first) * c->stride;
+      R.J.len += R.J.row_first;
+      R.J.abundance += R.J.row_first;
+    }
+    const size_t smem = static_cast<size_t>(kTsRows) * c->stride * 8 + 16 + static_cast<size_t>(2 * kTsRows) * R.rec_words * 8;
+    const unsigned route_grid = (R.J.row_count + kTsRows - 1) / kTsRows;
+    const unsigned scat_grid = static_cast<unsigned>(c->sm_count * 8);
+    k_ts_wait<<<1, 32, 0, c->stream>>>(R, 0);
+    if (route_grid) {
+      if (c->ts_fat) {
+        CK(cudaFuncSetAttribute(k_ts_route<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k_ts_route<true><<<route_grid, kTsRows, smem, c->stream>>>(R);
+      } else {
+        CK(cudaFuncSetAttribute(k_ts_route<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k_ts_route<false><<<route_grid, kTsRows, smem, c->stream>>>(R);
+      }
+    }
+    k_ts_wait<<<1, 32, 0, c->stream>>>(R, 1);
+    R.J = ts_params(c);                                        // the receiving side works on the local tiles (and, slim, on the whole database)
+    if (c->ts_fat) k_ts_scatter_inbox<true><<<scat_grid, 256, 0, c->stream>>>(R);
+    else k_ts_scatter_inbox<false><<<scat_grid, 256, 0, c->stream>>>(R);
+    CK(cudaGetLastError());
+    c->launches += 4;
+  } else if (T) {
     TileStoreParams J = ts_params(c);
     const size_t smem = static_cast<size_t>(kTsRows) * c->stride * 8 + 16;
     CK(cudaFuncSetAttribute(k_ts_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k_ts_scatter<<<(c->n + kTsRows - 1) / kTsRows, kTsRows, smem, c->stream>>>(J);
+    k_ts_scatter<<<(c->row_count + kTsRows - 1) / kTsRows, kTsRows, smem, c->stream>>>(J);
     CK(cudaGetLastError());
     c->launches += 1;
   }
@@ -617,6 +719,13 @@ int swb200_d1_index(swb200_ctx *c) {
   c->join_active = c->tile_active = c->ts_active = false;
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
   const bool join = c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8;
+  if (c->db_sharded) {
+    if (!(join && c->join_kernel == 0 && c->stride <= 64 && c->max_len < 8192 && c->dist_world > 1 && c->index_exchange && c->ts_fat && c->unsorted == 0)) {
+      g_err = "d1_index: a sharded database (swb200_load_db_rows) needs swb200_dist_setup, tile_rows = 1, the default join, a database sorted "
+              "by abundance and sequences of 16..8191 nt";
+      return SWB200_EUNSUPPORTED;
+    }
+  }
   if (join && c->join_kernel == 0 && c->stride <= 64 && c->max_len < 8192) {
     // JOIN over the tile store (d1_tilestore.cuh): one scatter pass, fat records in fixed-capacity tile slots
     c->tic();
@@ -842,6 +951,12 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
         continue;
       }
     }
+    if (c->ts_active && c->dist_world > 1 && c->index_exchange) {
+      uint32_t rerr[2] = {0, 0};
+      CK(cudaMemcpy(rerr, reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld) + 4, sizeof rerr, cudaMemcpyDeviceToHost));
+      if (rerr[0]) { c->toc(2); g_err = "d1_index: a peer did not take part in the index exchange within 5 s"; return SWB200_ECUDA; }
+      if (rerr[1]) { c->toc(2); g_err = "d1_index: an index inbox overflowed; set up larger peer buffers (swb200_dist_buffer_bytes)"; return SWB200_ENOMEM; }
+    }
     if (c->join_active && static_cast<uint32_t>(host[8])) { c->toc(2); g_err = "some fasta entries have identical sequences"; return SWB200_EDUPLICATE; }
     if (c->n_edges <= c->edges.n) break;
     c->edges.alloc(c->n_edges + c->n_edges / 8);    // link list overflowed: grow and redo (dense data)
@@ -897,6 +1012,7 @@ int swb200_d1_import_links_device(swb200_ctx *c, const void *d_pairs, uint64_t n
 
 int swb200_d1_get_network(swb200_ctx *c, uint64_t *row_ptr, uint32_t *col) {
   API_BEGIN(c)
+  if (c->db_sharded) { g_err = "d1_get_network: not available on a sharded database (use the multi-GPU entry points)"; return SWB200_EUNSUPPORTED; }
   if (!c->have_network || !row_ptr) { g_err = "get_network: no network / null buffer"; return SWB200_EINVAL; }
   // output path (-j writer), not the timed hot path: counting sort by source on the host, rows ascending
   std::vector<uint2> e(c->n_edges);
@@ -1056,6 +1172,7 @@ static void run_cluster(swb200_ctx *c) {
 
 int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent) {
   API_BEGIN(c)
+  if (c->db_sharded) { g_err = "d1_cluster: not available on a sharded database (use the multi-GPU entry points)"; return SWB200_EUNSUPPORTED; }
   if (!c->have_network) { g_err = "d1_cluster: call swb200_d1_network first"; return SWB200_EINVAL; }
   const uint32_t n = c->n;
   c->tic();
@@ -1124,6 +1241,8 @@ int swb200_dist_setup(swb200_ctx *c, uint32_t rank, uint32_t world, void *const 
   }
   c->dist_rank = rank;
   c->dist_world = world;
+  c->dist_buffer_bytes = buffer_bytes;
+  c->idx_epoch = 0;
   c->dist_cap = (buffer_bytes - kDistCtlBytes) / (static_cast<uint64_t>(world) * (sizeof(uint2) + kDistLogFactor * sizeof(DistRec)));
   c->dist_calls = 0;
   c->dist_lcnt.alloc(2 * kDistMaxWorld);
@@ -1164,7 +1283,7 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   CK(cudaFuncSetAttribute(k_cluster_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_dist, 256, dyn));
-  const unsigned grid = static_cast<unsigned>(c->sm_count * std::max(occ, 1));
+  const unsigned grid = std::max(1u, static_cast<unsigned>(c->sm_count * std::max(occ, 1)) / static_cast<unsigned>(c->dist_grid_div));
   c->tic();
   void *args[] = {&D};
   CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_dist), dim3(grid), dim3(256), args, dyn, c->stream));
@@ -1215,6 +1334,7 @@ int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const 
                       uint32_t *generation, uint32_t *parent, uint32_t *pdiff) {
   API_BEGIN(c)
   if (c->n == 0 || !penalties || d < 2) { g_err = "dn_cluster: needs a database, penalties and d >= 2"; return SWB200_EINVAL; }
+  if (c->db_sharded) { g_err = "dn_cluster: not available on a sharded database"; return SWB200_EUNSUPPORTED; }
   if (c->too_long) { g_err = "sequences longer than 5,000 nt are not supported by the clustering kernels"; return SWB200_EUNSUPPORTED; }
   const uint32_t n = c->n;
   const int64_t mis = penalties[0], go = penalties[1], ge = penalties[2];
@@ -1328,6 +1448,7 @@ int swb200_dn_cluster(swb200_ctx *c, uint32_t d, int no_cluster_breaking, const 
 int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand, uint64_t *n_light, uint64_t *n_heavy) {
   API_BEGIN(c)
   if (!c->clustered) { g_err = "d1_fastidious: call swb200_d1_cluster first"; return SWB200_EINVAL; }
+  if (c->db_sharded) { g_err = "d1_fastidious: not available on a sharded database"; return SWB200_EUNSUPPORTED; }
   const uint32_t n = c->n;
   const uint32_t Kj = std::min<uint32_t>(64, c->min_len / 3);
   if (c->fast_kernel != 1 && Kj >= 8) {
@@ -1457,6 +1578,7 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
 // d = 0 (src/derep.cc:276-354): classes of identical sequences, kernels in d0_derep.cuh.  Device-timed as phase 7.
 int swb200_d0_dereplicate(swb200_ctx *c, uint32_t *rep, uint64_t *mass, uint32_t *size, uint32_t *singletons, uint64_t *n_clusters) {
   API_BEGIN(c)
+  if (c->db_sharded) { g_err = "d0_dereplicate: not available on a sharded database (use the multi-GPU entry points)"; return SWB200_EUNSUPPORTED; }
   if (c->n == 0) { g_err = "d0_dereplicate: no database loaded"; return SWB200_EINVAL; }
   if (c->db_pending) { g_err = "d0_dereplicate: swb200_load_db_shard must be followed by the row exchange and swb200_db_commit"; return SWB200_EINVAL; }
   const uint32_t n = c->n;
