@@ -242,9 +242,8 @@ def main():
     ap.add_argument("--enum-mode", type=int, default=2, help="0 full microvariant enumeration, 1 half, 2 pigeonhole join (default)")
     ap.add_argument("--join-kernel", type=int, default=0, help="JOIN: 0 tile store (default), 1 global hash multimap, 2 r1 tile join")
     ap.add_argument("--cluster-kernel", type=int, default=0)
-    ap.add_argument("--multi", default="dist", choices=["dist", "replicated"],
-                    help="N>1 clustering: dist = sharded by amplicon, exchange over peer memory inside the kernel (default); "
-                         "replicated = links all-gathered with NCCL, every GPU clusters everything")
+    ap.add_argument("--multi", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="N>1 database layout: replicated on every GPU (default for c2) or sharded by rows (default for c5); see bench_multi.py")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

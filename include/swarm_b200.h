@@ -162,6 +162,10 @@ uint32_t swb200_dist_row_count(uint32_t n_total, uint32_t rank, uint32_t world);
 uint32_t swb200_dist_row_id(uint32_t rank, uint32_t world, uint32_t row);
 int  swb200_dist_setup(swb200_ctx *ctx, uint32_t rank, uint32_t world, void *const *peer_buffers, uint64_t buffer_bytes);
 int  swb200_d1_cluster_dist(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent);
+/* Optional: allocate now every device buffer the multi-GPU step will use for the loaded database.  Only needed when several
+ * ranks SHARE one GPU (tests): cudaMalloc / cudaFree wait for the whole device, so allocating inside a step would block behind
+ * a peer's kernel that is spinning on a cross-rank barrier. */
+int  swb200_d1_reserve(swb200_ctx *ctx);
 
 /* Replaces the fastidious passes (mark_light_thread / check_heavy_thread, src/algod1.cc:374-552):
  * for every amplicon l of a light swarm (mass < boundary), graft_cand[l] = the smallest amplicon id h

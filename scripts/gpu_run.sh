@@ -27,6 +27,8 @@ for step in "$@"; do
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python scripts/probe.py 10000000 default= > $O/${TAG}_fullp_$k.out 2>&1
           python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -45 $O/${TAG}_$k.txt ;;
+    san) timeout 900 compute-sanitizer --tool memcheck --print-limit 8 python -m pytest tests -x -q -m gpu -k "$arg" > $O/${TAG}_san.log 2>&1
+         grep -E "=========|passed|failed" $O/${TAG}_san.log | head -60 ;;
     sanitize) bash scripts/gpu_sanitize.sh ;;
     *) echo "unknown step $step" ;;
   esac

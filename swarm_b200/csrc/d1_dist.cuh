@@ -67,6 +67,7 @@ struct DistParams {
   unsigned long long epoch_base;                  // barrier epochs of this call start above it
   uint32_t dbg;                                   // profiling aid: bit 0 = skip the peer stores of the rounds (results are then wrong)
   unsigned long long *ts;                         // optional profiling aid: %globaltimer of thread 0 at phase boundaries (128 slots)
+  unsigned int *gbar;                             // grid barrier words (SwGrid), zero before the first launch
   uint32_t *lflags;                               // 3 rotating "this rank sent or lowered something" words + [3] abort + [4] rounds + [5] barrier result
 };
 
@@ -81,6 +82,37 @@ __device__ __forceinline__ uint2 *dist_links(const DistParams &D, uint32_t r, ui
 __device__ __forceinline__ DistRec *dist_upd(const DistParams &D, uint32_t r, uint32_t s) {
   return reinterpret_cast<DistRec *>(D.peer[r] + kDistCtlBytes + D.world * D.cap_links * sizeof(uint2)) + static_cast<size_t>(s) * D.cap_upd;
 }
+
+// Grid-wide barrier in global memory (count + generation).  cooperative_groups' grid.sync() needs a cooperative launch, and
+// the driver never co-schedules two cooperative kernels on one GPU — which is exactly what a job whose ranks share a GPU
+// (tests: several ranks on the single GPU of the box) needs.  With this barrier the kernel can be launched either way:
+// cooperatively (one rank per GPU: co-residency of the grid guaranteed) or plainly with a grid small enough to be resident.
+struct SwGrid {
+  unsigned int *bar;                              // [0] arrivals [1] generation [2] set when a CTA waited longer than 5 s
+  __device__ __forceinline__ void sync() const {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int gen = *reinterpret_cast<volatile unsigned int *>(&bar[1]);
+      if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
+        bar[0] = 0;
+        __threadfence();
+        atomicAdd(&bar[1], 1u);
+      } else {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        for (uint32_t spins = 0; *reinterpret_cast<volatile unsigned int *>(&bar[1]) == gen; ++spins) {
+          if ((spins & 1023u) == 1023u) {
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) { bar[2] = 1u; break; }      // a CTA of this grid never became resident
+          }
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
 
 struct DistSmem {
   uint32_t cnt[kDistMaxWorld + 1];
@@ -136,7 +168,7 @@ __device__ __forceinline__ void dist_scatter(const DistParams &D, DistSmem &sm, 
 
 // All CTAs of all ranks.  Publishes this sender's append counters (`counters[p]` -> the [rank] entry of the array at
 // `remote_offset` in peer p's control block), and returns the OR over the ranks of *lflag_word.
-__device__ __forceinline__ uint32_t dist_barrier(const DistParams &D, cooperative_groups::grid_group &grid, unsigned long long epoch,
+__device__ __forceinline__ uint32_t dist_barrier(const DistParams &D, const SwGrid &grid, unsigned long long epoch,
                                                  volatile uint32_t *lflag_word, unsigned long long *counters, size_t remote_offset) {
   grid.sync();
   if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -184,7 +216,7 @@ __device__ __forceinline__ void dist_stamp(const DistParams &D, uint64_t tid, ui
 }
 
 __global__ void __launch_bounds__(256, 3) k_cluster_dist(DistParams D) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const SwGrid grid{D.gbar};
   __shared__ DistSmem sm;
   __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
   extern __shared__ __align__(16) unsigned char dist_dyn[];      // kDistChunk * 16 bytes: sorted staging

@@ -602,8 +602,8 @@ static TileStoreParams ts_params(swb200_ctx *c) {
   return J;
 }
 
-// "Hashing sequences" for the tile store: geometry, buffers, ONE scatter pass.  No host synchronisation.
-static void index_tilestore(swb200_ctx *c) {
+// tile geometry + every buffer of the tile-store path (no stream work: swb200_d1_reserve calls it ahead of time)
+static uint32_t ts_prepare(swb200_ctx *c) {
   const uint32_t rw = c->ts_fat ? c->stride + 1 : 1;
   const uint32_t rec_bytes = 8 * (c->stride + 1);                // shared memory per record either way: entry + row
   uint32_t cap = std::min<uint32_t>(768, (36u * 1024u) / rec_bytes) & ~1u;
@@ -627,6 +627,15 @@ static void index_tilestore(swb200_ctx *c) {
     c->ts_ovf_cap = std::max<uint64_t>(c->ts_ovf_cap, c->tj_cmax_override >= 2 ? static_cast<uint64_t>(c->n) * 2 / own_world + (1u << 16)
                                                                                 : static_cast<uint64_t>(c->n) / 8 / own_world + (1u << 16));
   c->ts_ovf.alloc(c->ts_ovf_cap * (rw + 1));
+  c->ts_route_cnt.alloc(kDistMaxWorld + 4);
+  if (c->edges.n == 0) c->edges.alloc(std::max<size_t>(static_cast<size_t>(c->n) * 4 / own_world + (1u << 16), 1u << 16));
+  return per;
+}
+
+// "Hashing sequences" for the tile store: ONE scatter pass (or, multi-GPU, the index exchange).  No host synchronisation.
+static void index_tilestore(swb200_ctx *c) {
+  const uint32_t per = ts_prepare(c);
+  const uint32_t T = c->ts_hi - c->ts_lo;
   CK(cudaMemsetAsync(c->counters.p, 0, 17 * 8, c->stream));
   CK(cudaMemsetAsync(c->counters.p + 32, 0, 5 * 8, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p, 0, static_cast<size_t>(T) * 4, c->stream));
@@ -641,7 +650,6 @@ static void index_tilestore(swb200_ctx *c) {
     for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
     R.rec_words = c->ts_fat ? c->stride + 1 : 2;
     R.inbox_cap = (c->dist_buffer_bytes - kDistCtlBytes) / (static_cast<uint64_t>(R.world) * R.rec_words * 8);
-    c->ts_route_cnt.alloc(kDistMaxWorld + 4);
     R.counters = c->ts_route_cnt.p;
     R.done_ctas = reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld);
     R.err = R.done_ctas + 4;
@@ -649,7 +657,7 @@ static void index_tilestore(swb200_ctx *c) {
     if (R.epoch == 1) CK(cudaMemsetAsync(c->ts_route_cnt.p, 0, (kDistMaxWorld + 4) * 8, c->stream));
     else CK(cudaMemsetAsync(c->ts_route_cnt.p, 0, kDistMaxWorld * 8, c->stream));
     if (!c->db_sharded) {                                      // replicated database: this rank hashes an equal share of the rows
-      const uint32_t share = (c->n + R.world - 1) / R.world;
+      const uint32_t share = ((c->n + R.world - 1) / R.world + 1u) & ~1u;          // even: the TMA row staging needs 16-byte aligned sources
       R.J.row_first = std::min<uint64_t>(static_cast<uint64_t>(share) * R.rank, c->n);
       R.J.row_count = std::min<uint32_t>(share, c->n - R.J.row_first);
       R.J.words += static_cast<size_t>(R.J.row_first) * c->stride;
@@ -925,8 +933,10 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
       CK(cudaGetLastError());
     } else
     run_network(c);
-    unsigned long long host[37];                                           // one read-back: links, stats, duplicate flag, overflow counters
-    CK(cudaMemcpyAsync(host, c->counters.p, sizeof host, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long *host = static_cast<unsigned long long *>(c->staging(4096));   // one read-back (pinned): links, stats, duplicate flag, overflow counters
+    CK(cudaMemcpyAsync(host, c->counters.p, 37 * 8, cudaMemcpyDeviceToHost, c->stream));
+    const bool exchanged = c->ts_active && c->dist_world > 1 && c->index_exchange;
+    if (exchanged) CK(cudaMemcpyAsync(host + 40, reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld) + 4, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_edges = host[0];
     for (int i = 0; i < 4; ++i) c->stats[i] = host[1 + i];
@@ -951,9 +961,8 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
         continue;
       }
     }
-    if (c->ts_active && c->dist_world > 1 && c->index_exchange) {
-      uint32_t rerr[2] = {0, 0};
-      CK(cudaMemcpy(rerr, reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld) + 4, sizeof rerr, cudaMemcpyDeviceToHost));
+    if (exchanged) {
+      const uint32_t *rerr = reinterpret_cast<const uint32_t *>(host + 40);
       if (rerr[0]) { c->toc(2); g_err = "d1_index: a peer did not take part in the index exchange within 5 s"; return SWB200_ECUDA; }
       if (rerr[1]) { c->toc(2); g_err = "d1_index: an index inbox overflowed; set up larger peer buffers (swb200_dist_buffer_bytes)"; return SWB200_ENOMEM; }
     }
@@ -1244,12 +1253,51 @@ int swb200_dist_setup(swb200_ctx *c, uint32_t rank, uint32_t world, void *const 
   c->dist_buffer_bytes = buffer_bytes;
   c->idx_epoch = 0;
   c->dist_cap = (buffer_bytes - kDistCtlBytes) / (static_cast<uint64_t>(world) * (sizeof(uint2) + kDistLogFactor * sizeof(DistRec)));
+  c->dist_cap &= ~1ull;                            // even: the 16-byte message records behind the link sub-regions stay aligned for any world size
   c->dist_calls = 0;
   c->dist_lcnt.alloc(2 * kDistMaxWorld);
   c->dist_links.alloc(c->dist_cap * world);
   CK(cudaMemsetAsync(c->dist_lcnt.p, 0, 2 * kDistMaxWorld * 8, c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 40, 0, 2 * 8, c->stream));
   CK(cudaMemsetAsync(c->dist_peer[rank], 0, kDistCtlBytes, c->stream));      // my own control block; the caller barriers before the first use
   CK(cudaStreamSynchronize(c->stream));
+  API_END()
+}
+
+// every buffer swb200_d1_cluster_dist needs (no stream work)
+static void dist_prepare(swb200_ctx *c) {
+  const uint32_t n = c->n;
+  const uint64_t nblocks = (static_cast<uint64_t>(n) + kDistBlock - 1) / kDistBlock;
+  const uint32_t n_local = static_cast<uint32_t>((nblocks + c->dist_world - 1) / c->dist_world * kDistBlock);
+  c->key.alloc(std::max<uint32_t>(n_local, 1)); c->label.alloc(n); c->generation.alloc(n); c->parent.alloc(n);
+  c->cl_bits.alloc(static_cast<size_t>((n_local + 31) / 32) * 3);
+  c->cl_ts.alloc(128);
+  c->staging(4096);
+}
+
+// Allocate, ahead of time, every device buffer the multi-GPU step (d1_index with the index exchange, d1_network,
+// d1_cluster_dist) will use for the loaded database.  A real multi-GPU job does not need this; it exists for jobs whose ranks
+// SHARE one GPU (tests): cudaMalloc / cudaFree wait for the whole device, so a rank that allocated inside a step would block
+// behind a peer's kernel that is itself spinning on a cross-rank barrier, waiting for that rank.
+int swb200_d1_reserve(swb200_ctx *c) {
+  API_BEGIN(c)
+  if (c->n == 0 || c->dist_world == 0) { g_err = "d1_reserve: needs a database and swb200_dist_setup"; return SWB200_EINVAL; }
+  c->jK = std::min<uint32_t>(64, c->min_len / 2);
+  ts_prepare(c);
+  dist_prepare(c);
+  // CUDA loads a kernel lazily at its first launch, and that load synchronises the context: load them all now
+  const void *kernels[] = {reinterpret_cast<const void *>(k_ts_wait), reinterpret_cast<const void *>(k_ts_route<true>),
+                           reinterpret_cast<const void *>(k_ts_route<false>), reinterpret_cast<const void *>(k_ts_scatter_inbox<true>),
+                           reinterpret_cast<const void *>(k_ts_scatter_inbox<false>), reinterpret_cast<const void *>(k_ts_scatter),
+                           reinterpret_cast<const void *>(k_ts_join<true, true>), reinterpret_cast<const void *>(k_ts_join<true, false>),
+                           reinterpret_cast<const void *>(k_ts_join<false, true>), reinterpret_cast<const void *>(k_ts_join<false, false>),
+                           reinterpret_cast<const void *>(k_ts_big<true, true>), reinterpret_cast<const void *>(k_ts_big<true, false>),
+                           reinterpret_cast<const void *>(k_ts_big<false, true>), reinterpret_cast<const void *>(k_ts_big<false, false>),
+                           reinterpret_cast<const void *>(k_cluster_dist)};
+  for (const void *k : kernels) {
+    cudaFuncAttributes attr;
+    CK(cudaFuncGetAttributes(&attr, k));
+  }
   API_END()
 }
 
@@ -1263,9 +1311,8 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   const uint64_t nblocks = (static_cast<uint64_t>(n) + kDistBlock - 1) / kDistBlock;
   D.n_local = static_cast<uint32_t>((nblocks + D.world - 1) / D.world * kDistBlock);
   D.edges = c->edges.p; D.m_local = c->n_edges;
-  c->key.alloc(std::max<uint32_t>(D.n_local, 1)); c->label.alloc(n); c->generation.alloc(n); c->parent.alloc(n);
+  dist_prepare(c);
   D.nwords = (D.n_local + 31) / 32;
-  c->cl_bits.alloc(static_cast<size_t>(D.nwords) * 3);
   D.key = c->key.p; D.parent = c->parent.p; D.label = c->label.p; D.generation = c->generation.p; D.bits = c->cl_bits.p;
   D.my_links = c->dist_links.p; D.lcnt = c->dist_lcnt.p;
   for (uint32_t r = 0; r < D.world; ++r) D.peer[r] = c->dist_peer[r];
@@ -1273,6 +1320,7 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   D.cap_upd = c->dist_cap * kDistLogFactor;
   D.epoch_base = (++c->dist_calls) << 24;
   D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
+  D.gbar = reinterpret_cast<unsigned int *>(c->counters.p + 40);
   if (const char *dbg = std::getenv("SWB200_DIST_DBG")) D.dbg = static_cast<uint32_t>(std::atoi(dbg));
   if (std::getenv("SWB200_CLUSTER_TS")) {
     c->cl_ts.alloc(128);
@@ -1286,13 +1334,19 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   const unsigned grid = std::max(1u, static_cast<unsigned>(c->sm_count * std::max(occ, 1)) / static_cast<unsigned>(c->dist_grid_div));
   c->tic();
   void *args[] = {&D};
-  CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_dist), dim3(grid), dim3(256), args, dyn, c->stream));
+  if (c->dist_grid_div > 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);      // ranks sharing one GPU: cooperative kernels are never co-scheduled
+  else CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_dist), dim3(grid), dim3(256), args, dyn, c->stream));
+  CK(cudaGetLastError());
   c->launches++;
-  uint32_t h[6] = {0, 0, 0, 0, 0, 0};
-  uint32_t overflow = 0;
-  CK(cudaMemcpyAsync(h, D.lflags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&overflow, c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 4, cudaMemcpyDeviceToHost, c->stream));
+  // read-backs go through PINNED memory: a copy into pageable memory blocks inside the driver until the kernel has finished,
+  // and that kernel may be waiting for a peer whose host thread (ranks sharing one process) then cannot launch
+  uint32_t *hp = static_cast<uint32_t *>(c->staging(4096));
+  CK(cudaMemcpyAsync(hp, D.lflags, 6 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hp + 8, c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 4, cudaMemcpyDeviceToHost, c->stream));
   c->toc(3);
+  uint32_t h[6];
+  for (int i = 0; i < 6; ++i) h[i] = hp[i];
+  const uint32_t overflow = hp[8];
   c->dist_rounds = h[4];
   if (D.ts) {
     unsigned long long t[128];
@@ -1302,7 +1356,11 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
     for (int i = 1; i < 128 && t[i]; ++i) line += " " + std::to_string(static_cast<long long>((t[i] - t[i - 1]) / 1000));
     std::fprintf(stderr, "%s\n", line.c_str());
   }
-  if (h[3]) { g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s"; return SWB200_ECUDA; }
+  if (h[3]) {
+    CK(cudaMemsetAsync(c->counters.p + 40, 0, 2 * 8, c->stream));
+    g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s";
+    return SWB200_ECUDA;
+  }
   if (overflow) {
     CK(cudaMemsetAsync(c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 0, 4, c->stream));
     CK(cudaMemsetAsync(c->dist_lcnt.p, 0, 2 * kDistMaxWorld * 8, c->stream));

@@ -66,6 +66,7 @@ def engine_lib():
         L.swb200_dist_row_id.restype = C.c_uint32
         L.swb200_dist_setup.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.c_uint64]
         L.swb200_d1_cluster_dist.argtypes = [vp, _u32p, _u32p, _u32p]
+        L.swb200_d1_reserve.argtypes = [vp]
         L.swb200_d1_index.argtypes = [vp]
         L.swb200_d1_network.argtypes = [vp, C.c_int, _u64p]
         L.swb200_d1_get_network.argtypes = [vp, _u64p, _u32p]
@@ -460,6 +461,9 @@ class Engine:
     def dist_setup(self, rank: int, world: int, peer_ptrs, nbytes: int):
         arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         self._ck(engine_lib().swb200_dist_setup(self._h, int(rank), int(world), arr, int(nbytes)))
+
+    def d1_reserve(self):
+        self._ck(engine_lib().swb200_d1_reserve(self._h))
 
     def d1_cluster_dist(self, out=None):
         """multi-GPU clustering (every rank calls it); out: dict of caller-owned uint32 arrays for this rank's rows"""

@@ -2,7 +2,8 @@
 buffers of the same GPU, every rank runs on its own host thread and stream, and the persistent clustering kernels share the
 SMs (option dist_grid_div).  This exercises exactly the code a multi-GPU job runs (index exchange through the inboxes,
 sharded join, peer-memory clustering) where the driver has a single GPU; on real peers only the addresses differ.
-Parity: every rank's rows == the single-GPU engine == the CPU oracle."""
+Parity: every rank's rows == the single-GPU engine == the CPU oracle.  (At most 4 ranks: the ranks' streams must not share a
+hardware queue — CUDA_DEVICE_MAX_CONNECTIONS is 8 — or a kernel queues behind a peer's kernel that is waiting for it.)"""
 import threading
 
 import numpy as np
@@ -35,6 +36,7 @@ def run_virtual(db, world, sharded, steps=2, **opt):
         else:
             e.load(db)
         e.dist_setup(r, world, ptrs, nbytes)
+        e.d1_reserve()
     torch.cuda.synchronize()
     outs = [None] * world
     errs = []
@@ -62,7 +64,7 @@ def run_virtual(db, world, sharded, steps=2, **opt):
     return outs
 
 
-@pytest.mark.parametrize("world,sharded", [(2, True), (2, False), (4, True), (3, False), (8, True)])
+@pytest.mark.parametrize("world,sharded", [(2, True), (2, False), (4, True), (3, False), (3, True)])
 def test_virtual_ranks_vs_oracle(built, tmp_path, world, sharded):
     fa = helpers.make_fasta(tmp_path / "s.fa", 120000, 150, 31 + world, 0)
     db = HostDb(fa)
