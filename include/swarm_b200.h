@@ -161,6 +161,10 @@ uint64_t swb200_dist_buffer_bytes(uint32_t n_total, uint32_t world, uint32_t ite
 uint32_t swb200_dist_row_count(uint32_t n_total, uint32_t rank, uint32_t world);
 uint32_t swb200_dist_row_id(uint32_t rank, uint32_t world, uint32_t row);
 int  swb200_dist_setup(swb200_ctx *ctx, uint32_t rank, uint32_t world, void *const *peer_buffers, uint64_t buffer_bytes);
+/* The same for ONE process that drives all GPUs (the command line, SWARM_B200_DEVICES): ctxs[r] = rank r's context (one per
+ * device, or several on one device — they then share its SMs); the peer buffers are allocated here and peer access between
+ * the devices is enabled.  Each rank is then driven by its own host thread. */
+int  swb200_dist_setup_local(swb200_ctx *const *ctxs, uint32_t world, uint32_t n_total, uint32_t items_per_amplicon);
 int  swb200_d1_cluster_dist(swb200_ctx *ctx, uint32_t *swarm_of, uint32_t *generation, uint32_t *parent);
 /* Optional: allocate now every device buffer the multi-GPU step will use for the loaded database.  Only needed when several
  * ranks SHARE one GPU (tests): cudaMalloc / cudaFree wait for the whole device, so allocating inside a step would block behind

@@ -179,6 +179,7 @@ struct swb200_ctx {
   int dist_grid_div = 1;             // test hook: several ranks share ONE GPU, each persistent kernel takes 1/div of the SMs
   int index_exchange = 1;            // after swb200_dist_setup: hash only this rank's rows, route the records to the tile owners
   unsigned long long idx_epoch = 0;
+  DevBuf<unsigned char> dist_own;              // peer-visible buffer allocated by swb200_dist_setup_local
   DevBuf<unsigned long long> ts_route_cnt;     // [16] sender counters, then done_ctas[2] + err[2] as 32-bit words
   uint64_t dist_buffer_bytes = 0;
   int skew_fallback = 1;             // dense data: abandon the quadratic overflow sweep for the linear enumeration (single GPU)
@@ -310,7 +311,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
-  c->run_start_d.release(); c->ts_route_cnt.release();
+  c->run_start_d.release(); c->ts_route_cnt.release(); c->dist_own.release();
   c->ts_store.release(); c->ts_ovf.release(); c->ts_cursor.release(); c->fr_deg.release(); c->fr_adj.release(); c->fr_spill.release();
   c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
@@ -1262,6 +1263,44 @@ int swb200_dist_setup(swb200_ctx *c, uint32_t rank, uint32_t world, void *const 
   CK(cudaMemsetAsync(c->dist_peer[rank], 0, kDistCtlBytes, c->stream));      // my own control block; the caller barriers before the first use
   CK(cudaStreamSynchronize(c->stream));
   API_END()
+}
+
+// Single-process multi-GPU: one context per device (or several per device: ranks sharing a GPU), driven by one host thread each.
+// Allocates every rank's peer-visible buffer, opens peer access between the devices and hands all addresses to all contexts —
+// what CUDA IPC / symmetric-memory handles do across processes is plain cudaMalloc + cudaDeviceEnablePeerAccess inside one.
+int swb200_dist_setup_local(swb200_ctx *const *ctxs, uint32_t world, uint32_t n_total, uint32_t items_per_amplicon) {
+  if (!ctxs || world == 0 || world > kDistMaxWorld) { g_err = "dist_setup_local: bad argument (1 <= world <= 16)"; return SWB200_EINVAL; }
+  for (uint32_t r = 0; r < world; ++r) if (!ctxs[r]) { g_err = "dist_setup_local: null context"; return SWB200_EINVAL; }
+  try {
+    const uint64_t bytes = swb200_dist_buffer_bytes(n_total, world, items_per_amplicon);
+    void *bufs[kDistMaxWorld] = {};
+    for (uint32_t r = 0; r < world; ++r) {
+      swb200_ctx *c = ctxs[r];
+      CK(cudaSetDevice(c->device));
+      for (uint32_t q = 0; q < world; ++q)
+        if (ctxs[q]->device != c->device) {
+          int can = 0;
+          CK(cudaDeviceCanAccessPeer(&can, c->device, ctxs[q]->device));
+          if (!can) { g_err = "dist_setup_local: the devices cannot access each other's memory (no NVLink / PCIe peer path)"; return SWB200_EUNSUPPORTED; }
+          const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+          cudaGetLastError();
+        }
+      c->dist_own.alloc(bytes);
+      CK(cudaMemset(c->dist_own.p, 0, bytes < (1u << 20) ? bytes : (1u << 20)));
+      bufs[r] = c->dist_own.p;
+      int sharing = 0;
+      for (uint32_t q = 0; q < world; ++q) sharing += ctxs[q]->device == c->device ? 1 : 0;
+      c->dist_grid_div = sharing;
+    }
+    for (uint32_t r = 0; r < world; ++r) {
+      const int rc = swb200_dist_setup(ctxs[r], r, world, bufs, bytes);
+      if (rc != SWB200_OK) return rc;
+    }
+  } catch (const CudaFail &f) {
+    return f.code;
+  }
+  return SWB200_OK;
 }
 
 // every buffer swb200_d1_cluster_dist needs (no stream work)

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
@@ -114,6 +115,81 @@ void engine_check(int status) {
           "Such files can be produced with swarm or vsearch:\n swarm -d 0 -w derep.fasta -o /dev/null input.fasta\nor\n"
           " vsearch --derep_fulllength input.fasta --sizein --sizeout --output derep.fasta\n");
   fatal(std::string("GPU engine: ") + swb200_last_error());
+}
+
+// SWARM_B200_DEVICES="0,1,2,3": the d = 1 clustering as ONE job on several GPUs, all driven by this process,
+// one host thread per rank.  The database is SHARDED by rows (no GPU holds it all), every rank hashes its own rows and routes the
+// records to the tile owners over peer memory, the join tiles are sharded by hash range and the clustering by amplicon.
+// Returns the links of all ranks when `links` is given (-j).
+struct RankStatus { int status = SWB200_OK; std::string error; };
+
+template <typename F>
+void on_every_rank(uint32_t world, std::vector<RankStatus> &st, F body) {
+  std::vector<std::thread> th;
+  for (uint32_t r = 0; r < world; ++r)
+    th.emplace_back([&, r] {
+      if (st[r].status != SWB200_OK) return;
+      st[r].status = body(r);
+      if (st[r].status != SWB200_OK) st[r].error = swb200_last_error();      // the error text is thread-local
+    });
+  for (auto &t : th) t.join();
+  for (uint32_t r = 0; r < world; ++r)
+    if (st[r].status != SWB200_OK) {
+      if (st[r].status == SWB200_EDUPLICATE) engine_check(st[r].status);
+      fatal("GPU engine (rank " + std::to_string(r) + "): " + st[r].error);
+    }
+}
+
+void cluster_d1_multi(const std::vector<swb200_ctx *> &ctxs, swbh_db *db, bool ncb, const uint32_t *run_start, uint32_t n_runs,
+                      std::vector<uint32_t> &swarm_of, std::vector<uint32_t> &generation, std::vector<uint32_t> &parent,
+                      std::vector<uint32_t> *links) {
+  const uint32_t world = static_cast<uint32_t>(ctxs.size()), n = swbh_db_count(db), stride = swbh_db_stride_words(db);
+  const uint32_t *len = swbh_db_lengths(db);
+  const uint32_t lmin = *std::min_element(len, len + n), lmax = *std::max_element(len, len + n);
+  const uint32_t per = ((n + world - 1) / world + 1u) & ~1u;      // even: the row staging needs 16-byte aligned shards
+  std::vector<RankStatus> st(world);
+  on_every_rank(world, st, [&](uint32_t r) {
+    swb200_ctx *c = ctxs[r];
+    int rc = swb200_set_option(c, "tile_rows", 1);
+    if (rc == SWB200_OK) rc = swb200_set_option(c, "job_min_len", lmin);
+    if (rc == SWB200_OK) rc = swb200_set_option(c, "job_max_len", lmax);
+    if (rc != SWB200_OK) return rc;
+    const uint32_t first = std::min<uint64_t>(static_cast<uint64_t>(per) * r, n), count = std::min<uint32_t>(per, n - first);
+    return swb200_load_db_rows(c, swbh_db_words(db) + static_cast<size_t>(first) * stride, stride, len + first,
+                               swbh_db_abundances(db) + first, n, first, count, run_start, n_runs);
+  });
+  if (swb200_dist_setup_local(ctxs.data(), world, n, 4) != SWB200_OK) fatal(std::string("GPU engine: ") + swb200_last_error());
+  on_every_rank(world, st, [&](uint32_t r) { return swb200_d1_reserve(ctxs[r]); });
+  std::vector<std::vector<uint32_t>> out(world * 3);
+  std::vector<uint64_t> n_links(world, 0);
+  on_every_rank(world, st, [&](uint32_t r) {
+    const uint32_t rows = swb200_dist_row_count(n, r, world);
+    for (int k = 0; k < 3; ++k) out[r * 3 + k].resize(rows ? rows : 1);
+    int rc = swb200_d1_index(ctxs[r]);
+    if (rc == SWB200_OK) rc = swb200_d1_network(ctxs[r], ncb ? 1 : 0, &n_links[r]);
+    if (rc == SWB200_OK) rc = swb200_d1_cluster_dist(ctxs[r], out[r * 3].data(), out[r * 3 + 1].data(), out[r * 3 + 2].data());
+    return rc;
+  });
+  for (uint32_t r = 0; r < world; ++r) {
+    const uint32_t rows = swb200_dist_row_count(n, r, world);
+    for (uint32_t i = 0; i < rows; ++i) {
+      const uint32_t id = swb200_dist_row_id(r, world, i);
+      swarm_of[id] = out[r * 3][i];
+      generation[id] = out[r * 3 + 1][i];
+      parent[id] = out[r * 3 + 2][i];
+    }
+  }
+  if (links) {
+    uint64_t total = 0;
+    for (uint64_t m : n_links) total += m;
+    links->resize(total * 2 + 2);
+    uint64_t at = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+      if (n_links[r] && swb200_d1_export_links(ctxs[r], links->data() + at * 2) != SWB200_OK) fatal(std::string("GPU engine: ") + swb200_last_error());
+      at += n_links[r];
+    }
+    links->resize(total * 2);
+  }
 }
 
 }  // namespace
@@ -237,13 +313,28 @@ int main(int argc, char **argv) {
   else std::fprintf(logf, "Fastidious:        No\n\n");
 
   // The CUDA context (driver initialisation, ~0.3-0.5 s) is created on a helper thread while the FASTA is parsed.
-  swb200_ctx *ctx = nullptr;
+  // SWARM_B200_DEVICES = "0,1,2,3": one clustering job on several GPUs (d = 1 without -f; anything else uses the first device).
+  std::vector<int> devices;
+  if (const char *list = std::getenv("SWARM_B200_DEVICES")) {
+    for (const char *p = list; *p;) {
+      char *end = nullptr;
+      const long v = std::strtol(p, &end, 10);
+      if (end == p) break;
+      devices.push_back(static_cast<int>(v));
+      p = *end == ',' ? end + 1 : end;
+    }
+  }
+  if (devices.empty()) { const char *dev = std::getenv("SWARM_B200_DEVICE"); devices.push_back(dev ? std::atoi(dev) : 0); }
+  if (devices.size() > 16 || P.differences != 1 || P.fastidious) devices.resize(1);
+  std::vector<swb200_ctx *> ctxs(devices.size(), nullptr);
+  swb200_ctx *&ctx = ctxs[0];
   int ctx_status = SWB200_OK;
   std::string ctx_error;
   std::thread ctx_thread([&] {
-    const char *dev = std::getenv("SWARM_B200_DEVICE");
-    ctx_status = swb200_create(&ctx, dev ? std::atoi(dev) : 0);
-    if (ctx_status != SWB200_OK) ctx_error = swb200_last_error();      // the error text is thread-local
+    for (size_t r = 0; r < devices.size() && ctx_status == SWB200_OK; ++r) {
+      ctx_status = swb200_create(&ctxs[r], devices[r]);
+      if (ctx_status != SWB200_OK) ctx_error = swb200_last_error();      // the error text is thread-local
+    }
   });
   // db_read
   if (used['t' - 'a']) swbh_set_threads(static_cast<int>(P.threads));      // -t bounds the ingest workers; default: all cores
@@ -262,7 +353,9 @@ int main(int argc, char **argv) {
     {
       const uint16_t *len16 = nullptr; const uint64_t *run_ab = nullptr; const uint32_t *run_start = nullptr;
       const uint32_t runs = swbh_db_compact(db, &len16, &run_ab, &run_start);
-      if (runs != 0) engine_check(swb200_load_db_compact(ctx, swbh_db_words(db), swbh_db_stride_words(db), len16, run_ab, run_start, runs, n));
+      if (ctxs.size() > 1 && runs != 0 && n >= 8192u * ctxs.size() && swbh_db_longest(db) < 8192) {
+        // multi-GPU job: every rank uploads its own rows (cluster_d1_multi)
+      } else if (runs != 0) engine_check(swb200_load_db_compact(ctx, swbh_db_words(db), swbh_db_stride_words(db), len16, run_ab, run_start, runs, n));
       else engine_check(swb200_load_db(ctx, swbh_db_words(db), swbh_db_stride_words(db), swbh_db_lengths(db), swbh_db_abundances(db), n));
     }
     if (P.differences == 0) {                                  // dereplicate, src/derep.cc:393-418
@@ -270,7 +363,7 @@ int main(int argc, char **argv) {
       std::vector<uint64_t> mass(n);
       uint64_t clusters = 0;
       engine_check(swb200_d0_dereplicate(ctx, rep.data(), mass.data(), size.data(), singles.data(), &clusters));
-      swb200_destroy(ctx);
+      for (swb200_ctx *c : ctxs) swb200_destroy(c);
       swbh_derep *dr = nullptr;
       if (swbh_d0_assemble(db, rep.data(), mass.data(), size.data(), singles.data(), &dr) != 0) fatal(swbh_last_error());
       if (swbh_d0_write_swarms(db, dr, P.mothur, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
@@ -288,7 +381,25 @@ int main(int argc, char **argv) {
       return EXIT_SUCCESS;
     }
     std::vector<uint32_t> swarm_of(n), generation(n), parent(n), extra(n, SWB200_NONE);
-    if (P.differences == 1) {
+    const uint16_t *len16m = nullptr; const uint64_t *run_abm = nullptr; const uint32_t *run_startm = nullptr;
+    const uint32_t runs_m = ctxs.size() > 1 ? swbh_db_compact(db, &len16m, &run_abm, &run_startm) : 0;
+    if (ctxs.size() > 1 && runs_m != 0 && n >= 8192u * ctxs.size() && swbh_db_longest(db) < 8192) {
+      std::vector<uint32_t> links;
+      cluster_d1_multi(ctxs, db, P.ncb, run_startm, runs_m, swarm_of, generation, parent, netf ? &links : nullptr);
+      if (netf) {                                              // -j: CSR of the union of the ranks' links, rows ascending (src/algod1.cc:755-788)
+        std::vector<uint64_t> row_ptr(static_cast<size_t>(n) + 1, 0);
+        const uint64_t m = links.size() / 2;
+        for (uint64_t e = 0; e < m; ++e) row_ptr[links[2 * e] + 1]++;
+        for (uint32_t i = 0; i < n; ++i) row_ptr[i + 1] += row_ptr[i];
+        std::vector<uint32_t> col(m ? m : 1);
+        std::vector<uint64_t> cur(row_ptr.begin(), row_ptr.end() - 1);
+        for (uint64_t e = 0; e < m; ++e) col[cur[links[2 * e]]++] = links[2 * e + 1];
+        for (uint32_t i = 0; i < n; ++i) std::sort(col.begin() + static_cast<int64_t>(row_ptr[i]), col.begin() + static_cast<int64_t>(row_ptr[i + 1]));
+        if (swbh_write_network(db, row_ptr.data(), col.data(), P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
+        write_all(netf, text, len);
+      }
+      if (swbh_d1_assemble(db, swarm_of.data(), generation.data(), parent.data(), nullptr, static_cast<uint64_t>(P.boundary), &res) != 0) fatal(swbh_last_error());
+    } else if (P.differences == 1) {
       engine_check(swb200_d1_index(ctx));
       uint64_t links = 0;
       engine_check(swb200_d1_network(ctx, P.ncb ? 1 : 0, &links));
@@ -313,7 +424,7 @@ int main(int argc, char **argv) {
                                      parent.data(), extra.data()));
       if (swbh_dn_assemble(db, swarm_of.data(), generation.data(), parent.data(), extra.data(), &res) != 0) fatal(swbh_last_error());
     }
-    swb200_destroy(ctx);
+    for (swb200_ctx *c : ctxs) swb200_destroy(c);
     if (swbh_write_swarms(db, res, P.mothur, P.differences, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
     write_all(out, text, len);
     if (seedsf) { if (swbh_write_seeds(db, res, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); }
@@ -337,7 +448,7 @@ int main(int argc, char **argv) {
                  P.differences == 1 ? swbh_result_maxgen(res) : std::max(1u, swbh_result_maxgen(res)));
     swbh_result_free(res);
   } else {                                                     // empty input: the reference still reports (and the mothur line is written)
-    if (ctx) swb200_destroy(ctx);
+    for (swb200_ctx *c : ctxs) if (c) swb200_destroy(c);
     if (P.mothur && P.differences < 2) std::fprintf(out, "swarm_%" PRId64 "\t0\n", P.differences);   // src/algo.cc writes nothing
     std::fprintf(logf, "\nNumber of swarms:  0\nLargest swarm:     0\n%s0\n", P.differences == 0 ? "Heaviest swarm:    " : "Max generations:   ");
   }

@@ -118,3 +118,27 @@ def test_cli_duplicate_sequences_message(built, tmp_path):
         ref = subprocess.run([str(helpers.REF_BIN), "-o", os.devnull, str(fa)], capture_output=True)
         assert ref.returncode == 1
         assert mine.stderr[mine.stderr.index(b"\nError:"):] == ref.stderr[ref.stderr.index(b"\nError:"):]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0"])
+def test_cli_multi_gpu_job_on_shared_device(built, tmp_path, devices):
+    """SWARM_B200_DEVICES: ONE d=1 job on several ranks driven by the command line itself (C++ host: one thread per rank,
+    peer buffers + peer access set up by swb200_dist_setup_local).  Here the ranks share cuda:0 — the code path of a
+    multi-GPU box, runnable where there is one GPU.  -o -s -i -j must be byte-identical to the single-rank run and to the
+    reference binary."""
+    fa = helpers.make_fasta(tmp_path / "m.fa", 90000, 150, 71, 0)
+    outs = {}
+    for tag, env in (("one", {}), ("multi", {"SWARM_B200_DEVICES": devices})):
+        d = tmp_path / tag
+        d.mkdir()
+        cmd = [str(CLI), "-l", str(d / "log"), "-o", str(d / "o"), "-s", str(d / "s"), "-i", str(d / "i"), "-j", str(d / "j"), str(fa)]
+        p = subprocess.run(cmd, capture_output=True, env=dict(os.environ, **env), timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[tag] = {k: (d / k).read_bytes() for k in "osij"}
+    for k in "osij":
+        assert outs["one"][k] == outs["multi"][k], k
+    if helpers.have_ref():
+        r = helpers.run_ref(fa, outputs=("o", "s", "i", "j"), threads=4)
+        for k in "osij":
+            assert outs["multi"][k] == r[k], k
