@@ -409,14 +409,16 @@ def main():
     avg = {p: sum(v) / len(v) for p, v in phase.items()}
     if d == 1:
         e_ = m_links
+        rows_ = st["rows_gathered"]
         ph = {
-            "index": {"kernel": "k_ts_scatter", "s": avg[1], "bytes": n * (P_ + 12) + 2 * n * (8 + P_),
-                      "formula": "per amplicon: packed row + length + abundance read, two fat records (8-byte entry + row) written"},
-            "network": {"kernel": "k_ts_join (+ k_ts_big, idle on this data)", "s": avg[2], "bytes": 2 * n * (8 + P_) + 8 * e_,
-                        "formula": "every tile record (entry + row) read once by TMA, links written"},
-            "cluster": {"kernel": "k_cluster_frontier", "s": avg[3], "bytes": n * 32 + e_ * 36, "rounds": st["cluster_rounds"],
-                        "formula": "per amplicon: key/degree/parent initialised, key read + label/generation written; per link: list read, "
-                                   "row slot written, key relaxed, parent pass (row + key read, parent written); frontier traffic of the later rounds not counted"},
+            "index": {"kernel": "k_ts_scatter", "s": avg[1], "bytes": n * (P_ + 12) + 2 * n * 8,
+                      "formula": "per amplicon: packed row + length + abundance read (one TMA-staged pass), two 8-byte tile entries written"},
+            "network": {"kernel": "k_ts_join (+ k_ts_big, idle on this data)", "s": avg[2], "bytes": 2 * n * 8 + rows_ * P_ + 8 * e_,
+                        "formula": "every tile entry read once by TMA, one packed row per entry that has a bucket mate (counted), links written",
+                        "rows_gathered_per_amplicon": rows_ / n},
+            "cluster": {"kernel": "k_cluster_persistent", "s": avg[3], "bytes": n * 28 + st["cluster_rounds"] * 8 * e_ + 24 * e_, "rounds": st["cluster_rounds"],
+                        "formula": "key + parent initialised, label + generation written, the 8-byte link list re-read every round, parent pass (link + two keys); "
+                                   "relaxation traffic (two random keys per ACTIVE link) not counted: a lower bound"},
         }
         if args.join_kernel != 0 or args.enum_mode != 2 or args.cluster_kernel != 0:
             for k in ph:

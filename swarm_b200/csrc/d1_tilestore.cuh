@@ -32,8 +32,6 @@
 namespace swb {
 
 constexpr uint32_t kTsBuckets = 1024;     // hash-chain heads per tile
-constexpr uint32_t kTsQueue = 1536;       // pairs queued per pass of the join
-constexpr uint32_t kTsOut = 512;          // links staged per tile before one global atomicAdd
 constexpr uint32_t kTsNil = 0xFFFFu;
 constexpr uint32_t kTsRows = 256;         // rows one CTA of the scatter pass stages
 
@@ -50,6 +48,7 @@ struct TileStoreParams {
   uint64_t kmask0, kmask1;          // the first K nucleotides of a packed row: masks of words 0 and 1
   int sorted_desc, ncb;
   uint32_t n_tiles, t_lo, t_hi;     // global tile count; this context's tiles
+  uint32_t q_cap, out_cap;          // join: pairs queued per pass, links staged per tile before one global atomicAdd
   uint32_t cap, rec_words;          // records per tile slot; words per record: 1 + stride (FAT: entry + packed row) or 1 (slim: the
                                     // join gathers the rows it needs from `words`, which must then hold every amplicon)
   unsigned long long *store;        // (t_hi - t_lo) * cap * rec_words
@@ -217,6 +216,7 @@ __device__ __forceinline__ int ts_classify_eq(const uint64_t *x, const uint64_t 
 
 // warp-collective: lanes contribute nl (0..2) links; staged in the tile's shared-memory buffer, spilled to the global list
 __device__ __forceinline__ void ts_stage_links(const TileStoreParams &J, uint2 *out, uint32_t *out_n, uint32_t nl, uint2 l0, uint2 l1, uint32_t lane) {
+  const uint32_t kTsOut = J.out_cap;
   const uint32_t b1 = __ballot_sync(kFull, nl >= 1), b2 = __ballot_sync(kFull, nl >= 2);
   const uint32_t tot = __popc(b1) + __popc(b2);
   if (tot == 0) return;
@@ -256,8 +256,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //      one shared-memory atomic per warp; a full queue suspends the enumeration until its pairs have been decided;
 //  (5) the pairs are decided converged, one per thread: differing-word count then one popcount for equal lengths, the
 //      shifted comparison for lengths one apart (the lane-parallel check_variant, src/variants.cc:118-165).
-template <bool FAT, bool STATS>
-__global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
+template <bool FAT, bool STATS, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_ts_join(TileStoreParams J) {
   extern __shared__ __align__(128) unsigned char ts_smem[];
   const uint32_t rw = J.rec_words, stride = J.stride;
   unsigned long long *recs = reinterpret_cast<unsigned long long *>(ts_smem);          // cap * rec_words
@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(256, 4) k_ts_join(TileStoreParams J) {
   uint32_t *boff = reinterpret_cast<uint32_t *>(rows + (FAT ? 0 : static_cast<size_t>(J.cap) * stride));   // kTsBuckets + 2
   uint32_t *sdesc = boff + kTsBuckets + 2;                                              // cap descriptors, by sorted position
   uint32_t *queue = sdesc + J.cap;                                                      // kTsQueue pairs: s | q << 16 (sorted positions)
+  const uint32_t kTsQueue = J.q_cap, kTsOut = J.out_cap;
   uint2 *out = reinterpret_cast<uint2 *>(queue + kTsQueue);                             // kTsOut links
   uint16_t *order = reinterpret_cast<uint16_t *>(out + kTsOut);                         // cap: record index of every sorted position
   __shared__ uint64_t bar;

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace swb;
@@ -162,6 +163,8 @@ struct swb200_ctx {
   bool tile_active = false;
   // tile store (d1_tilestore.cuh): fat records in fixed-capacity tile slots
   bool ts_active = false;
+  uint32_t ts_qcap = 1536, ts_outcap = 512;
+  int ts_occ = 4, ts_occ_opt = 0;    // CTAs of the join per SM (register bound of the kernel variant): 4, 5 or 6
   uint32_t ts_cap_opt = 0;           // tuning: records per tile slot (0 = derived from the record size)
   int ts_fat = 0;                    // 1: records carry their packed row (the sharded-database multi-GPU layout); 0: 8-byte entries, rows gathered
   DevBuf<unsigned long long> ts_store, ts_ovf;
@@ -338,6 +341,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "job_min_len" && v >= 0 && v < (1ll << 32)) c->job_min_len = static_cast<uint32_t>(v);
   else if (k == "job_max_len" && v >= 0 && v < (1ll << 32)) c->job_max_len = static_cast<uint32_t>(v);
   else if (k == "tile_cap" && v >= 0 && v <= 768) c->ts_cap_opt = static_cast<uint32_t>(v);
+  else if (k == "join_occupancy" && (v == 0 || (v >= 4 && v <= 6))) c->ts_occ_opt = static_cast<int>(v);
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
@@ -589,6 +593,7 @@ static TileStoreParams ts_params(swb200_ctx *c) {
   J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0; J.ncb = c->ncb;
   J.n_tiles = c->ts_tiles; J.t_lo = c->ts_lo; J.t_hi = c->ts_hi;
   J.cap = c->ts_cap; J.rec_words = c->ts_fat ? c->stride + 1 : 1;
+  J.q_cap = c->ts_qcap; J.out_cap = c->ts_outcap;
   J.store = c->ts_store.p; J.cursor = c->ts_cursor.p; J.ovf_head = c->ts_cursor.p + (c->ts_hi - c->ts_lo);
   J.ovf = c->ts_ovf.p; J.ovf_count = c->counters.p + 32; J.ovf_cap = c->ts_ovf_cap;
   J.ovf_abort = reinterpret_cast<uint32_t *>(c->counters.p + 34);
@@ -621,7 +626,19 @@ static uint32_t ts_prepare(swb200_ctx *c) {
   c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * own_rank, c->ts_tiles));
   c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
   const uint32_t T = c->ts_hi - c->ts_lo;
-  c->ts_smem = static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + static_cast<size_t>(cap) * 4 + kTsQueue * 4 + kTsOut * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
+  // occupancy of the join: the kernel is bound by instruction issue and by shared-memory latency, so more resident warps pay;
+  // 4 CTAs/SM leave 64 registers per thread, 6 leave 40 (ptxas: no spills at 5, 4 bytes at 6) when the tile fits 1/6 of the SM
+  auto smem_for = [&](uint32_t q, uint32_t o) {
+    return static_cast<size_t>(cap) * rec_bytes + (kTsBuckets + 2) * 4 + static_cast<size_t>(cap) * 4 + q * 4 + o * 8 + ((static_cast<size_t>(cap) * 2 + 15) & ~size_t(15));
+  };
+  const size_t sm_bytes = 233472;
+  c->ts_occ = 4; c->ts_qcap = 1536; c->ts_outcap = 512;
+  for (int occ = 6; occ > 4; --occ) {
+    if (c->ts_occ_opt && occ > c->ts_occ_opt) continue;
+    if ((smem_for(1024, 256) + 1024 + 256) * occ <= sm_bytes) { c->ts_occ = occ; c->ts_qcap = 1024; c->ts_outcap = 256; break; }
+  }
+  if (c->ts_occ_opt == 4) { c->ts_occ = 4; c->ts_qcap = 1536; c->ts_outcap = 512; }
+  c->ts_smem = smem_for(c->ts_qcap, c->ts_outcap);
   c->ts_store.alloc(std::max<uint64_t>(static_cast<uint64_t>(T) * cap * rw, 2) + 2);
   c->ts_cursor.alloc(static_cast<size_t>(T) * 2 + 2);
   if (c->ts_ovf_cap == 0 || c->tj_cmax_override >= 2)
@@ -883,8 +900,14 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
           join<<<T, 256, c->ts_smem, c->stream>>>(J);
           big<<<c->sm_count * 4, 256, 0, c->stream>>>(J);
         };
-        if (c->ts_fat) { if (c->collect_stats) launch(k_ts_join<true, true>, k_ts_big<true, true>); else launch(k_ts_join<true, false>, k_ts_big<true, false>); }
-        else { if (c->collect_stats) launch(k_ts_join<false, true>, k_ts_big<false, true>); else launch(k_ts_join<false, false>, k_ts_big<false, false>); }
+        auto pick = [&](auto occ) {
+          constexpr int O = decltype(occ)::value;
+          if (c->ts_fat) { if (c->collect_stats) launch(k_ts_join<true, true, O>, k_ts_big<true, true>); else launch(k_ts_join<true, false, O>, k_ts_big<true, false>); }
+          else { if (c->collect_stats) launch(k_ts_join<false, true, O>, k_ts_big<false, true>); else launch(k_ts_join<false, false, O>, k_ts_big<false, false>); }
+        };
+        if (c->ts_occ >= 6) pick(std::integral_constant<int, 6>{});
+        else if (c->ts_occ == 5) pick(std::integral_constant<int, 5>{});
+        else pick(std::integral_constant<int, 4>{});
         c->launches += 2;
         CK(cudaGetLastError());
       }
@@ -1328,8 +1351,12 @@ int swb200_d1_reserve(swb200_ctx *c) {
   const void *kernels[] = {reinterpret_cast<const void *>(k_ts_wait), reinterpret_cast<const void *>(k_ts_route<true>),
                            reinterpret_cast<const void *>(k_ts_route<false>), reinterpret_cast<const void *>(k_ts_scatter_inbox<true>),
                            reinterpret_cast<const void *>(k_ts_scatter_inbox<false>), reinterpret_cast<const void *>(k_ts_scatter),
-                           reinterpret_cast<const void *>(k_ts_join<true, true>), reinterpret_cast<const void *>(k_ts_join<true, false>),
-                           reinterpret_cast<const void *>(k_ts_join<false, true>), reinterpret_cast<const void *>(k_ts_join<false, false>),
+                           reinterpret_cast<const void *>(k_ts_join<true, true, 4>), reinterpret_cast<const void *>(k_ts_join<true, false, 4>),
+                           reinterpret_cast<const void *>(k_ts_join<false, true, 4>), reinterpret_cast<const void *>(k_ts_join<false, false, 4>),
+                           reinterpret_cast<const void *>(k_ts_join<true, true, 5>), reinterpret_cast<const void *>(k_ts_join<true, false, 5>),
+                           reinterpret_cast<const void *>(k_ts_join<false, true, 5>), reinterpret_cast<const void *>(k_ts_join<false, false, 5>),
+                           reinterpret_cast<const void *>(k_ts_join<true, true, 6>), reinterpret_cast<const void *>(k_ts_join<true, false, 6>),
+                           reinterpret_cast<const void *>(k_ts_join<false, true, 6>), reinterpret_cast<const void *>(k_ts_join<false, false, 6>),
                            reinterpret_cast<const void *>(k_ts_big<true, true>), reinterpret_cast<const void *>(k_ts_big<true, false>),
                            reinterpret_cast<const void *>(k_ts_big<false, true>), reinterpret_cast<const void *>(k_ts_big<false, false>),
                            reinterpret_cast<const void *>(k_cluster_dist)};
