@@ -29,6 +29,9 @@ for step in "$@"; do
           python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -45 $O/${TAG}_$k.txt ;;
     san) timeout 900 compute-sanitizer --tool memcheck --print-limit 8 python -m pytest tests -x -q -m gpu -k "$arg" > $O/${TAG}_san.log 2>&1
          grep -E "=========|passed|failed" $O/${TAG}_san.log | head -60 ;;
+    mbench) g=${arg%%:*}; extra=""; [[ "$arg" == *:* ]] && extra=${arg#*:}
+            SWB200_CLUSTER_TS=${TS:-} timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $g $extra > $O/${TAG}_mbench_$g.json 2> $O/${TAG}_mbench_$g.err
+            echo "== mbench $g rc=$?"; tail -c 3000 $O/${TAG}_mbench_$g.json; grep -E "cluster_dist rank 0|Error|error" $O/${TAG}_mbench_$g.err | tail -5 ;;
     sanitize) bash scripts/gpu_sanitize.sh ;;
     *) echo "unknown step $step" ;;
   esac

@@ -612,10 +612,10 @@ static TileStoreParams ts_params(swb200_ctx *c) {
 static uint32_t ts_prepare(swb200_ctx *c) {
   const uint32_t rw = c->ts_fat ? c->stride + 1 : 1;
   const uint32_t rec_bytes = 8 * (c->stride + 1);                // shared memory per record either way: entry + row
-  uint32_t cap = std::min<uint32_t>(768, (36u * 1024u) / rec_bytes) & ~1u;
+  uint32_t cap = std::min<uint32_t>(512, (36u * 1024u) / rec_bytes) & ~1u;      // 512 x 48 B: five CTAs of the join per SM (measured best, profiles/r2h)
   cap = std::max<uint32_t>(cap, 64);
   if (c->ts_cap_opt >= 64) cap = std::min(cap, c->ts_cap_opt & ~1u);
-  const uint32_t fill = cap * 2 / 3;                       // mean records per tile: Poisson(512) never reaches 768
+  const uint32_t fill = cap * 2 / 3;                       // mean records per tile; the slack absorbs the tail, the rest overflows (k_ts_big)
   const uint64_t want_tiles = (static_cast<uint64_t>(c->n) * 2 + fill - 1) / fill;
   c->ts_tiles = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(want_tiles, 0x7FFFFFFFull)));
   if (c->tj_cmax_override >= 2) cap = std::max<uint32_t>(2, std::min(cap, c->tj_cmax_override) & ~1u);
