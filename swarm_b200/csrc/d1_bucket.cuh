@@ -1,0 +1,351 @@
+// swarm_b200/csrc/d1_bucket.cuh — "Clustering" (src/algod1.cc:1185-1280, process_seed :673-718) with the links BUCKETED BY
+// SOURCE BLOCK: one kernel for one GPU (world = 1) and for the multi-GPU job (the exchange over NVLink peer memory of
+// d1_dist.cuh: same inboxes, same message records, same cross-GPU barrier).
+//
+// Closed form: key[v] = swarm << 32 | generation = min over links u -> v of key[u] + 1 to the fixed point;
+// parent[v] = min { u : u -> v, key[u] + 1 == key[v] }.  What r1's kernels (k_cluster_persistent, k_cluster_dist) paid for,
+// per ncu and per the %globaltimer stamps of profiles/r2i_*: every one of the ~15 rounds walked ALL links and tested one bit of a
+// "lowered last round" bitmap per link at a random address — a 44 us floor per round however few amplicons were still moving
+// (0.6 of 1.1 ms on one GPU, 1.6 of 2.5 ms in the multi-GPU kernel, whose per-chunk staging ran even for idle chunks) — and every
+// ACTIVE link read key[src] at a random address.  Here, once, the links are counting-sorted by the 4096-id block of their
+// source (a count pass of fire-and-forget atomics, one scan, one scatter pass: ~2 400 buckets at 10 M amplicons); then
+//   * a round walks the bucketed list in units of 2 048 links and SKIPS every unit whose source blocks had no amplicon lowered
+//     in the previous round (one flag byte per block): late rounds touch a few units instead of 70 MB;
+//   * inside a unit the sources span one block (or a few): their bitmap words (512 B) and keys (32 KB) are L1-resident, so only
+//     key[dst] is a random access;
+//   * round 0 is fused into the scatter pass (every key still has its initial value src << 32: no load);
+//   * multi-GPU: a remote destination becomes a 16-byte record in the owner's message log, appended per WARP — one ballot per
+//     destination rank, one atomicAdd issued by `world` lanes at once on the sender's LOCAL counters, consecutive slots for the
+//     lanes of a run — instead of r1's per-chunk counting sort in shared memory with three CTA barriers.
+// Ownership is block-cyclic (blocks of kDistBlock = 4096 ids), so "source block" = ownership block: a bucket never mixes owners.
+#pragma once
+#include "d1_dist.cuh"
+
+namespace swb {
+
+constexpr uint32_t kBkUnit = 2048;                // links per work unit of a round (256 threads x 8)
+
+struct BucketParams {
+  DistParams D;                                   // rank, world, n, n_local, edges, m_local, key, parent, label, generation, bits, nwords, peers ...
+  uint32_t nblk;                                  // owned blocks = n_local / kDistBlock
+  uint8_t *bflag;                                 // 3 x nblk rotating flags: some amplicon of the block was lowered (read / set / clear)
+  uint32_t *bcount;                               // nblk: links per source block, then the scatter cursors
+  unsigned long long *boff;                       // nblk + 1: first bucketed link of every block
+  uint2 *blinks;                                  // the links, bucketed by source block
+  uint64_t blinks_cap;
+};
+
+// position of the first block whose links start after link p (boff is non-decreasing): block of link p
+__device__ __forceinline__ uint32_t bk_block_of(const BucketParams &B, unsigned long long p) {
+  uint32_t lo = 0, hi = B.nblk;                   // last b with boff[b] <= p
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (B.boff[mid] <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// offer cand to the owned amplicon with local index lv; a lowered key marks it (and its block) for the next round
+__device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *wr, uint8_t *fwr, uint32_t lv, unsigned long long cand) {
+  if (cand < B.D.key[lv] && atomicMin(&B.D.key[lv], cand) > cand) {
+    atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
+    fwr[lv / kDistBlock] = 1;
+    return true;
+  }
+  return false;
+}
+
+// warp-collective: lanes with `remote` append (v, u, cand) to the message log of owner[lane] on that rank.  One ballot per
+// destination rank; the `world` reservations are issued together by the first `world` lanes on the sender's local counters.
+__device__ __forceinline__ void bk_send(const BucketParams &B, unsigned long long *counters, bool remote, uint32_t owner, uint32_t v, uint32_t u,
+                                        unsigned long long cand, uint32_t lane) {
+  const DistParams &D = B.D;
+  uint32_t my_mask = 0, lane_mask = 0;
+  for (uint32_t d = 0; d < D.world; ++d) {
+    const uint32_t m = __ballot_sync(kFull, remote && owner == d);
+    if (lane == d) lane_mask = m;
+    if (remote && owner == d) my_mask = m;
+  }
+  unsigned long long base = 0;
+  if (lane < D.world && lane_mask) base = atomicAdd(&counters[lane], static_cast<unsigned long long>(__popc(lane_mask)));
+  const unsigned long long b = shfl_u64(base, remote ? static_cast<int>(owner) : 0);
+  if (remote) {
+    const unsigned long long slot = b + __popc(my_mask & ((1u << lane) - 1u));
+    if (slot >= D.cap_upd) dist_ctl(D, D.rank)->overflow = 1u;
+    else if (!(D.dbg & 1u)) {
+      uint4 rec;
+      rec.x = v; rec.y = u; rec.z = static_cast<uint32_t>(cand); rec.w = static_cast<uint32_t>(cand >> 32);
+      *reinterpret_cast<uint4 *>(dist_upd(D, owner, D.rank) + slot) = rec;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
+  const DistParams &D = B.D;
+  const SwGrid grid{D.gbar};
+  __shared__ DistSmem sm;
+  __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
+  __shared__ unsigned long long s_prev[kDistMaxWorld], s_cur[kDistMaxWorld];
+  __shared__ unsigned long long scan_part[256];
+  __shared__ uint32_t s_b0, s_b1;
+  extern __shared__ __align__(16) unsigned char dist_dyn[];      // kDistChunk * 16 bytes: staging of the link routing
+  const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  volatile uint32_t *lflags = D.lflags;
+  DistCtl *me = dist_ctl(D, D.rank);
+  const bool multi = D.world > 1;
+  unsigned long long epoch = D.epoch_base;
+  uint32_t tslot = 0;
+  dist_stamp(D, tid, tslot);
+
+  // ---- init (local); multi-GPU: route the links this rank's join found to the owners of their sources
+  for (uint64_t l = tid; l < D.n_local; l += nth) {
+    const uint32_t v = dist_global(D, static_cast<uint32_t>(l));
+    D.key[l] = static_cast<unsigned long long>(v) << 32;
+    if (v < D.n) D.parent[v] = kNone;
+  }
+  for (uint64_t w = tid; w < 3ull * D.nwords; w += nth) D.bits[w] = 0;
+  for (uint64_t w = tid; w < 3ull * B.nblk; w += nth) B.bflag[w] = 0;
+  for (uint64_t w = tid; w < B.nblk; w += nth) B.bcount[w] = 0;
+  if (tid == 0) { lflags[0] = 0; lflags[1] = 0; lflags[2] = 0; lflags[3] = 0; }
+  if (multi) {
+    uint2 *sorted = reinterpret_cast<uint2 *>(dist_dyn);
+    for (uint64_t base = static_cast<uint64_t>(blockIdx.x) * kDistChunk; base < D.m_local; base += static_cast<uint64_t>(gridDim.x) * kDistChunk) {
+      uint2 item[kDistU];
+      uint32_t owner[kDistU];
+#pragma unroll
+      for (int k = 0; k < kDistU; ++k) {
+        const uint64_t i = base + static_cast<uint64_t>(k) * blockDim.x + threadIdx.x;
+        if (i < D.m_local) { item[k] = D.edges[i]; owner[k] = dist_owner(D, item[k].x); }
+        else { item[k] = make_uint2(0, 0); owner[k] = kNone; }
+      }
+      dist_scatter<uint2>(D, sm, sorted, item, owner, [&](uint32_t o) { return dist_links(D, o, D.rank); }, D.lcnt, D.cap_links);
+    }
+    __threadfence_system();
+    dist_barrier(D, grid, ++epoch, lflags + 0, D.lcnt, offsetof(DistCtl, links_cnt));
+  } else {
+    grid.sync();
+  }
+  dist_stamp(D, tid, tslot);                                      // init + route + barrier
+  // the links whose source this rank owns: the sender sub-regions of my inbox (multi) or the join's own list
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (uint32_t s = 0; s < D.world; ++s) {
+      s_pref[s] = run;
+      run += multi ? min(static_cast<unsigned long long>(D.cap_links), *reinterpret_cast<volatile unsigned long long *>(&me->links_cnt[s]))
+                   : static_cast<unsigned long long>(D.m_local);
+    }
+    s_pref[D.world] = run;
+  }
+  if (threadIdx.x < kDistMaxWorld) { s_prev[threadIdx.x] = 0; s_cur[threadIdx.x] = 0; }
+  __syncthreads();
+  const uint64_t m = min(s_pref[D.world], static_cast<unsigned long long>(B.blinks_cap));
+  auto link_at = [&](uint64_t i) -> uint2 {
+    if (!multi) return __ldcs(&D.edges[i]);
+    uint32_t s = 0;
+    while (i >= s_pref[s + 1]) ++s;
+    return __ldcg(&dist_links(D, D.rank, s)[i - s_pref[s]]);
+  };
+
+  // ---- bucket the links by the block of their source: count, scan, scatter (+ round 0)
+  for (uint64_t i = tid; i < m; i += nth) atomicAdd(&B.bcount[dist_local(D, link_at(i).x) / kDistBlock], 1u);
+  grid.sync();
+  if (blockIdx.x == 0) {                                           // exclusive scan of nblk counts by one CTA
+    const uint32_t per = (B.nblk + 255u) / 256u;
+    const uint32_t b0 = min(B.nblk, threadIdx.x * per), b1 = min(B.nblk, b0 + per);
+    unsigned long long s = 0;
+    for (uint32_t b = b0; b < b1; ++b) s += B.bcount[b];
+    scan_part[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t off = 1; off < 256; off <<= 1) {
+      const unsigned long long v = threadIdx.x >= off ? scan_part[threadIdx.x - off] : 0ull;
+      __syncthreads();
+      scan_part[threadIdx.x] += v;
+      __syncthreads();
+    }
+    unsigned long long run = scan_part[threadIdx.x] - s;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const uint32_t c = B.bcount[b];
+      B.boff[b] = run;
+      B.bcount[b] = 0;                                              // becomes the scatter cursor
+      run += c;
+    }
+    if (threadIdx.x == 255) B.boff[B.nblk] = scan_part[255];
+  }
+  grid.sync();
+  dist_stamp(D, tid, tslot);                                      // count + scan
+  unsigned long long *counters = D.lcnt + kDistMaxWorld;
+  {
+    uint32_t *wr = D.bits + D.nwords;                               // round 1 reads bitmap 1 / flags 1
+    uint8_t *fwr = B.bflag + B.nblk;
+    int ch = 0;
+    const uint64_t m_round = (m + 31u) & ~31ull;                    // whole warps: bk_send is warp-collective
+    for (uint64_t i = tid; i < m_round; i += nth) {
+      const bool in = i < m;
+      uint2 ed = in ? link_at(i) : make_uint2(0u, 0u);
+      bool remote = false;
+      uint32_t o = 0;
+      const unsigned long long cand = (static_cast<unsigned long long>(ed.x) << 32) + 1ull;   // key[src] is still src << 32
+      if (in) {
+        const uint32_t b = dist_local(D, ed.x) / kDistBlock;
+        B.blinks[B.boff[b] + atomicAdd(&B.bcount[b], 1u)] = ed;
+        o = multi ? dist_owner(D, ed.y) : D.rank;
+        if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed.y), cand) ? 1 : 0;
+        else remote = true;
+      }
+      if (multi) {
+        if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed.y, ed.x, cand, lane); ch = 1; }
+      }
+    }
+    if (__syncthreads_or(ch) && threadIdx.x == 0) lflags[0] = 1;
+  }
+
+  // ---- rounds
+  uint32_t round = 0;
+  for (;; ++round) {
+    uint32_t *wr = D.bits + static_cast<size_t>((round + 1) % 3) * D.nwords;
+    uint8_t *fwr = B.bflag + static_cast<size_t>((round + 1) % 3) * B.nblk;
+    if (round) {
+      const uint32_t *rd = D.bits + static_cast<size_t>(round % 3) * D.nwords;
+      const uint8_t *frd = B.bflag + static_cast<size_t>(round % 3) * B.nblk;
+      uint32_t *cl = D.bits + static_cast<size_t>((round + 2) % 3) * D.nwords;
+      uint8_t *fcl = B.bflag + static_cast<size_t>((round + 2) % 3) * B.nblk;
+      if (tid == 0) lflags[(round + 1) % 3] = 0;
+      for (uint64_t w = tid; w < D.nwords; w += nth) cl[w] = 0;
+      for (uint64_t w = tid; w < B.nblk; w += nth) fcl[w] = 0;
+      int ch = 0;
+      const uint64_t n_units = (m + kBkUnit - 1) / kBkUnit;
+      for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const unsigned long long p0 = unit * kBkUnit, p1 = min(static_cast<unsigned long long>(m), p0 + kBkUnit);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_b0 = bk_block_of(B, p0); s_b1 = bk_block_of(B, p1 - 1); }
+        __syncthreads();
+        const uint32_t b0 = s_b0, b1 = s_b1;
+        int act = 0;
+        for (uint32_t b = b0 + threadIdx.x; b <= b1; b += 256) act |= frd[b];
+        if (!__syncthreads_or(act)) continue;                        // nothing lowered among this unit's sources last round
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
+          const unsigned long long p = p0 + static_cast<unsigned long long>(k) * 256 + threadIdx.x;
+          const bool in = p < p1;
+          const uint2 ed = in ? B.blinks[p] : make_uint2(0u, 0u);
+          const uint32_t lu = in ? dist_local(D, ed.x) : 0u;
+          const bool active = in && ((rd[lu >> 5] >> (lu & 31u)) & 1u);
+          bool remote = false;
+          uint32_t o = 0;
+          unsigned long long cand = 0;
+          if (active) {
+            cand = D.key[lu] + 1ull;
+            o = multi ? dist_owner(D, ed.y) : D.rank;
+            if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed.y), cand) ? 1 : 0;
+            else remote = true;
+          }
+          if (multi) {
+            if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed.y, ed.x, cand, lane); ch = 1; }
+          }
+        }
+      }
+      if (__syncthreads_or(ch) && threadIdx.x == 0) lflags[round % 3] = 1;
+    }
+    if (multi) __threadfence_system();                              // peer writes of this thread are visible system-wide before it arrives
+    uint32_t busy;
+    if (multi) busy = dist_barrier(D, grid, ++epoch, lflags + (round % 3), counters, offsetof(DistCtl, upd_cnt));
+    else { grid.sync(); busy = lflags[round % 3]; }
+    dist_stamp(D, tid, tslot);                                      // relax (+ barrier)
+    if (!busy || lflags[3]) break;
+    if (multi) {
+      // apply what arrived in this round, one sub-region per sender
+      if (threadIdx.x < D.world) {
+        s_prev[threadIdx.x] = s_cur[threadIdx.x];
+        s_cur[threadIdx.x] = min(static_cast<unsigned long long>(D.cap_upd), *reinterpret_cast<volatile unsigned long long *>(&me->upd_cnt[threadIdx.x]));
+      }
+      __syncthreads();
+      for (uint32_t s = 0; s < D.world; ++s) {
+        if (s == D.rank) continue;
+        const DistRec *in = dist_upd(D, D.rank, s);
+        for (uint64_t base = s_prev[s] + tid; base < s_cur[s]; base += nth * 4) {
+          uint4 raw[4];
+          unsigned long long kv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t i = base + static_cast<uint64_t>(k) * nth;
+            raw[k] = i < s_cur[s] ? __ldcg(reinterpret_cast<const uint4 *>(in + i)) : make_uint4(kNone, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kv[k] = raw[k].x != kNone ? D.key[dist_local(D, raw[k].x)] : 0ull;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (raw[k].x == kNone) continue;
+            const uint32_t lv = dist_local(D, raw[k].x);
+            const unsigned long long cand = (static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z;
+            if (cand < kv[k] && atomicMin(&D.key[lv], cand) > cand) {
+              atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
+              fwr[lv / kDistBlock] = 1;
+            }
+          }
+        }
+      }
+      grid.sync();
+      dist_stamp(D, tid, tslot);                                    // apply
+    }
+  }
+
+  // ---- parents: smallest u among the in-links that offer exactly the final key — local links, then the message log
+  for (uint64_t base = tid; base < m; base += nth * kDistU) {
+    uint2 ed[kDistU];
+    unsigned long long ku[kDistU], kv[kDistU];
+#pragma unroll
+    for (int k = 0; k < kDistU; ++k) {
+      const uint64_t i = base + static_cast<uint64_t>(k) * nth;
+      ed[k] = i < m ? B.blinks[i] : make_uint2(kNone, kNone);
+      if (multi && ed[k].x != kNone && dist_owner(D, ed[k].y) != D.rank) ed[k].x = kNone;       // remote destination: its owner decides
+    }
+#pragma unroll
+    for (int k = 0; k < kDistU; ++k) {
+      ku[k] = ed[k].x != kNone ? D.key[dist_local(D, ed[k].x)] : 0ull;
+      kv[k] = ed[k].x != kNone ? D.key[dist_local(D, ed[k].y)] : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < kDistU; ++k)
+      if (ed[k].x != kNone && ku[k] + 1ull == kv[k]) atomicMin(&D.parent[ed[k].y], ed[k].x);
+  }
+  if (multi) {
+    for (uint32_t s = 0; s < D.world; ++s) {
+      if (s == D.rank) continue;
+      const DistRec *in = dist_upd(D, D.rank, s);
+      const uint64_t cnt = s_cur[s];
+      for (uint64_t base = tid; base < cnt; base += nth * kDistU) {
+        uint4 raw[kDistU];
+        unsigned long long kv[kDistU];
+#pragma unroll
+        for (int k = 0; k < kDistU; ++k) {
+          const uint64_t i = base + static_cast<uint64_t>(k) * nth;
+          raw[k] = i < cnt ? __ldcg(reinterpret_cast<const uint4 *>(in + i)) : make_uint4(kNone, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < kDistU; ++k) kv[k] = raw[k].x != kNone ? D.key[dist_local(D, raw[k].x)] : 0ull;
+#pragma unroll
+        for (int k = 0; k < kDistU; ++k)
+          if (raw[k].x != kNone && ((static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z) == kv[k]) atomicMin(&D.parent[raw[k].x], raw[k].y);
+      }
+    }
+  }
+  for (uint64_t l = tid; l < D.n_local; l += nth) {
+    const uint32_t v = dist_global(D, static_cast<uint32_t>(l));
+    if (v >= D.n) continue;
+    const unsigned long long kv = D.key[l];
+    D.label[v] = static_cast<uint32_t>(kv >> 32);
+    D.generation[v] = static_cast<uint32_t>(kv);
+  }
+  if (tid == 0) lflags[4] = round + 1;
+  if (multi) {
+    // nobody starts the next call (and appends to an inbox) before every rank has finished reading its own
+    dist_barrier(D, grid, ++epoch, lflags + 3, nullptr, 0);
+    if (tid < 2 * kDistMaxWorld) D.lcnt[tid] = 0;            // this sender's counters restart with the next call
+  }
+  dist_stamp(D, tid, tslot);                                 // parents + unpack (+ last barrier)
+  if (D.ts && tid == 0) D.ts[tslot] = 0;
+}
+
+}  // namespace swb

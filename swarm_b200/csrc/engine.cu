@@ -11,6 +11,7 @@
 #include "d1_tilestore.cuh"
 #include "d1_frontier.cuh"
 #include "d1_tsroute.cuh"
+#include "d1_bucket.cuh"
 #include "d1_cluster.cuh"
 #include "d1_dist.cuh"
 #include "dn_kernels.cuh"
@@ -182,6 +183,11 @@ struct swb200_ctx {
   int dist_grid_div = 1;             // test hook: several ranks share ONE GPU, each persistent kernel takes 1/div of the SMs
   int index_exchange = 1;            // after swb200_dist_setup: hash only this rank's rows, route the records to the tile owners
   unsigned long long idx_epoch = 0;
+  DevBuf<uint8_t> bk_flag;                     // bucketed clustering (d1_bucket.cuh)
+  DevBuf<uint32_t> bk_count;
+  DevBuf<unsigned long long> bk_off;
+  DevBuf<uint2> bk_links;
+  int dist_kernel = 0;                         // 0 = links bucketed by source block (d1_bucket.cuh), 1 = r1's k_cluster_dist
   DevBuf<unsigned char> dist_own;              // peer-visible buffer allocated by swb200_dist_setup_local
   DevBuf<unsigned long long> ts_route_cnt;     // [16] sender counters, then done_ctas[2] + err[2] as 32-bit words
   uint64_t dist_buffer_bytes = 0;
@@ -315,6 +321,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
   c->run_start_d.release(); c->ts_route_cnt.release(); c->dist_own.release();
+  c->bk_flag.release(); c->bk_count.release(); c->bk_off.release(); c->bk_links.release();
   c->ts_store.release(); c->ts_ovf.release(); c->ts_cursor.release(); c->fr_deg.release(); c->fr_adj.release(); c->fr_spill.release();
   c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
@@ -338,6 +345,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "tile_rows" && (v == 0 || v == 1)) c->ts_fat = static_cast<int>(v);
   else if (k == "index_exchange" && (v == 0 || v == 1)) c->index_exchange = static_cast<int>(v);
   else if (k == "dist_grid_div" && v >= 1 && v <= 16) c->dist_grid_div = static_cast<int>(v);
+  else if (k == "dist_kernel" && (v == 0 || v == 1)) c->dist_kernel = static_cast<int>(v);
   else if (k == "job_min_len" && v >= 0 && v < (1ll << 32)) c->job_min_len = static_cast<uint32_t>(v);
   else if (k == "job_max_len" && v >= 0 && v < (1ll << 32)) c->job_max_len = static_cast<uint32_t>(v);
   else if (k == "tile_cap" && v >= 0 && v <= 768) c->ts_cap_opt = static_cast<uint32_t>(v);
@@ -1070,6 +1078,51 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
+  if (c->cluster_kernel == 0) {
+    // links bucketed by source block, one persistent kernel (d1_bucket.cuh), world = 1
+    BucketParams B{};
+    DistParams &D = B.D;
+    D.rank = 0; D.world = 1; D.n = n;
+    D.n_local = static_cast<uint32_t>((static_cast<uint64_t>(n) + kDistBlock - 1) / kDistBlock * kDistBlock);
+    D.edges = c->edges.p; D.m_local = m;
+    c->key.alloc(D.n_local);
+    D.nwords = D.n_local / 32;
+    c->cl_bits.alloc(static_cast<size_t>(D.nwords) * 3);
+    B.nblk = D.n_local / kDistBlock;
+    c->bk_flag.alloc(static_cast<size_t>(B.nblk) * 3 + 16); c->bk_count.alloc(B.nblk + 1); c->bk_off.alloc(static_cast<size_t>(B.nblk) + 2);
+    if (c->bk_links.n < m) c->bk_links.alloc(std::max<uint64_t>(m + m / 8, 1));
+    D.key = c->key.p; D.parent = c->parent.p; D.label = c->label.p; D.generation = c->generation.p; D.bits = c->cl_bits.p;
+    D.lcnt = c->counters.p + 44;                     // unused at world = 1
+    D.epoch_base = 0;
+    D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
+    D.gbar = reinterpret_cast<unsigned int *>(c->counters.p + 42);
+    B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+    if (std::getenv("SWB200_CLUSTER_TS")) {
+      c->cl_ts.alloc(128);
+      CK(cudaMemsetAsync(c->cl_ts.p, 0, 128 * 8, c->stream));
+      D.ts = c->cl_ts.p;
+    }
+    CK(cudaMemsetAsync(c->counters.p + 42, 0, 2 * 8, c->stream));
+    const size_t dyn = static_cast<size_t>(kDistChunk) * sizeof(DistRec);
+    CK(cudaFuncSetAttribute(k_cluster_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_bucket, 256, dyn));
+    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+    void *args[] = {&B};
+    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_bucket), dim3(grid), dim3(256), args, dyn, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(reinterpret_cast<uint32_t *>(c->counters.p + 19), reinterpret_cast<uint32_t *>(c->counters.p + 22) + 4, 4, cudaMemcpyDeviceToDevice, c->stream));   // rounds
+    if (D.ts) {
+      unsigned long long h[128];
+      CK(cudaMemcpyAsync(h, c->cl_ts.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      std::fprintf(stderr, "[cluster_bucket n=%u m=%llu] us (init, count + scan, scatter + round 0, rounds ..., parents + unpack):", n, static_cast<unsigned long long>(m));
+      for (int i = 1; i < 128 && h[i]; ++i) std::fprintf(stderr, " %.1f", (h[i] - h[i - 1]) * 1e-3);
+      std::fprintf(stderr, "\n");
+    }
+    return;
+  }
   if (c->cluster_kernel == 4) {
     // frontier relaxation over 8-slot out-rows, one persistent cooperative kernel (d1_frontier.cuh)
     int occ = 1;
@@ -1139,7 +1192,7 @@ static void run_cluster(swb200_ctx *c) {
     }
     return;
   }
-  if (c->cluster_kernel == 0 || c->cluster_kernel == 5 || c->cluster_kernel == 3) {
+  if (c->cluster_kernel == 5 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
     auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;
@@ -1335,6 +1388,9 @@ static void dist_prepare(swb200_ctx *c) {
   c->cl_bits.alloc(static_cast<size_t>((n_local + 31) / 32) * 3);
   c->cl_ts.alloc(128);
   c->staging(4096);
+  const uint32_t nblk = n_local / kDistBlock;
+  c->bk_flag.alloc(static_cast<size_t>(nblk) * 3 + 16); c->bk_count.alloc(nblk + 1); c->bk_off.alloc(static_cast<size_t>(nblk) + 2);
+  c->bk_links.alloc(std::max<uint64_t>(c->dist_cap * c->dist_world, 1));      // everything the link inboxes can hold
 }
 
 // Allocate, ahead of time, every device buffer the multi-GPU step (d1_index with the index exchange, d1_network,
@@ -1359,7 +1415,7 @@ int swb200_d1_reserve(swb200_ctx *c) {
                            reinterpret_cast<const void *>(k_ts_join<false, true, 6>), reinterpret_cast<const void *>(k_ts_join<false, false, 6>),
                            reinterpret_cast<const void *>(k_ts_big<true, true>), reinterpret_cast<const void *>(k_ts_big<true, false>),
                            reinterpret_cast<const void *>(k_ts_big<false, true>), reinterpret_cast<const void *>(k_ts_big<false, false>),
-                           reinterpret_cast<const void *>(k_cluster_dist)};
+                           reinterpret_cast<const void *>(k_cluster_dist), reinterpret_cast<const void *>(k_cluster_bucket)};
   for (const void *k : kernels) {
     cudaFuncAttributes attr;
     CK(cudaFuncGetAttributes(&attr, k));
@@ -1394,14 +1450,23 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
     D.ts = c->cl_ts.p;
   }
   const size_t dyn = static_cast<size_t>(kDistChunk) * sizeof(DistRec);
-  CK(cudaFuncSetAttribute(k_cluster_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+  BucketParams B{};
+  B.D = D;
+  B.nblk = D.n_local / kDistBlock;
+  B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+  const void *kern = c->dist_kernel == 1 ? reinterpret_cast<const void *>(k_cluster_dist) : reinterpret_cast<const void *>(k_cluster_bucket);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_dist, 256, dyn));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
   const unsigned grid = std::max(1u, static_cast<unsigned>(c->sm_count * std::max(occ, 1)) / static_cast<unsigned>(c->dist_grid_div));
   c->tic();
-  void *args[] = {&D};
-  if (c->dist_grid_div > 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);      // ranks sharing one GPU: cooperative kernels are never co-scheduled
-  else CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_dist), dim3(grid), dim3(256), args, dyn, c->stream));
+  void *args_d[] = {&D}, *args_b[] = {&B};
+  if (c->dist_grid_div > 1) {                       // ranks sharing one GPU: cooperative kernels are never co-scheduled
+    if (c->dist_kernel == 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);
+    else k_cluster_bucket<<<grid, 256, dyn, c->stream>>>(B);
+  } else {
+    CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), c->dist_kernel == 1 ? args_d : args_b, dyn, c->stream));
+  }
   CK(cudaGetLastError());
   c->launches++;
   // read-backs go through PINNED memory: a copy into pageable memory blocks inside the driver until the kernel has finished,
@@ -1418,7 +1483,7 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
     unsigned long long t[128];
     CK(cudaMemcpy(t, c->cl_ts.p, sizeof t, cudaMemcpyDeviceToHost));
     std::string line = "[cluster_dist rank " + std::to_string(D.rank) + " rounds " + std::to_string(h[4]) +
-                       "] us (route, barrier, compact, then relax/barrier/apply per round, tail):";
+                       "] us (" + std::string(c->dist_kernel == 1 ? "route, barrier, compact, then relax/barrier/apply per round, tail" : "init + route, count + scan, then relax + barrier / apply per round, tail") + "):";
     for (int i = 1; i < 128 && t[i]; ++i) line += " " + std::to_string(static_cast<long long>((t[i] - t[i - 1]) / 1000));
     std::fprintf(stderr, "%s\n", line.c_str());
   }

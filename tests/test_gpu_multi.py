@@ -91,8 +91,8 @@ def test_virtual_ranks_tie_heavy_and_mixed_lengths(built, tmp_path):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for world, sharded in ((2, True), (4, False)):
-        outs = run_virtual(db, world, sharded, steps=1)
+    for world, sharded, opt in ((2, True, {}), (4, False, {}), (2, False, {"dist_kernel": 1})):
+        outs = run_virtual(db, world, sharded, steps=1, **opt)
         links = np.concatenate([o[2] for o in outs])
         links = links[np.lexsort((links[:, 1], links[:, 0]))]
         assert np.array_equal(links, orc.links())
