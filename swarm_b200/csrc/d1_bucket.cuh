@@ -33,6 +33,10 @@ struct BucketParams {
   unsigned long long *boff;                       // nblk + 1: first bucketed link of every block
   uint2 *blinks;                                  // the links, bucketed by source block
   uint64_t blinks_cap;
+  uint2 *unit_blk;                                // per work unit: first and last source block of its links
+  uint32_t *act_list;                             // units to walk in the current round
+  uint32_t *act_n;                                // [2] rotating counters of act_list
+  uint64_t unit_cap;
 };
 
 // position of the first block whose links start after link p (boff is non-decreasing): block of link p
@@ -45,11 +49,16 @@ __device__ __forceinline__ uint32_t bk_block_of(const BucketParams &B, unsigned 
   return lo;
 }
 
+// raise a block flag; read first: millions of plain stores to the same few sectors serialise in the L2 slice that owns them
+__device__ __forceinline__ void bk_flag(uint8_t *f, uint32_t b) {
+  if (*reinterpret_cast<volatile uint8_t *>(&f[b]) == 0) f[b] = 1;
+}
+
 // offer cand to the owned amplicon with local index lv; a lowered key marks it (and its block) for the next round
 __device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *wr, uint8_t *fwr, uint32_t lv, unsigned long long cand) {
   if (cand < B.D.key[lv] && atomicMin(&B.D.key[lv], cand) > cand) {
     atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
-    fwr[lv / kDistBlock] = 1;
+    bk_flag(fwr, lv / kDistBlock);
     return true;
   }
   return false;
@@ -87,7 +96,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
   __shared__ unsigned long long s_prev[kDistMaxWorld], s_cur[kDistMaxWorld];
   __shared__ unsigned long long scan_part[256];
-  __shared__ uint32_t s_b0, s_b1;
   extern __shared__ __align__(16) unsigned char dist_dyn[];      // kDistChunk * 16 bytes: staging of the link routing
   const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -149,7 +157,20 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   };
 
   // ---- bucket the links by the block of their source: count, scan, scatter (+ round 0)
-  for (uint64_t i = tid; i < m; i += nth) atomicAdd(&B.bcount[dist_local(D, link_at(i).x) / kDistBlock], 1u);
+  // (source blocks are very unevenly loaded — abundant amplicons have the links — so per-link global atomics pile up on a few
+  // addresses: 0.5 ms for the count and 1.5 ms for the scatter in the first cut; histograms and ranks live in shared memory)
+  uint32_t *hist = reinterpret_cast<uint32_t *>(dist_dyn);          // nblk counters when they fit the staging buffer
+  const bool smem_hist = static_cast<size_t>(B.nblk) * 8 <= static_cast<size_t>(kDistChunk) * sizeof(DistRec);
+  if (smem_hist) {
+    for (uint32_t b = threadIdx.x; b < B.nblk; b += 256) hist[b] = 0;
+    __syncthreads();
+    for (uint64_t i = tid; i < m; i += nth) atomicAdd(&hist[dist_local(D, link_at(i).x) / kDistBlock], 1u);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < B.nblk; b += 256)
+      if (hist[b]) atomicAdd(&B.bcount[b], hist[b]);
+  } else {
+    for (uint64_t i = tid; i < m; i += nth) atomicAdd(&B.bcount[dist_local(D, link_at(i).x) / kDistBlock], 1u);
+  }
   grid.sync();
   if (blockIdx.x == 0) {                                           // exclusive scan of nblk counts by one CTA
     const uint32_t per = (B.nblk + 255u) / 256u;
@@ -172,30 +193,66 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
       run += c;
     }
     if (threadIdx.x == 255) B.boff[B.nblk] = scan_part[255];
+    if (threadIdx.x < 2) B.act_n[threadIdx.x] = 0;
   }
   grid.sync();
+  // first and last source block of every work unit (a round then reads 8 bytes per unit instead of searching)
+  const uint64_t n_units = min(static_cast<unsigned long long>((m + kBkUnit - 1) / kBkUnit), static_cast<unsigned long long>(B.unit_cap));
+  for (uint64_t u = tid; u < n_units; u += nth) {
+    const unsigned long long p0 = u * kBkUnit, p1 = min(static_cast<unsigned long long>(m), p0 + kBkUnit);
+    B.unit_blk[u] = make_uint2(bk_block_of(B, p0), bk_block_of(B, p1 - 1));
+  }
   dist_stamp(D, tid, tslot);                                      // count + scan
   unsigned long long *counters = D.lcnt + kDistMaxWorld;
   {
     uint32_t *wr = D.bits + D.nwords;                               // round 1 reads bitmap 1 / flags 1
     uint8_t *fwr = B.bflag + B.nblk;
     int ch = 0;
-    const uint64_t m_round = (m + 31u) & ~31ull;                    // whole warps: bk_send is warp-collective
-    for (uint64_t i = tid; i < m_round; i += nth) {
-      const bool in = i < m;
-      uint2 ed = in ? link_at(i) : make_uint2(0u, 0u);
-      bool remote = false;
-      uint32_t o = 0;
-      const unsigned long long cand = (static_cast<unsigned long long>(ed.x) << 32) + 1ull;   // key[src] is still src << 32
-      if (in) {
-        const uint32_t b = dist_local(D, ed.x) / kDistBlock;
-        B.blinks[B.boff[b] + atomicAdd(&B.bcount[b], 1u)] = ed;
-        o = multi ? dist_owner(D, ed.y) : D.rank;
-        if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed.y), cand) ? 1 : 0;
-        else remote = true;
+    // a CTA takes chunks of kBkUnit links: rank inside (chunk, block) from a shared-memory atomic, ONE global atomicAdd per
+    // (chunk, block) reserves the range in the bucket
+    uint32_t *base_s = hist + B.nblk;
+    if (smem_hist) { __syncthreads(); for (uint32_t b = threadIdx.x; b < B.nblk; b += 256) hist[b] = 0; }
+    for (uint64_t c0 = static_cast<uint64_t>(blockIdx.x) * kBkUnit; c0 < m; c0 += static_cast<uint64_t>(gridDim.x) * kBkUnit) {
+      uint2 ed[kBkUnit / 256];
+      uint32_t blk[kBkUnit / 256], rk[kBkUnit / 256];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
+        const uint64_t i = c0 + static_cast<uint64_t>(k) * 256 + threadIdx.x;
+        const bool in = i < m;
+        ed[k] = in ? link_at(i) : make_uint2(kNone, kNone);
+        blk[k] = in ? dist_local(D, ed[k].x) / kDistBlock : 0u;
+        rk[k] = 0;
+        if (in) rk[k] = smem_hist ? atomicAdd(&hist[blk[k]], 1u) : atomicAdd(&B.bcount[blk[k]], 1u);
       }
-      if (multi) {
-        if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed.y, ed.x, cand, lane); ch = 1; }
+      if (smem_hist) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k)
+          if (ed[k].x != kNone && rk[k] == 0) base_s[blk[k]] = atomicAdd(&B.bcount[blk[k]], hist[blk[k]]);
+        __syncthreads();
+      }
+#pragma unroll
+      for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
+        const bool in = ed[k].x != kNone;
+        bool remote = false;
+        uint32_t o = 0;
+        const unsigned long long cand = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;   // key[src] is still src << 32
+        if (in) {
+          B.blinks[B.boff[blk[k]] + (smem_hist ? base_s[blk[k]] : 0u) + rk[k]] = ed[k];
+          o = multi ? dist_owner(D, ed[k].y) : D.rank;
+          if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed[k].y), cand) ? 1 : 0;
+          else remote = true;
+        }
+        if (multi) {
+          if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed[k].y, ed[k].x, cand, lane); ch = 1; }
+        }
+      }
+      if (smem_hist) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k)
+          if (ed[k].x != kNone) hist[blk[k]] = 0;                   // only the touched counters
       }
     }
     if (__syncthreads_or(ch) && threadIdx.x == 0) lflags[0] = 1;
@@ -215,16 +272,29 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
       for (uint64_t w = tid; w < D.nwords; w += nth) cl[w] = 0;
       for (uint64_t w = tid; w < B.nblk; w += nth) fcl[w] = 0;
       int ch = 0;
-      const uint64_t n_units = (m + kBkUnit - 1) / kBkUnit;
-      for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      // the units whose source blocks had an amplicon lowered in the previous round
+      uint32_t *an = B.act_n + (round & 1u);
+      for (uint64_t u0 = tid - lane; u0 < n_units; u0 += nth) {
+        const uint64_t u = u0 + lane;
+        bool act = false;
+        if (u < n_units) {
+          const uint2 bb = B.unit_blk[u];
+          for (uint32_t b = bb.x; b <= bb.y && !act; ++b) act = frd[b] != 0;
+        }
+        const uint32_t mask = __ballot_sync(kFull, act);
+        if (mask) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(an, static_cast<uint32_t>(__popc(mask)));
+          base = __shfl_sync(kFull, base, 0);
+          if (act) B.act_list[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint32_t>(u);
+        }
+      }
+      if (tid == 0) B.act_n[(round + 1) & 1u] = 0;
+      grid.sync();
+      const uint32_t n_act = *reinterpret_cast<volatile uint32_t *>(an);
+      for (uint32_t a = blockIdx.x; a < n_act; a += gridDim.x) {
+        const uint64_t unit = B.act_list[a];
         const unsigned long long p0 = unit * kBkUnit, p1 = min(static_cast<unsigned long long>(m), p0 + kBkUnit);
-        __syncthreads();
-        if (threadIdx.x == 0) { s_b0 = bk_block_of(B, p0); s_b1 = bk_block_of(B, p1 - 1); }
-        __syncthreads();
-        const uint32_t b0 = s_b0, b1 = s_b1;
-        int act = 0;
-        for (uint32_t b = b0 + threadIdx.x; b <= b1; b += 256) act |= frd[b];
-        if (!__syncthreads_or(act)) continue;                        // nothing lowered among this unit's sources last round
 #pragma unroll
         for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
           const unsigned long long p = p0 + static_cast<unsigned long long>(k) * 256 + threadIdx.x;
@@ -281,7 +351,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
             const unsigned long long cand = (static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z;
             if (cand < kv[k] && atomicMin(&D.key[lv], cand) > cand) {
               atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
-              fwr[lv / kDistBlock] = 1;
+              bk_flag(fwr, lv / kDistBlock);
             }
           }
         }

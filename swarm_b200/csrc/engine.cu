@@ -186,7 +186,8 @@ struct swb200_ctx {
   DevBuf<uint8_t> bk_flag;                     // bucketed clustering (d1_bucket.cuh)
   DevBuf<uint32_t> bk_count;
   DevBuf<unsigned long long> bk_off;
-  DevBuf<uint2> bk_links;
+  DevBuf<uint2> bk_links, bk_unit;
+  DevBuf<uint32_t> bk_act;
   int dist_kernel = 0;                         // 0 = links bucketed by source block (d1_bucket.cuh), 1 = r1's k_cluster_dist
   DevBuf<unsigned char> dist_own;              // peer-visible buffer allocated by swb200_dist_setup_local
   DevBuf<unsigned long long> ts_route_cnt;     // [16] sender counters, then done_ctas[2] + err[2] as 32-bit words
@@ -321,7 +322,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->is_light.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
   c->run_start_d.release(); c->ts_route_cnt.release(); c->dist_own.release();
-  c->bk_flag.release(); c->bk_count.release(); c->bk_off.release(); c->bk_links.release();
+  c->bk_flag.release(); c->bk_count.release(); c->bk_off.release(); c->bk_links.release(); c->bk_unit.release(); c->bk_act.release();
   c->ts_store.release(); c->ts_ovf.release(); c->ts_cursor.release(); c->fr_deg.release(); c->fr_adj.release(); c->fr_spill.release();
   c->ld_len16.release(); c->ld_run_value.release(); c->ld_run_start.release();
   c->dr_table.release(); c->dr_mass.release(); c->dr_slot.release(); c->dr_rep.release(); c->dr_size.release(); c->dr_single.release();
@@ -1091,12 +1092,14 @@ static void run_cluster(swb200_ctx *c) {
     B.nblk = D.n_local / kDistBlock;
     c->bk_flag.alloc(static_cast<size_t>(B.nblk) * 3 + 16); c->bk_count.alloc(B.nblk + 1); c->bk_off.alloc(static_cast<size_t>(B.nblk) + 2);
     if (c->bk_links.n < m) c->bk_links.alloc(std::max<uint64_t>(m + m / 8, 1));
+    c->bk_unit.alloc(c->bk_links.n / kBkUnit + 2); c->bk_act.alloc(c->bk_links.n / kBkUnit + 2);
     D.key = c->key.p; D.parent = c->parent.p; D.label = c->label.p; D.generation = c->generation.p; D.bits = c->cl_bits.p;
     D.lcnt = c->counters.p + 44;                     // unused at world = 1
     D.epoch_base = 0;
     D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
     D.gbar = reinterpret_cast<unsigned int *>(c->counters.p + 42);
     B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+    B.unit_blk = c->bk_unit.p; B.act_list = c->bk_act.p; B.unit_cap = c->bk_unit.n - 1; B.act_n = reinterpret_cast<uint32_t *>(c->counters.p + 46);
     if (std::getenv("SWB200_CLUSTER_TS")) {
       c->cl_ts.alloc(128);
       CK(cudaMemsetAsync(c->cl_ts.p, 0, 128 * 8, c->stream));
@@ -1391,6 +1394,7 @@ static void dist_prepare(swb200_ctx *c) {
   const uint32_t nblk = n_local / kDistBlock;
   c->bk_flag.alloc(static_cast<size_t>(nblk) * 3 + 16); c->bk_count.alloc(nblk + 1); c->bk_off.alloc(static_cast<size_t>(nblk) + 2);
   c->bk_links.alloc(std::max<uint64_t>(c->dist_cap * c->dist_world, 1));      // everything the link inboxes can hold
+  c->bk_unit.alloc(c->bk_links.n / kBkUnit + 2); c->bk_act.alloc(c->bk_links.n / kBkUnit + 2);
 }
 
 // Allocate, ahead of time, every device buffer the multi-GPU step (d1_index with the index exchange, d1_network,
@@ -1454,6 +1458,7 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   B.D = D;
   B.nblk = D.n_local / kDistBlock;
   B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+  B.unit_blk = c->bk_unit.p; B.act_list = c->bk_act.p; B.unit_cap = c->bk_unit.n - 1; B.act_n = reinterpret_cast<uint32_t *>(c->counters.p + 46);
   const void *kern = c->dist_kernel == 1 ? reinterpret_cast<const void *>(k_cluster_dist) : reinterpret_cast<const void *>(k_cluster_bucket);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
   int occ = 1;
