@@ -232,20 +232,35 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
           if (ed[k].x != kNone && rk[k] == 0) base_s[blk[k]] = atomicAdd(&B.bcount[blk[k]], hist[blk[k]]);
         __syncthreads();
       }
+      constexpr int U = static_cast<int>(kBkUnit / 256);
+      uint32_t own[U], lv[U];
+      unsigned long long kd[U];
 #pragma unroll
-      for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
+      for (int k = 0; k < U; ++k) {
         const bool in = ed[k].x != kNone;
-        bool remote = false;
-        uint32_t o = 0;
+        if (in) B.blinks[B.boff[blk[k]] + (smem_hist ? base_s[blk[k]] : 0u) + rk[k]] = ed[k];
+        own[k] = in ? (multi ? dist_owner(D, ed[k].y) : D.rank) : kNone;
+        lv[k] = own[k] == D.rank ? dist_local(D, ed[k].y) : kNone;
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) kd[k] = lv[k] != kNone ? D.key[lv[k]] : 0ull;
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
         const unsigned long long cand = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;   // key[src] is still src << 32
-        if (in) {
-          B.blinks[B.boff[blk[k]] + (smem_hist ? base_s[blk[k]] : 0u) + rk[k]] = ed[k];
-          o = multi ? dist_owner(D, ed[k].y) : D.rank;
-          if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed[k].y), cand) ? 1 : 0;
-          else remote = true;
+        if (lv[k] != kNone && cand < kd[k] && atomicMin(&D.key[lv[k]], cand) > cand) {
+          atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
+          bk_flag(fwr, lv[k] / kDistBlock);
+          ch = 1;
         }
-        if (multi) {
-          if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed[k].y, ed[k].x, cand, lane); ch = 1; }
+      }
+      if (multi) {
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const bool remote = own[k] != kNone && own[k] != D.rank;
+          if (__any_sync(kFull, remote)) {
+            bk_send(B, counters, remote, own[k], ed[k].y, ed[k].x, (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull, lane);
+            ch = 1;
+          }
         }
       }
       if (smem_hist) {
@@ -295,24 +310,45 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
       for (uint32_t a = blockIdx.x; a < n_act; a += gridDim.x) {
         const uint64_t unit = B.act_list[a];
         const unsigned long long p0 = unit * kBkUnit, p1 = min(static_cast<unsigned long long>(m), p0 + kBkUnit);
+        // loads issued stage by stage (links, bitmap words, source keys, destination keys): a link is a chain of dependent
+        // reads, and one link at a time leaves every warp with a single request in flight
+        constexpr int U = static_cast<int>(kBkUnit / 256);
+        uint2 ed[U];
+        uint32_t lu[U], w[U];
+        bool act[U];
 #pragma unroll
-        for (int k = 0; k < static_cast<int>(kBkUnit / 256); ++k) {
+        for (int k = 0; k < U; ++k) {
           const unsigned long long p = p0 + static_cast<unsigned long long>(k) * 256 + threadIdx.x;
-          const bool in = p < p1;
-          const uint2 ed = in ? B.blinks[p] : make_uint2(0u, 0u);
-          const uint32_t lu = in ? dist_local(D, ed.x) : 0u;
-          const bool active = in && ((rd[lu >> 5] >> (lu & 31u)) & 1u);
-          bool remote = false;
-          uint32_t o = 0;
-          unsigned long long cand = 0;
-          if (active) {
-            cand = D.key[lu] + 1ull;
-            o = multi ? dist_owner(D, ed.y) : D.rank;
-            if (o == D.rank) ch |= bk_offer_local(B, wr, fwr, dist_local(D, ed.y), cand) ? 1 : 0;
-            else remote = true;
+          act[k] = p < p1;
+          ed[k] = act[k] ? B.blinks[p] : make_uint2(0u, 0u);
+          lu[k] = dist_local(D, ed[k].x);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) w[k] = act[k] ? rd[lu[k] >> 5] : 0u;
+#pragma unroll
+        for (int k = 0; k < U; ++k) act[k] = act[k] && ((w[k] >> (lu[k] & 31u)) & 1u);
+        unsigned long long cand[U], kd[U];
+        uint32_t own[U], lv[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          cand[k] = (act[k] ? D.key[lu[k]] : ~0ull) + 1ull;
+          own[k] = act[k] ? (multi ? dist_owner(D, ed[k].y) : D.rank) : kNone;
+          lv[k] = own[k] == D.rank ? dist_local(D, ed[k].y) : kNone;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) kd[k] = lv[k] != kNone ? D.key[lv[k]] : 0ull;
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          if (lv[k] != kNone && cand[k] < kd[k] && atomicMin(&D.key[lv[k]], cand[k]) > cand[k]) {
+            atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
+            bk_flag(fwr, lv[k] / kDistBlock);
+            ch = 1;
           }
-          if (multi) {
-            if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, o, ed.y, ed.x, cand, lane); ch = 1; }
+        if (multi) {
+#pragma unroll
+          for (int k = 0; k < U; ++k) {
+            const bool remote = own[k] != kNone && own[k] != D.rank;
+            if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, own[k], ed[k].y, ed[k].x, cand[k], lane); ch = 1; }
           }
         }
       }
