@@ -10,7 +10,7 @@
 // ACTIVE link read key[src] at a random address.  Here, once, the links are counting-sorted by the 4096-id block of their
 // source (a count pass of fire-and-forget atomics, one scan, one scatter pass: ~2 400 buckets at 10 M amplicons); then
 //   * a round walks the bucketed list in units of 2 048 links and SKIPS every unit whose source blocks had no amplicon lowered
-//     in the previous round (one flag byte per block): late rounds touch a few units instead of 70 MB;
+//     in the previous round (a warp ORs the 128 bitmap words of the unit's block): late rounds touch a few units, not 70 MB;
 //   * inside a unit the sources span one block (or a few): their bitmap words (512 B) and keys (32 KB) are L1-resident, so only
 //     key[dst] is a random access;
 //   * round 0 is fused into the scatter pass (every key still has its initial value src << 32: no load);
@@ -28,7 +28,6 @@ constexpr uint32_t kBkUnit = 2048;                // links per work unit of a ro
 struct BucketParams {
   DistParams D;                                   // rank, world, n, n_local, edges, m_local, key, parent, label, generation, bits, nwords, peers ...
   uint32_t nblk;                                  // owned blocks = n_local / kDistBlock
-  uint8_t *bflag;                                 // 3 x nblk rotating flags: some amplicon of the block was lowered (read / set / clear)
   uint32_t *bcount;                               // nblk: links per source block, then the scatter cursors
   unsigned long long *boff;                       // nblk + 1: first bucketed link of every block
   uint2 *blinks;                                  // the links, bucketed by source block
@@ -49,16 +48,10 @@ __device__ __forceinline__ uint32_t bk_block_of(const BucketParams &B, unsigned 
   return lo;
 }
 
-// raise a block flag; read first: millions of plain stores to the same few sectors serialise in the L2 slice that owns them
-__device__ __forceinline__ void bk_flag(uint8_t *f, uint32_t b) {
-  if (*reinterpret_cast<volatile uint8_t *>(&f[b]) == 0) f[b] = 1;
-}
-
 // offer cand to the owned amplicon with local index lv; a lowered key marks it (and its block) for the next round
-__device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *wr, uint8_t *fwr, uint32_t lv, unsigned long long cand) {
+__device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *wr, uint32_t lv, unsigned long long cand) {
   if (cand < B.D.key[lv] && atomicMin(&B.D.key[lv], cand) > cand) {
     atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
-    bk_flag(fwr, lv / kDistBlock);
     return true;
   }
   return false;
@@ -114,7 +107,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
     if (v < D.n) D.parent[v] = kNone;
   }
   for (uint64_t w = tid; w < 3ull * D.nwords; w += nth) D.bits[w] = 0;
-  for (uint64_t w = tid; w < 3ull * B.nblk; w += nth) B.bflag[w] = 0;
   for (uint64_t w = tid; w < B.nblk; w += nth) B.bcount[w] = 0;
   if (tid == 0) { lflags[0] = 0; lflags[1] = 0; lflags[2] = 0; lflags[3] = 0; }
   if (multi) {
@@ -206,7 +198,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   unsigned long long *counters = D.lcnt + kDistMaxWorld;
   {
     uint32_t *wr = D.bits + D.nwords;                               // round 1 reads bitmap 1 / flags 1
-    uint8_t *fwr = B.bflag + B.nblk;
     int ch = 0;
     // a CTA takes chunks of kBkUnit links: rank inside (chunk, block) from a shared-memory atomic, ONE global atomicAdd per
     // (chunk, block) reserves the range in the bucket
@@ -249,7 +240,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         const unsigned long long cand = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;   // key[src] is still src << 32
         if (lv[k] != kNone && cand < kd[k] && atomicMin(&D.key[lv[k]], cand) > cand) {
           atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
-          bk_flag(fwr, lv[k] / kDistBlock);
           ch = 1;
         }
       }
@@ -277,32 +267,27 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   uint32_t round = 0;
   for (;; ++round) {
     uint32_t *wr = D.bits + static_cast<size_t>((round + 1) % 3) * D.nwords;
-    uint8_t *fwr = B.bflag + static_cast<size_t>((round + 1) % 3) * B.nblk;
     if (round) {
       const uint32_t *rd = D.bits + static_cast<size_t>(round % 3) * D.nwords;
-      const uint8_t *frd = B.bflag + static_cast<size_t>(round % 3) * B.nblk;
       uint32_t *cl = D.bits + static_cast<size_t>((round + 2) % 3) * D.nwords;
-      uint8_t *fcl = B.bflag + static_cast<size_t>((round + 2) % 3) * B.nblk;
       if (tid == 0) lflags[(round + 1) % 3] = 0;
       for (uint64_t w = tid; w < D.nwords; w += nth) cl[w] = 0;
-      for (uint64_t w = tid; w < B.nblk; w += nth) fcl[w] = 0;
       int ch = 0;
       // the units whose source blocks had an amplicon lowered in the previous round
       uint32_t *an = B.act_n + (round & 1u);
-      for (uint64_t u0 = tid - lane; u0 < n_units; u0 += nth) {
-        const uint64_t u = u0 + lane;
-        bool act = false;
-        if (u < n_units) {
-          const uint2 bb = B.unit_blk[u];
-          for (uint32_t b = bb.x; b <= bb.y && !act; ++b) act = frd[b] != 0;
+      // (a warp per unit ORs the 128 bitmap words of each of the unit's source blocks: no per-block flag array — a first cut
+      // kept one flag byte per block and its 2.4 KB were hammered by every lowering: all of it lives in one or two L2 slices)
+      constexpr uint32_t kWordsPerBlock = kDistBlock / 32;
+      for (uint64_t u = tid >> 5; u < n_units; u += nth >> 5) {
+        const uint2 bb = B.unit_blk[u];
+        uint32_t any = 0;
+        for (uint32_t b = bb.x; b <= bb.y && !any; ++b) {
+          uint32_t acc = 0;
+#pragma unroll
+          for (uint32_t w = 0; w < kWordsPerBlock; w += 32) acc |= rd[static_cast<size_t>(b) * kWordsPerBlock + w + lane];
+          any = __any_sync(kFull, acc != 0) ? 1u : 0u;
         }
-        const uint32_t mask = __ballot_sync(kFull, act);
-        if (mask) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(an, static_cast<uint32_t>(__popc(mask)));
-          base = __shfl_sync(kFull, base, 0);
-          if (act) B.act_list[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint32_t>(u);
-        }
+        if (any && lane == 0) B.act_list[atomicAdd(an, 1u)] = static_cast<uint32_t>(u);
       }
       if (tid == 0) B.act_n[(round + 1) & 1u] = 0;
       grid.sync();
@@ -341,7 +326,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         for (int k = 0; k < U; ++k)
           if (lv[k] != kNone && cand[k] < kd[k] && atomicMin(&D.key[lv[k]], cand[k]) > cand[k]) {
             atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
-            bk_flag(fwr, lv[k] / kDistBlock);
             ch = 1;
           }
         if (multi) {
@@ -387,7 +371,6 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
             const unsigned long long cand = (static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z;
             if (cand < kv[k] && atomicMin(&D.key[lv], cand) > cand) {
               atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
-              bk_flag(fwr, lv / kDistBlock);
             }
           }
         }

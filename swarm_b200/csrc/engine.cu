@@ -1098,7 +1098,7 @@ static void run_cluster(swb200_ctx *c) {
     D.epoch_base = 0;
     D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
     D.gbar = reinterpret_cast<unsigned int *>(c->counters.p + 42);
-    B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+    B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
     B.unit_blk = c->bk_unit.p; B.act_list = c->bk_act.p; B.unit_cap = c->bk_unit.n - 1; B.act_n = reinterpret_cast<uint32_t *>(c->counters.p + 46);
     if (std::getenv("SWB200_CLUSTER_TS")) {
       c->cl_ts.alloc(128);
@@ -1457,7 +1457,7 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   BucketParams B{};
   B.D = D;
   B.nblk = D.n_local / kDistBlock;
-  B.bflag = c->bk_flag.p; B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
+  B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
   B.unit_blk = c->bk_unit.p; B.act_list = c->bk_act.p; B.unit_cap = c->bk_unit.n - 1; B.act_n = reinterpret_cast<uint32_t *>(c->counters.p + 46);
   const void *kern = c->dist_kernel == 1 ? reinterpret_cast<const void *>(k_cluster_dist) : reinterpret_cast<const void *>(k_cluster_bucket);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
