@@ -67,8 +67,9 @@ const char *swb200_last_error(void);
  * huge groups sharing one K-mer — swb200_d1_network switches to the linear HALF enumeration, like the reference's
  * cost model; 0 = always sweep),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "cluster_kernel" (0 links bucketed by source block, inactive buckets skipped, one persistent kernel, d1_bucket.cuh;
- * 5 r1's persistent kernel over the whole link list every round; 4 frontier bitmap over 8-slot out-rows, d1_frontier.cuh;
+ * "cluster_kernel" (0 = 5 fused label/generation relaxation over the link list in one persistent cooperative kernel;
+ * 6 links bucketed by source block, inactive buckets skipped, d1_bucket.cuh (the multi-GPU kernel run on one GPU);
+ * 4 frontier bitmap over 8-slot out-rows, d1_frontier.cuh;
  * 3 links counting-sorted by source; 2 one launch per round; 1 label propagation then BFS — same result),
  * "dist_kernel" (multi-GPU clustering: 0 the bucketed kernel, 1 r1's k_cluster_dist), "dn_filter" (0 auto,
  * 1 all-pairs q-gram filter),

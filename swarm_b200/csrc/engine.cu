@@ -354,7 +354,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
-  else if (k == "cluster_kernel" && v >= 0 && v <= 5) c->cluster_kernel = static_cast<int>(v);
+  else if (k == "cluster_kernel" && v >= 0 && v <= 6) c->cluster_kernel = static_cast<int>(v);
   else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
@@ -1079,8 +1079,9 @@ static void run_cluster(swb200_ctx *c) {
   const int vb = (n + 255) / 256;
   const int eb = static_cast<int>(std::min<uint64_t>((m + 255) / 256, static_cast<uint64_t>(c->sm_count) * 16));
   uint32_t *h_changed = static_cast<uint32_t *>(c->staging(64));
-  if (c->cluster_kernel == 0) {
-    // links bucketed by source block, one persistent kernel (d1_bucket.cuh), world = 1
+  if (c->cluster_kernel == 6) {
+    // links bucketed by source block, one persistent kernel (d1_bucket.cuh), world = 1: measured 1.39 ms at 10 M against the 1.08 ms of
+    // k_cluster_persistent (the rounds are faster, 0.73 ms, but bucketing costs 0.33 ms once) — the multi-GPU kernel, an option here
     BucketParams B{};
     DistParams &D = B.D;
     D.rank = 0; D.world = 1; D.n = n;
@@ -1195,7 +1196,7 @@ static void run_cluster(swb200_ctx *c) {
     }
     return;
   }
-  if (c->cluster_kernel == 5 || c->cluster_kernel == 3) {
+  if (c->cluster_kernel == 0 || c->cluster_kernel == 5 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
     int occ = 1;
     auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;

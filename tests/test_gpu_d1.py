@@ -242,7 +242,7 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
     orc.cluster()
     for mode, opt in ((ENUM_FULL, {"cluster_kernel": 1}), (ENUM_HALF, {"net_kernel": 1, "cluster_kernel": 2}), (ENUM_HALF, {"net_kernel": 2, "cluster_kernel": 3}), (ENUM_JOIN, {}),
                       (ENUM_JOIN, {"cluster_kernel": 4, "tile_rows": 1}),
-                      (ENUM_JOIN, {"cluster_kernel": 5})):
+                      (ENUM_JOIN, {"cluster_kernel": 6})):
         links, sw, gen, par, *_ = run_engine(db, mode, **opt)
         assert np.array_equal(links, orc.links())
         assert np.array_equal(sw, orc.swarm_of)

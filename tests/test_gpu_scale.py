@@ -21,7 +21,7 @@ def test_reference_digests_small(built, name):
     _check(name)
 
 
-@pytest.mark.parametrize("opt", [{"tile_rows": 1, "cluster_kernel": 4}, {"join_kernel": 2, "cluster_kernel": 3}, {"join_kernel": 1}, {"enum_mode": 1, "cluster_kernel": 2}])
+@pytest.mark.parametrize("opt", [{"tile_rows": 1, "cluster_kernel": 4}, {"cluster_kernel": 6}, {"join_kernel": 2, "cluster_kernel": 3}, {"join_kernel": 1}, {"enum_mode": 1, "cluster_kernel": 2}])
 def test_reference_digests_other_kernels(built, opt):
     _check("tie1m", **opt)
 
