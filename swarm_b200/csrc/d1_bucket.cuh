@@ -14,9 +14,9 @@
 //   * inside a unit the sources span one block (or a few): their bitmap words (512 B) and keys (32 KB) are L1-resident, so only
 //     key[dst] is a random access;
 //   * round 0 is fused into the scatter pass (every key still has its initial value src << 32: no load);
-//   * multi-GPU: a remote destination becomes a 16-byte record in the owner's message log, appended per WARP — one ballot per
-//     destination rank, one atomicAdd issued by `world` lanes at once on the sender's LOCAL counters, consecutive slots for the
-//     lanes of a run — instead of r1's per-chunk counting sort in shared memory with three CTA barriers.
+//   * multi-GPU: a remote destination becomes a 16-byte record in the owner's message log; a unit reserves its range with one
+//     atomicAdd per destination rank on the sender's LOCAL counters (ranks inside the unit from ballots + shared-memory
+//     atomics) and writes straight from registers — no counting sort of the records in shared memory as in r1.
 // Ownership is block-cyclic (blocks of kDistBlock = 4096 ids), so "source block" = ownership block: a bucket never mixes owners.
 #pragma once
 #include "d1_dist.cuh"
@@ -57,29 +57,52 @@ __device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *
   return false;
 }
 
-// warp-collective: lanes with `remote` append (v, u, cand) to the message log of owner[lane] on that rank.  One ballot per
-// destination rank; the `world` reservations are issued together by the first `world` lanes on the sender's local counters.
-__device__ __forceinline__ void bk_send(const BucketParams &B, unsigned long long *counters, bool remote, uint32_t owner, uint32_t v, uint32_t u,
-                                        unsigned long long cand, uint32_t lane) {
+// CTA-collective: every thread holds U links; those with a remote destination (own[k] is another rank) append the record
+// (v, u, cand) to the message log of that rank.  Ranks inside the CTA come from warp ballots + one shared-memory atomic per warp
+// and destination, then ONE global atomicAdd per destination and call reserves the CTA's range on the sender's LOCAL counter
+// (a first cut reserved per warp: 250 k atomics a round on the one counter of the peer, +170 us a round at 2 GPUs), and the
+// lanes of a warp write consecutive 16-byte slots.
+template <int U>
+__device__ __forceinline__ bool bk_send_unit(const BucketParams &B, unsigned long long *counters, uint32_t *s_cnt, unsigned long long *s_base,
+                                             const uint32_t (&own)[U], const uint2 (&ed)[U], const unsigned long long (&cand)[U], uint32_t lane) {
   const DistParams &D = B.D;
-  uint32_t my_mask = 0, lane_mask = 0;
-  for (uint32_t d = 0; d < D.world; ++d) {
-    const uint32_t m = __ballot_sync(kFull, remote && owner == d);
-    if (lane == d) lane_mask = m;
-    if (remote && owner == d) my_mask = m;
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < U; ++k) any |= own[k] != kNone && own[k] != D.rank;
+  if (!__syncthreads_or(any)) return false;
+  if (threadIdx.x < kDistMaxWorld) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t off[U];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const bool remote = own[k] != kNone && own[k] != D.rank;
+    off[k] = 0;
+    if (!__any_sync(kFull, remote)) continue;
+    for (uint32_t d = 0; d < D.world; ++d) {
+      const uint32_t m = __ballot_sync(kFull, remote && own[k] == d);
+      if (!m) continue;
+      uint32_t base = 0;
+      if (lane == static_cast<uint32_t>(__ffs(m) - 1)) base = atomicAdd(&s_cnt[d], static_cast<uint32_t>(__popc(m)));
+      base = __shfl_sync(kFull, base, __ffs(m) - 1);
+      if (remote && own[k] == d) off[k] = base + __popc(m & lt);
+    }
   }
-  unsigned long long base = 0;
-  if (lane < D.world && lane_mask) base = atomicAdd(&counters[lane], static_cast<unsigned long long>(__popc(lane_mask)));
-  const unsigned long long b = shfl_u64(base, remote ? static_cast<int>(owner) : 0);
-  if (remote) {
-    const unsigned long long slot = b + __popc(my_mask & ((1u << lane) - 1u));
+  __syncthreads();
+  if (threadIdx.x < D.world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (own[k] == kNone || own[k] == D.rank) continue;
+    const unsigned long long slot = s_base[own[k]] + off[k];
     if (slot >= D.cap_upd) dist_ctl(D, D.rank)->overflow = 1u;
     else if (!(D.dbg & 1u)) {
       uint4 rec;
-      rec.x = v; rec.y = u; rec.z = static_cast<uint32_t>(cand); rec.w = static_cast<uint32_t>(cand >> 32);
-      *reinterpret_cast<uint4 *>(dist_upd(D, owner, D.rank) + slot) = rec;
+      rec.x = ed[k].y; rec.y = ed[k].x; rec.z = static_cast<uint32_t>(cand[k]); rec.w = static_cast<uint32_t>(cand[k] >> 32);
+      *reinterpret_cast<uint4 *>(dist_upd(D, own[k], D.rank) + slot) = rec;
     }
   }
+  return true;
 }
 
 __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
@@ -89,6 +112,8 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
   __shared__ unsigned long long s_prev[kDistMaxWorld], s_cur[kDistMaxWorld];
   __shared__ unsigned long long scan_part[256];
+  __shared__ uint32_t s_cnt[kDistMaxWorld];
+  __shared__ unsigned long long s_base[kDistMaxWorld];
   extern __shared__ __align__(16) unsigned char dist_dyn[];      // kDistChunk * 16 bytes: staging of the link routing
   const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -244,14 +269,10 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         }
       }
       if (multi) {
+        unsigned long long cand0[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-          const bool remote = own[k] != kNone && own[k] != D.rank;
-          if (__any_sync(kFull, remote)) {
-            bk_send(B, counters, remote, own[k], ed[k].y, ed[k].x, (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull, lane);
-            ch = 1;
-          }
-        }
+        for (int k = 0; k < U; ++k) cand0[k] = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;
+        if (bk_send_unit<U>(B, counters, s_cnt, s_base, own, ed, cand0, lane)) ch = 1;
       }
       if (smem_hist) {
         __syncthreads();
@@ -329,11 +350,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
             ch = 1;
           }
         if (multi) {
-#pragma unroll
-          for (int k = 0; k < U; ++k) {
-            const bool remote = own[k] != kNone && own[k] != D.rank;
-            if (__any_sync(kFull, remote)) { bk_send(B, counters, remote, own[k], ed[k].y, ed[k].x, cand[k], lane); ch = 1; }
-          }
+          if (bk_send_unit<U>(B, counters, s_cnt, s_base, own, ed, cand, lane)) ch = 1;
         }
       }
       if (__syncthreads_or(ch) && threadIdx.x == 0) lflags[round % 3] = 1;
