@@ -61,8 +61,9 @@ const char *swb200_last_error(void);
  * same links), "tile_cmax" (test hook: cap on the records a tile slot holds; the rest takes the overflow path),
  * "tile_rows" (0 default: a tile record is the 8-byte entry and the join gathers the packed rows it needs from the
  * database; 1: a record carries its packed row — the layout of the sharded multi-GPU job), "tile_cap" (tuning: records per
- * tile slot), "index_exchange" (1 default: after swb200_dist_setup every rank hashes only its own rows and routes the
- * records to the tile owners over the peer buffers; 0: every rank scans the whole replicated database),
+ * tile slot), "index_exchange" (after swb200_dist_setup: 2 = every rank hashes only its own rows and routes the records
+ * to the tile owners over the peer buffers, 0 = every rank scans the whole replicated database and keeps its tiles' records,
+ * 1 default = the exchange from 3 ranks on and always for a sharded database),
  * "skew_fallback" (1 default: when the overflow path would cost more than ~32 pair tests per amplicon — dense data,
  * huge groups sharing one K-mer — swb200_d1_network switches to the linear HALF enumeration, like the reference's
  * cost model; 0 = always sweep),

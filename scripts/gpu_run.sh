@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parametrised runner for the GPU box (under gpurun): scripts/gpu_run.sh TAG step [step ...]
-#   steps: box | fullp:<kernel regex>[:skip] (ncu --set full of one launch under scripts/probe.py) | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
+#   steps: box | full:<kernel regex>[:skip[:bench args]] | fullp:<kernel regex>[:skip] (ncu --set full of one launch under scripts/probe.py) | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
 # Everything lands in gpurun_out/TAG_*.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
@@ -13,16 +13,17 @@ for step in "$@"; do
     tests) if [ -n "$arg" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -k "$arg" > $O/${TAG}_tests.log 2>&1; else timeout 2400 python -m pytest tests -x -q -m gpu > $O/${TAG}_tests.log 2>&1; fi
            echo "== tests rc=$?"; tail -5 $O/${TAG}_tests.log ;;
     scale) timeout 1500 python -m pytest tests/test_gpu_scale.py -x -q -m gpu > $O/${TAG}_scale.log 2>&1; echo "== scale rc=$?"; tail -5 $O/${TAG}_scale.log ;;
-    bench) timeout 1500 python bench.py $arg > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "== bench rc=$?"; tail -c 2500 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err ;;
+    bench) n=$(echo "$arg" | tr -c 'a-zA-Z0-9' '_'); timeout 1500 python bench.py $arg > $O/${TAG}_bench$n.json 2> $O/${TAG}_bench$n.err; echo "== bench $arg rc=$?"
+           python -c "import json,sys; d=json.loads(open('$O/${TAG}_bench$n.json').read().strip().splitlines()[-1]); print({k: d.get(k) for k in ('impl','value','ms_per_step','phases_ms','parity','unavailable')}, 'e2e', d.get('e2e',{}).get('ms_per_step'), 'roofline', {k: (d.get('roofline') or {}).get(k) for k in ('kernel','frac')}, 'cpu', (d.get('cpu_baseline') or {}).get('value'))"; tail -3 $O/${TAG}_bench$n.err ;;
     probe) timeout 900 python scripts/probe.py $arg > $O/${TAG}_probe.log 2>&1; echo "== probe rc=$?"; cat $O/${TAG}_probe.log ;;
     ts) SWB200_CLUSTER_TS=1 timeout 600 python scripts/probe.py 10000000 default= > $O/${TAG}_ts.log 2>&1; grep -E "cluster_frontier|cluster_dist" $O/${TAG}_ts.log | tail -3 ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv \
                 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_launches.out 2>&1
               python scripts/ncu_summary.py launches $O/${TAG}_launches.csv > $O/${TAG}_launches.txt; head -20 $O/${TAG}_launches.txt ;;
-    full) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
+    full) IFS=: read -r k skip extra <<< "$arg"; skip=${skip:-0}
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
-            python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_full_$k.out 2>&1
-          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -40 $O/${TAG}_$k.txt ;;
+            python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity $extra > $O/${TAG}_full_$k.out 2>&1
+          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -12 $O/${TAG}_$k.txt ;;
     fullp) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python scripts/probe.py 10000000 default= > $O/${TAG}_fullp_$k.out 2>&1

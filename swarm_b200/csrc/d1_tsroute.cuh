@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kTsRows) k_ts_route(TsRouteParams R) {
   unsigned long long e[2] = {0, 0};
   uint32_t owner[2] = {kNone, kNone}, tl[2] = {0, 0}, rk[2] = {0, 0};
   const uint64_t *w = rows + static_cast<size_t>(tid) * J.stride;
+  uint32_t kept_local = 0;
   if (tid < n_rows) {
     const uint32_t r = r0 + tid;
     const uint32_t L = J.len[r];
@@ -94,7 +95,16 @@ __global__ void __launch_bounds__(kTsRows) k_ts_route(TsRouteParams R) {
       owner[piece] = tile / R.tiles_per_rank;
       tl[piece] = tile - owner[piece] * R.tiles_per_rank;
       e[piece] = ts_pack(J, h, piece, L, ab, J.row_first + r);
+      if (owner[piece] == R.rank) {                        // my own tile: no detour through the inbox
+        ts_append(J, tl[piece], e[piece], w);
+        owner[piece] = kNone;
+        ++kept_local;
+      }
     }
+  }
+  if (J.stats) {
+    kept_local = __reduce_add_sync(kFull, kept_local);
+    if (lane == 0 && kept_local) atomicAdd(J.appended, static_cast<unsigned long long>(kept_local));
   }
   // rank of every record inside its owner's run: one shared-memory atomic per warp and owner
 #pragma unroll
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(256) k_ts_scatter_inbox(TsRouteParams R) {
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   unsigned long long kept = 0;
   for (uint32_t s = 0; s < R.world; ++s) {
+    if (s == R.rank) continue;                             // my own records went straight into the tiles
     const uint64_t n_rec = min(*reinterpret_cast<const volatile unsigned long long *>(&me->cnt[s]), static_cast<unsigned long long>(R.inbox_cap));
     const unsigned long long *in = ts_inbox(R, R.rank, s);
     for (uint64_t i = tid; i < n_rec; i += nth) {

@@ -181,7 +181,7 @@ struct swb200_ctx {
   uint32_t n_runs = 0;
   uint32_t job_min_len = 0, job_max_len = 0;   // length range of the whole job (every rank must use the same piece length K)
   int dist_grid_div = 1;             // test hook: several ranks share ONE GPU, each persistent kernel takes 1/div of the SMs
-  int index_exchange = 1;            // after swb200_dist_setup: hash only this rank's rows, route the records to the tile owners
+  int index_exchange = 1;            // 0 never, 1 auto, 2 always:            // after swb200_dist_setup: hash only this rank's rows, route the records to the tile owners
   unsigned long long idx_epoch = 0;
   DevBuf<uint8_t> bk_flag;                     // bucketed clustering (d1_bucket.cuh)
   DevBuf<uint32_t> bk_count;
@@ -227,6 +227,10 @@ struct swb200_ctx {
   uint64_t launches = 0;
   uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+  // multi-GPU "Hashing sequences": hash only this rank's rows and route the records to the tile owners (d1_tsroute.cuh)?  A sharded
+  // database has no alternative; a replicated one can also be scanned whole by every rank, which is cheaper at 2 GPUs (2 x 0.34 ms
+  // against 0.9 ms for route + inbox scatter, profiles/r2i) and loses from 3 GPUs on
+  bool exchange() const { return dist_world > 1 && (db_sharded || index_exchange == 2 || (index_exchange == 1 && dist_world >= 3)); }
   void *staging(size_t bytes) {
     if (bytes > pinned_bytes) {
       if (pinned) cudaFreeHost(pinned);
@@ -344,7 +348,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "join_kernel" && v >= 0 && v <= 2) c->join_kernel = static_cast<int>(v);
   else if (k == "skew_fallback" && (v == 0 || v == 1)) c->skew_fallback = static_cast<int>(v);
   else if (k == "tile_rows" && (v == 0 || v == 1)) c->ts_fat = static_cast<int>(v);
-  else if (k == "index_exchange" && (v == 0 || v == 1)) c->index_exchange = static_cast<int>(v);
+  else if (k == "index_exchange" && v >= 0 && v <= 2) c->index_exchange = static_cast<int>(v);
   else if (k == "dist_grid_div" && v >= 1 && v <= 16) c->dist_grid_div = static_cast<int>(v);
   else if (k == "dist_kernel" && (v == 0 || v == 1)) c->dist_kernel = static_cast<int>(v);
   else if (k == "job_min_len" && v >= 0 && v < (1ll << 32)) c->job_min_len = static_cast<uint32_t>(v);
@@ -629,8 +633,8 @@ static uint32_t ts_prepare(swb200_ctx *c) {
   c->ts_tiles = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(want_tiles, 0x7FFFFFFFull)));
   if (c->tj_cmax_override >= 2) cap = std::max<uint32_t>(2, std::min(cap, c->tj_cmax_override) & ~1u);
   c->ts_cap = cap;
-  const uint32_t own_world = (c->dist_world > 1 && c->index_exchange) ? c->dist_world : static_cast<uint32_t>(c->shard_world);
-  const uint32_t own_rank = (c->dist_world > 1 && c->index_exchange) ? c->dist_rank : static_cast<uint32_t>(c->shard_rank);
+  const uint32_t own_world = c->dist_world > 1 ? c->dist_world : static_cast<uint32_t>(c->shard_world);      // after dist_setup the job's ranks share the tiles
+  const uint32_t own_rank = c->dist_world > 1 ? c->dist_rank : static_cast<uint32_t>(c->shard_rank);
   const uint32_t per = (c->ts_tiles + own_world - 1) / own_world;
   c->ts_lo = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(per) * own_rank, c->ts_tiles));
   c->ts_hi = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(c->ts_lo) + per, c->ts_tiles));
@@ -667,8 +671,7 @@ static void index_tilestore(swb200_ctx *c) {
   CK(cudaMemsetAsync(c->counters.p + 32, 0, 5 * 8, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p, 0, static_cast<size_t>(T) * 4, c->stream));
   CK(cudaMemsetAsync(c->ts_cursor.p + T, 0xFF, static_cast<size_t>(T) * 4, c->stream));
-  const bool exchange = c->dist_world > 1 && c->index_exchange;
-  if (exchange) {
+  if (c->exchange()) {
     // multi-GPU: hash only this rank's rows, route every record to the owner of its tile over NVLink (d1_tsroute.cuh)
     TsRouteParams R{};
     R.J = ts_params(c);
@@ -755,7 +758,7 @@ int swb200_d1_index(swb200_ctx *c) {
   c->jK = std::min<uint32_t>(64, c->min_len / 2);
   const bool join = c->enum_mode == SWB200_ENUM_JOIN && c->jK >= 8;
   if (c->db_sharded) {
-    if (!(join && c->join_kernel == 0 && c->stride <= 64 && c->max_len < 8192 && c->dist_world > 1 && c->index_exchange && c->ts_fat && c->unsorted == 0)) {
+    if (!(join && c->join_kernel == 0 && c->stride <= 64 && c->max_len < 8192 && c->dist_world > 1 && c->ts_fat && c->unsorted == 0)) {
       g_err = "d1_index: a sharded database (swb200_load_db_rows) needs swb200_dist_setup, tile_rows = 1, the default join, a database sorted "
               "by abundance and sequences of 16..8191 nt";
       return SWB200_EUNSUPPORTED;
@@ -968,7 +971,7 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
     run_network(c);
     unsigned long long *host = static_cast<unsigned long long *>(c->staging(4096));   // one read-back (pinned): links, stats, duplicate flag, overflow counters
     CK(cudaMemcpyAsync(host, c->counters.p, 37 * 8, cudaMemcpyDeviceToHost, c->stream));
-    const bool exchanged = c->ts_active && c->dist_world > 1 && c->index_exchange;
+    const bool exchanged = c->ts_active && c->exchange();
     if (exchanged) CK(cudaMemcpyAsync(host + 40, reinterpret_cast<uint32_t *>(c->ts_route_cnt.p + kDistMaxWorld) + 4, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->n_edges = host[0];

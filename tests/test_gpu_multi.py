@@ -23,7 +23,7 @@ def run_virtual(db, world, sharded, steps=2, **opt):
     nbytes = dist_buffer_bytes(n, world, 4)
     bufs = [torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device="cuda") for _ in range(world)]
     ptrs = [b.data_ptr() for b in bufs]
-    engs = [Engine(0, tile_rows=1 if sharded else 0, dist_grid_div=world, collect_stats=1, **opt) for _ in range(world)]
+    engs = [Engine(0, tile_rows=1 if sharded else 0, dist_grid_div=world, collect_stats=1, **dict({"index_exchange": 2}, **opt)) for _ in range(world)]
     _l16, _rab, rst = compact_form(db.len, db.abundance)
     per = (n + world - 1) // world
     for r, e in enumerate(engs):
@@ -91,7 +91,7 @@ def test_virtual_ranks_tie_heavy_and_mixed_lengths(built, tmp_path):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for world, sharded, opt in ((2, True, {}), (4, False, {}), (2, False, {"dist_kernel": 1})):
+    for world, sharded, opt in ((2, True, {}), (4, False, {}), (2, False, {"dist_kernel": 1}), (2, False, {"index_exchange": 0})):
         outs = run_virtual(db, world, sharded, steps=1, **opt)
         links = np.concatenate([o[2] for o in outs])
         links = links[np.lexsort((links[:, 1], links[:, 0]))]
