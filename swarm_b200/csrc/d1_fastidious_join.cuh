@@ -35,6 +35,7 @@ struct JoinParams {
   uint64_t cand_cap;
   uint32_t *graft_cand;
   unsigned long long *fstats;    // [0] entries stored [1] lookups [2] candidates [3] verified (ed<=2)
+  uint32_t *overflow;            // set when a chunk produced more candidates than `cands` holds
 };
 
 // 2K bits starting at nucleotide `off`, hashed together with the piece id
@@ -177,60 +178,75 @@ __global__ void __launch_bounds__(256) k_fj_candidates(JoinParams J, uint32_t a_
   }
 }
 
-// heavy pass, step 2: exact decision ed(h, l) <= 2 with a banded (±2) unit-cost DP, one pair per thread.
-// rows = positions of h, band index k <-> column c = r - 2 + k of l.
-__global__ void __launch_bounds__(256) k_fj_verify(JoinParams J, uint64_t m) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const uint2 pr = J.cands[i];
-  const uint32_t a = pr.x, l = pr.y;
-  if (J.graft_cand[l] <= a) return;                                    // already grafted on an earlier heavy amplicon
-  const uint64_t *hw = J.words + static_cast<uint64_t>(a) * J.stride;
-  const uint64_t *lw = J.words + static_cast<uint64_t>(l) * J.stride;
-  const int Lh = static_cast<int>(J.len[a]), Ll = static_cast<int>(J.len[l]);
-  // D[-1][c] = c + 1 (row "-1" is the empty prefix of h): band slots for row 0 hold columns -3..2 of row -1
-  int prev[6];                                                         // prev[k] = D[r-1][c = (r-1) - 2 + k], k = 0..5
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { const int c = -3 + k; prev[k] = (c >= -1 && c < Ll) ? c + 1 : 99; }
-  // window of l's bases: bits 2k = base at column r - 2 + k
-  uint32_t lwin = 0;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { const int c = -2 + k; if (c >= 0 && c < Ll) lwin |= base_at(lw, static_cast<uint32_t>(c)) << (2 * k); }
-  uint64_t hword = 0;
-  bool ok = true;
-  for (int r = 0; r < Lh; ++r) {
-    if ((r & 31) == 0) hword = hw[r >> 5];
-    const uint32_t hb = static_cast<uint32_t>(hword >> ((r & 31) << 1)) & 3u;
-    int rowmin = 99;
-    int cur[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const int c = r - 2 + k;
-      int v = 99;
-      if (c >= 0 && c < Ll) {
-        const int diag = (c == 0) ? r : prev[k];                       // D[r-1][c-1]; for c == 0 it is D[r-1][-1] = r
-        const int up = prev[k + 1];                                    // D[r-1][c]
-        const int lf = (c == 0) ? r + 1 : ((k == 0) ? 99 : cur[k - 1]); // D[r][c-1]; for c == 0 it is D[r][-1] = r + 1
-        const uint32_t lb = (lwin >> (2 * k)) & 3u;
-        v = min(diag + (lb == hb ? 0 : 1), min(up, lf) + 1);
-      }
-      cur[k] = v;
-      rowmin = min(rowmin, v);
-    }
-    if (rowmin > 2) { ok = false; break; }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) prev[k] = cur[k];
-    prev[5] = 99;                                                      // D[r][r+3] is outside the band
-    lwin >>= 2;
-    { const int c = r + 1 + 2; if (c < Ll) lwin |= base_at(lw, static_cast<uint32_t>(c)) << 8; }
+// 32 nucleotides of the packed sequence w starting at position p (zero beyond its words)
+__device__ __forceinline__ uint64_t fj_window(const uint64_t *w, uint32_t stride, uint32_t p) {
+  const uint32_t wi = p >> 5, sh = (p & 31u) << 1;
+  const uint64_t a = wi < stride ? w[wi] : 0ull;
+  if (sh == 0) return a;
+  const uint64_t b = wi + 1 < stride ? w[wi + 1] : 0ull;
+  return (a >> sh) | (b << (64 - sh));
+}
+// longest common extension: how many nucleotides of h[i..) and l[j..) agree, at most cap (32 per step: one XOR of two windows)
+__device__ __forceinline__ int fj_lce(const uint64_t *h, const uint64_t *l, uint32_t stride, int i, int j, int cap) {
+  int n = 0;
+  while (n < cap) {
+    const uint64_t x = fj_window(h, stride, static_cast<uint32_t>(i + n)) ^ fj_window(l, stride, static_cast<uint32_t>(j + n));
+    if (x) { n += (__ffsll(static_cast<long long>(x)) - 1) >> 1; break; }
+    n += 32;
   }
-  if (!ok) return;
-  // result = D[Lh-1][Ll-1], band index of column Ll-1 in row Lh-1 (prev[] holds that row now, shifted by one row)
-  const int kend = (Ll - 1) - (Lh - 1) + 2;
-  int dist = 99;
+  return min(n, cap);
+}
+
+// heavy pass, step 2: exact decision ed(h, l) <= 2, one pair per thread, grid-stride over the candidates counted ON THE DEVICE
+// (no host round trip between the two steps of a chunk).  r1 filled a banded (+-2) unit-cost DP row by row (~9 000
+// instructions a pair, 8.4 of the 10.5 ms of the graft search at 10 M amplicons, profiles/r2r_k_fj_verify); this is the
+// diagonal-wise formulation of the same distance (Landau-Vishkin): fr_e[d] = the furthest row of h reachable on diagonal d
+// (column - row) with e edits; one edit moves to a neighbouring diagonal or one step down, then the path slides along the
+// diagonal for as long as the sequences agree — a longest-common-extension query on the 2-bit packed words.  At most
+// 1 + 3 + 5 diagonal states for e = 0, 1, 2; accepted iff the end (Lh, Ll) is reached.
+__global__ void __launch_bounds__(256) k_fj_verify(JoinParams J) {
+  const uint64_t m = min(*J.cand_count, static_cast<unsigned long long>(J.cand_cap));
+  if (*J.cand_count > J.cand_cap && blockIdx.x == 0 && threadIdx.x == 0) *J.overflow = 1u;
+  const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  unsigned long long verified = 0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m; i += nth) {
+    const uint2 pr = J.cands[i];
+    const uint32_t a = pr.x, l = pr.y;
+    if (J.graft_cand[l] <= a) continue;                                  // already grafted on an earlier heavy amplicon
+    const uint64_t *hw = J.words + static_cast<uint64_t>(a) * J.stride;
+    const uint64_t *lw = J.words + static_cast<uint64_t>(l) * J.stride;
+    const int Lh = static_cast<int>(J.len[a]), Ll = static_cast<int>(J.len[l]);
+    const int dt = Ll - Lh;                                              // the diagonal of the end point, |dt| <= 2 (length filter)
+    constexpr int NONE = -100000;
+    int fr[5] = {NONE, NONE, NONE, NONE, NONE};                          // index d + 2
+    fr[2] = fj_lce(hw, lw, J.stride, 0, 0, min(Lh, Ll));
+    bool ok = dt == 0 && fr[2] >= Lh;
+    for (int e = 1; e <= 2 && !ok; ++e) {
+      int nf[5] = {NONE, NONE, NONE, NONE, NONE};
 #pragma unroll
-  for (int k = 0; k < 5; ++k) if (k == kend) dist = prev[k];
-  if (dist <= 2) atomicMin(&J.graft_cand[l], a);
+      for (int k = 0; k < 5; ++k) {
+        const int d = k - 2;
+        if (d < -e || d > e) continue;
+        int best = fr[k] != NONE ? fr[k] + 1 : NONE;                     // substitution: one step down the same diagonal
+        if (k > 0 && fr[k - 1] != NONE) best = max(best, fr[k - 1]);     // one more base of l: arrive from diagonal d - 1, same row
+        if (k < 4 && fr[k + 1] != NONE) best = max(best, fr[k + 1] + 1); // one more base of h: arrive from diagonal d + 1, next row
+        if (best == NONE) continue;
+        int r = min(best, min(Lh, Ll - d));
+        if (r < 0 || r + d < 0) continue;
+        r += fj_lce(hw, lw, J.stride, r, r + d, min(Lh - r, Ll - (r + d)));
+        nf[k] = r;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) fr[k] = nf[k];
+      ok = fr[dt + 2] >= Lh;
+    }
+    if (ok) { atomicMin(&J.graft_cand[l], a); ++verified; }
+  }
+  if (J.fstats) {
+#pragma unroll
+    for (int mm = 16; mm >= 1; mm >>= 1) verified += __shfl_xor_sync(kFull, verified, mm);
+    if ((threadIdx.x & 31u) == 0 && verified) atomicAdd(&J.fstats[3], verified);
+  }
 }
 
 }  // namespace swb

@@ -1677,27 +1677,30 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
       c->launches++;
       if (c->cands.n == 0) c->cands.alloc(std::max<size_t>(static_cast<size_t>(n) * 4, 1u << 20));
       J.cand_count = c->counters.p + 11;
-      uint32_t chunk = std::max<uint32_t>(1, (n + 15) / 16);
-      for (uint32_t a0 = 0; a0 < n;) {
-        const uint32_t a1 = static_cast<uint32_t>(std::min<uint64_t>(n, static_cast<uint64_t>(a0) + chunk));
-        J.cands = c->cands.p; J.cand_cap = c->cands.n;
-        CK(cudaMemsetAsync(c->counters.p + 11, 0, 8, c->stream));
-        const uint64_t threads = static_cast<uint64_t>(a1 - a0) * 7;
-        k_fj_candidates<<<static_cast<unsigned>(std::min<uint64_t>((threads + 255) / 256, static_cast<uint64_t>(c->sm_count) * 8)), 256, 0, c->stream>>>(J, a0, a1);
-        c->launches++;
-        unsigned long long m = 0;
-        CK(cudaMemcpyAsync(&m, c->counters.p + 11, 8, cudaMemcpyDeviceToHost, c->stream));
+      J.overflow = reinterpret_cast<uint32_t *>(c->counters.p + 48);
+      // heavy amplicons in ascending id chunks (graft_cand[l] <= h prunes the later candidates of l); candidates and verification of
+      // a chunk run back to back, the candidate count stays on the device — the host only looks at an overflow flag at the end
+      uint32_t n_chunks = 16;
+      for (int attempt = 0; attempt < 6; ++attempt) {
+        CK(cudaMemsetAsync(c->counters.p + 48, 0, 8, c->stream));
+        const uint32_t chunk = std::max<uint32_t>(1, (n + n_chunks - 1) / n_chunks);
+        for (uint32_t a0 = 0; a0 < n; a0 += chunk) {
+          const uint32_t a1 = static_cast<uint32_t>(std::min<uint64_t>(n, static_cast<uint64_t>(a0) + chunk));
+          J.cands = c->cands.p; J.cand_cap = c->cands.n;
+          CK(cudaMemsetAsync(c->counters.p + 11, 0, 8, c->stream));
+          const uint64_t threads = static_cast<uint64_t>(a1 - a0) * 7;
+          k_fj_candidates<<<static_cast<unsigned>(std::min<uint64_t>((threads + 255) / 256, static_cast<uint64_t>(c->sm_count) * 8)), 256, 0, c->stream>>>(J, a0, a1);
+          k_fj_verify<<<c->sm_count * 8, 256, 0, c->stream>>>(J);
+          c->launches += 2;
+        }
+        uint32_t ovf = 0;
+        CK(cudaMemcpyAsync(&ovf, c->counters.p + 48, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (m > c->cands.n) {                       // candidate list overflow: retry this range with a smaller chunk / larger buffer
-          if (chunk > 1024) { chunk /= 2; continue; }
-          c->cands.alloc(m + m / 8);
-          continue;
-        }
-        if (m) {
-          k_fj_verify<<<static_cast<unsigned>((m + 255) / 256), 256, 0, c->stream>>>(J, m);
-          c->launches++;
-        }
-        a0 = a1;
+        if (!ovf) break;
+        // a chunk produced more candidates than the buffer holds: what was verified so far stands (every graft written is a real
+        // one and the minimum is taken atomically); go again with smaller chunks and a larger buffer
+        n_chunks *= 4;
+        c->cands.alloc(c->cands.n * 2);
       }
       CK(cudaGetLastError());
     }
