@@ -226,7 +226,9 @@ __device__ __forceinline__ uint32_t tj_pair(const TileJoinParams &J, unsigned lo
                                             uint2 &l1) {
   bool pfx_eq;
   const int cls = tj_classify(ri, tj_len(J, ei), rj, tj_len(J, ej), J.stride, kmask0, kmask1, pfx_eq);
-  if ((tj_key(J, ei) & 1u) && pfx_eq) return 0;          // suffix tile: a pair that also shares the prefix belongs to the prefix tile
+  // a pair that shares the prefix belongs to its prefix tile; a prefix-tile pair whose first K nucleotides differ (the truncated
+  // keys collided) belongs to its suffix tile: every linked pair is emitted exactly once
+  if (((tj_key(J, ei) & 1u) != 0) == pfx_eq) return 0;
   if (STATS) st_x++;
   if (cls == 0) atomicExch(J.dup_flag, 1u);
   if (cls != 1) return 0;

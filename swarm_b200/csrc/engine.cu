@@ -509,6 +509,10 @@ int swb200_load_db_shard(swb200_ctx *c, const uint64_t *words, uint32_t stride_w
     return SWB200_EINVAL;
   }
   if (n_total >= 0xFFFFFFF0u) { g_err = "load_db_shard: too many amplicons"; return SWB200_EINVAL; }
+  {                                     // the in-place all-gather writes shard_world equal shards of ceil(n / world) rows: the shard must be one of them
+    const uint64_t per = (static_cast<uint64_t>(n_total) + c->shard_world - 1) / c->shard_world;
+    if (first % per != 0 || count > per) { g_err = "load_db_shard: [first, first + count) is not a shard of ceil(n / shard_world) rows (set \"shard_world\" first)"; return SWB200_EINVAL; }
+  }
   db_alloc(c, n_total, stride_words);
   c->tic();
   db_upload(c, c->words.p + static_cast<size_t>(first) * stride_words, words, static_cast<size_t>(count) * stride_words * 8);

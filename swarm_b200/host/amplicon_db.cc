@@ -271,7 +271,7 @@ std::atomic<int> g_threads{0};           // 0 = hardware concurrency (at most 32
 unsigned ingest_threads() {
   int t = g_threads.load();
   if (t <= 0) t = static_cast<int>(std::min(32u, std::max(1u, std::thread::hardware_concurrency())));
-  return static_cast<unsigned>(t);
+  return static_cast<unsigned>(std::min(t, 512));       // the sample sort keeps bucket ids in 16 bits and samples 64 x T records
 }
 
 template <typename F>
@@ -638,7 +638,8 @@ static uint64_t ingest_min_bytes() {          // SWARM_B200_INGEST_MIN_BYTES: te
 }
 
 std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db) {
-  const unsigned T = ingest_threads();
+  // no more workers than ~64 KiB of text each: a worker needs records to sample (the sort's splitters) and a range to cut
+  const unsigned T = static_cast<unsigned>(std::min<uint64_t>(ingest_threads(), std::max<uint64_t>(1, size >> 16)));
   if (T > 1 && size >= ingest_min_bytes() && db_parse_parallel(text, size, opt, db, T)) return "";
   return db_parse_serial(text, size, opt, db);
 }

@@ -39,3 +39,11 @@ def built():
     if not (ROOT / "swarm_b200" / "libswarm_b200.so").exists():
         subprocess.run(["make", "-s", "engine"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
     return True
+
+
+def pytest_terminal_summary(terminalreporter):
+    import helpers
+    r = helpers.REF_CHECKS
+    if r["ran"] or r["skipped"]:
+        terminalreporter.write_line(f"reference-binary comparisons inside tests: {r['ran']} ran, {r['skipped']} skipped "
+                                    f"({'oracle/_ref/swarm present' if helpers.have_ref() else 'oracle/_ref/swarm MISSING'})")

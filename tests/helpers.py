@@ -233,6 +233,19 @@ def have_ref() -> bool:
     return REF_BIN.exists() and os.access(REF_BIN, os.X_OK)
 
 
+REF_CHECKS = {"ran": 0, "skipped": 0}
+
+
+def with_ref() -> bool:
+    """gate of the comparisons against the reference binary INSIDE a test: counts them, so that the terminal summary says how
+    many ran and how many were skipped for lack of oracle/_ref/swarm (a silent pass would hide a missing binary)"""
+    if have_ref():
+        REF_CHECKS["ran"] += 1
+        return True
+    REF_CHECKS["skipped"] += 1
+    return False
+
+
 def make_variant_fasta(path, n, L, seed, kmin=3, kmax=60):
     """one abundant seed + n distinct variants, each kmin..kmax random edits (60 % substitutions, 20 % deletions, 20 %
     insertions) away from it: related sequences far apart, the input for large-d tests"""

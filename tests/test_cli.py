@@ -114,7 +114,7 @@ def test_cli_duplicate_sequences_message(built, tmp_path):
     fa.write_bytes(b">a_3\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n>b_2\nACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n")
     mine = subprocess.run([str(CLI), "-o", os.devnull, str(fa)], capture_output=True)
     assert mine.returncode == 1 and b"some fasta entries have identical sequences" in mine.stderr
-    if helpers.have_ref():
+    if helpers.with_ref():
         ref = subprocess.run([str(helpers.REF_BIN), "-o", os.devnull, str(fa)], capture_output=True)
         assert ref.returncode == 1
         assert mine.stderr[mine.stderr.index(b"\nError:"):] == ref.stderr[ref.stderr.index(b"\nError:"):]
@@ -138,7 +138,7 @@ def test_cli_multi_gpu_job_on_shared_device(built, tmp_path, devices):
         outs[tag] = {k: (d / k).read_bytes() for k in "osij"}
     for k in "osij":
         assert outs["one"][k] == outs["multi"][k], k
-    if helpers.have_ref():
+    if helpers.with_ref():
         r = helpers.run_ref(fa, outputs=("o", "s", "i", "j"), threads=4)
         for k in "osij":
             assert outs["multi"][k] == r[k], k

@@ -287,7 +287,7 @@ def test_large_set_properties(built, tmp_path):
     assert np.all(genf[roots] == 0) and np.all(parf[roots] == 0xFFFFFFFF)
     nz = ~roots
     assert np.all(genf[parf[nz].astype(np.int64)] + 1 == genf[nz]) and np.all(swf[parf[nz].astype(np.int64)] == swf[nz])
-    if helpers.have_ref():
+    if helpers.with_ref():
         r = helpers.run_ref(fa, outputs=("o",), threads=8)
         res = D1Result(db, swf, genf, parf)
         assert res.swarms_text() == r["o"]
@@ -346,7 +346,7 @@ def test_fastidious_seeded_vs_oracle(built, tmp_path, n, L, seed, mode_ab, bound
     res_g = D1Result(db, sw, gen, par, graft_cand=gc, boundary=boundary)
     res_o = D1Result(db, orc.swarm_of, orc.generation, orc.parent, graft_cand=orc.graft_cand, boundary=boundary)
     assert res_g.swarms_text() == res_o.swarms_text() and res_g.grafts == grafts
-    if helpers.have_ref():
+    if helpers.with_ref():
         r = helpers.run_ref(fa, "-f", "-b", str(boundary), outputs=("o", "s", "i"), threads=1)
         assert res_g.swarms_text() == r["o"] and res_g.stats_text() == r["s"] and res_g.structure_text() == r["i"]
 
@@ -393,7 +393,7 @@ def test_dn_seeded_vs_oracle_and_reference(built, tmp_path, n, L, seed, mode_ab,
     eng.close()
     assert np.array_equal(sw, osw) and np.array_equal(gen, ogen) and np.array_equal(par, opar) and np.array_equal(pd, opd)
     assert st["dn_links"] >= int(orc.dn_stats[2])      # all directed links vs the greedy loop's accepted ones
-    if helpers.have_ref():
+    if helpers.with_ref():
         r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
         res = DnResult(db, sw, gen, par, pd)
         assert res.swarms_text() == r["o"]
@@ -419,7 +419,7 @@ def test_dn_wide_related_sequences(built, tmp_path, d):
     sw, gen, par, pd = eng.dn_cluster(d)
     eng.close()
     assert np.array_equal(sw, osw) and np.array_equal(gen, ogen) and np.array_equal(par, opar) and np.array_equal(pd, opd)
-    if helpers.have_ref():
+    if helpers.with_ref():
         r = helpers.run_ref(fa, "-d", str(d), outputs=("o", "s", "i"), threads=4)
         res = DnResult(db, sw, gen, par, pd)
         assert res.swarms_text() == r["o"] and res.stats_text() == r["s"] and res.structure_text() == r["i"]

@@ -32,7 +32,7 @@ def test_two_gaps_vs_three_mismatches(built):
     orc = Oracle(db)
     d = orc.nw_diffs(0, 1, scoring())
     ref = None
-    if helpers.have_ref():
+    if helpers.with_ref():
         import tempfile, os
         with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
             f.write(f">a_2\n{a}\n>b_1\n{b}\n".encode())

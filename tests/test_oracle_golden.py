@@ -104,7 +104,7 @@ def test_uclust_cigar_known_answers(built):
         lines = res.uclust_text().decode().splitlines()
         assert lines[0] == "C\t0\t2\t*\t*\t*\t*\t*\ts_9\t*" and lines[1] == "S\t0\t30\t*\t*\t*\t*\t*\ts_9\t*"
         assert lines[2] == f"H\t0\t{len(member)}\t{pct}\t+\t0\t0\t{cigar}\tm_1\ts_9"
-        if helpers.have_ref():
+        if helpers.with_ref():
             import os, tempfile
             with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
                 f.write(text)
@@ -210,7 +210,7 @@ def test_fasta_errors(built, text, msg):
     with pytest.raises(ValueError) as e:
         HostDb(text=text)
     assert msg in str(e.value)
-    if helpers.have_ref():      # the reference prints the same message (src/db.cc)
+    if helpers.with_ref():      # the reference prints the same message (src/db.cc)
         import tempfile, os
         with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
             f.write(text)
