@@ -84,38 +84,3 @@ def test_link_allgather_world2_gloo(built, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert all("ok" in o for o in outs)
-
-
-def test_bench_two_jobs_leg_never_raises():
-    """bench.py's informational "two jobs in flight" leg: threads, result comparison, and every failure mode ends in
-    a dict — it must not be able to take the JSON line down"""
-    import numpy as np
-    import bench
-
-    class Fake:
-        def __init__(self, fail=False):
-            self.fail, self.closed = fail, False
-
-        def close(self):
-            self.closed = True
-
-    def job(e, r):
-        if e.fail:
-            raise RuntimeError("boom")
-        r["swarm_of"][:] = 7
-
-    res = {"swarm_of": np.zeros(4, np.uint32)}
-    made = []
-
-    def make(fail=False):
-        made.append(Fake(fail))
-        return made[-1]
-
-    out = bench.two_jobs_in_flight(make, job, Fake(), res, lambda: {"swarm_of": np.zeros(4, np.uint32)}, 3, 100, lambda: None)
-    assert out["results_identical"] and out["value"] > 0 and made[-1].closed
-    out = bench.two_jobs_in_flight(lambda: make(True), job, Fake(), res, lambda: {"swarm_of": np.zeros(4, np.uint32)}, 3, 100, lambda: None)
-    assert "boom" in out["error"] and made[-1].closed
-
-    def no_engine():
-        raise MemoryError("no engine")
-    assert "no engine" in bench.two_jobs_in_flight(no_engine, job, Fake(), res, dict, 3, 100, lambda: None)["error"]
