@@ -108,6 +108,40 @@ void write_all(std::FILE *f, char *text, uint64_t len) {
   swbh_free(text);
 }
 
+// one line of the reference's progress meter (src/utils/progress.cc:36-80): with -l the finished phase reads "<prompt> 100%";
+// on a terminal the reference rewrites the line in place, of which the first and the last state are printed here
+void phase_line(std::FILE *logf, bool to_file, const char *prompt) {
+  if (to_file) std::fprintf(logf, "%s 100%%\n", prompt);
+  else std::fprintf(logf, "%s 0%%  \r%s 100%%\n", prompt, prompt);
+}
+
+// |V(x)| summed over the amplicons picked by `want`: 3L substitutions + 3L + 4 insertions + one deletion per homopolymer run
+// (src/variants.cc:184-249) — the reference's "Generated ... variants from light swarms" / "Heavy variants" log figures
+template <typename Pick>
+uint64_t count_microvariants(const swbh_db *db, Pick want) {
+  const uint32_t n = swbh_db_count(db), stride = swbh_db_stride_words(db);
+  const uint64_t *words = swbh_db_words(db);
+  const uint32_t *len = swbh_db_lengths(db);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!want(i)) continue;
+    const uint64_t *w = words + static_cast<size_t>(i) * stride;
+    const uint32_t L = len[i];
+    uint64_t runs = 0, prev_top = 0;
+    for (uint32_t k = 0; k * 32 < L; ++k) {
+      const uint64_t x = w[k] ^ ((w[k] << 2) | prev_top);          // base p against base p - 1
+      uint64_t nz = (x | (x >> 1)) & 0x5555555555555555ull;
+      const uint32_t in_word = std::min<uint32_t>(32, L - k * 32);
+      if (in_word < 32) nz &= (1ull << (2 * in_word)) - 1;
+      if (k == 0) nz &= ~1ull;                                     // position 0 opens the first run whatever it holds
+      runs += static_cast<uint64_t>(__builtin_popcountll(nz));
+      prev_top = w[k] >> 62;
+    }
+    total += 6ull * L + 4 + (L ? runs + 1 : 0);
+  }
+  return total;
+}
+
 void engine_check(int status) {
   if (status == SWB200_OK) return;
   if (status == SWB200_EDUPLICATE)                          // same text as src/algod1.cc:1141-1150
@@ -343,6 +377,8 @@ int main(int argc, char **argv) {
   ctx_thread.join();
   if (db_status != 0) fatal(swbh_last_error());
   const uint32_t n = swbh_db_count(db);
+  const bool log_to_file = !P.log.empty();
+  for (const char *prompt : {"Reading sequences:", "Indexing database:", "Abundance sorting:"}) phase_line(logf, log_to_file, prompt);   // src/db.cc:390,477,675
   std::fprintf(logf, "Database info:     %" PRIu64 " nt in %u sequences, longest %u nt\n", swbh_db_nucleotides(db), n, swbh_db_longest(db));
 
   swbh_result *res = nullptr;
@@ -364,14 +400,17 @@ int main(int argc, char **argv) {
       uint64_t clusters = 0;
       engine_check(swb200_d0_dereplicate(ctx, rep.data(), mass.data(), size.data(), singles.data(), &clusters));
       for (swb200_ctx *c : ctxs) swb200_destroy(c);
+      phase_line(logf, log_to_file, "Dereplicating:    ");                 // src/derep.cc:281, :78, :213-251, :195, :153, :129, :111
+      phase_line(logf, log_to_file, "Sorting:          ");
       swbh_derep *dr = nullptr;
       if (swbh_d0_assemble(db, rep.data(), mass.data(), size.data(), singles.data(), &dr) != 0) fatal(swbh_last_error());
       if (swbh_d0_write_swarms(db, dr, P.mothur, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
       write_all(out, text, len);
-      if (seedsf) { if (swbh_d0_write_seeds(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); }
-      if (uclustf) { if (swbh_d0_write_uclust(db, dr, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error()); write_all(uclustf, text, len); }
-      if (structf) { if (swbh_d0_write_structure(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(structf, text, len); }
-      if (statsf) { if (swbh_d0_write_stats(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(statsf, text, len); }
+      phase_line(logf, log_to_file, "Writing swarms:   ");
+      if (seedsf) { if (swbh_d0_write_seeds(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); phase_line(logf, log_to_file, "Writing seeds:    "); }
+      if (uclustf) { if (swbh_d0_write_uclust(db, dr, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error()); write_all(uclustf, text, len); phase_line(logf, log_to_file, "Writing UCLUST:   "); }
+      if (structf) { if (swbh_d0_write_structure(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(structf, text, len); phase_line(logf, log_to_file, "Writing structure:"); }
+      if (statsf) { if (swbh_d0_write_stats(db, dr, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(statsf, text, len); phase_line(logf, log_to_file, "Writing stats:    "); }
       std::fprintf(logf, "\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\nHeaviest swarm:    %" PRIu64 "\n", swbh_derep_clusters(dr),
                    swbh_derep_largest(dr), swbh_derep_heaviest(dr));
       swbh_derep_free(dr);
@@ -386,6 +425,8 @@ int main(int argc, char **argv) {
     if (ctxs.size() > 1 && runs_m != 0 && n >= 8192u * ctxs.size() && swbh_db_longest(db) < 8192) {
       std::vector<uint32_t> links;
       cluster_d1_multi(ctxs, db, P.ncb, run_startm, runs_m, swarm_of, generation, parent, netf ? &links : nullptr);
+      phase_line(logf, log_to_file, "Hashing sequences:");
+      phase_line(logf, log_to_file, "Building network: ");
       if (netf) {                                              // -j: CSR of the union of the ranks' links, rows ascending (src/algod1.cc:755-788)
         std::vector<uint64_t> row_ptr(static_cast<size_t>(n) + 1, 0);
         const uint64_t m = links.size() / 2;
@@ -397,51 +438,116 @@ int main(int argc, char **argv) {
         for (uint32_t i = 0; i < n; ++i) std::sort(col.begin() + static_cast<int64_t>(row_ptr[i]), col.begin() + static_cast<int64_t>(row_ptr[i + 1]));
         if (swbh_write_network(db, row_ptr.data(), col.data(), P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
         write_all(netf, text, len);
+        phase_line(logf, log_to_file, "Dumping network:  ");
       }
+      phase_line(logf, log_to_file, "Clustering:       ");
       if (swbh_d1_assemble(db, swarm_of.data(), generation.data(), parent.data(), nullptr, static_cast<uint64_t>(P.boundary), &res) != 0) fatal(swbh_last_error());
     } else if (P.differences == 1) {
       engine_check(swb200_d1_index(ctx));
+      phase_line(logf, log_to_file, "Hashing sequences:");                  // src/algod1.cc:1129, :1162, :759, :1183
       uint64_t links = 0;
       engine_check(swb200_d1_network(ctx, P.ncb ? 1 : 0, &links));
+      phase_line(logf, log_to_file, "Building network: ");
       if (netf) {
         std::vector<uint64_t> row_ptr(static_cast<size_t>(n) + 1);
         std::vector<uint32_t> col(links ? links : 1);
         engine_check(swb200_d1_get_network(ctx, row_ptr.data(), col.data()));
         if (swbh_write_network(db, row_ptr.data(), col.data(), P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
         write_all(netf, text, len);
+        phase_line(logf, log_to_file, "Dumping network:  ");
       }
       engine_check(swb200_d1_cluster(ctx, swarm_of.data(), generation.data(), parent.data()));
+      phase_line(logf, log_to_file, "Clustering:       ");
       bool grafting = false;
       if (P.fastidious) {
+        // the fastidious block of the log, src/algod1.cc:1291-1475
+        std::vector<uint32_t> sw_size(n, 0);
+        std::vector<uint64_t> sw_mass(n, 0);
+        const uint64_t *ab = swbh_db_abundances(db);
+        const uint32_t *ln = swbh_db_lengths(db);
+        for (uint32_t i = 0; i < n; ++i) { sw_size[swarm_of[i]]++; sw_mass[swarm_of[i]] += ab[i]; }
+        uint64_t swarms_before = 0, light_swarms = 0, light_amps = 0, light_nt = 0;
+        uint32_t largest_before = 0;
+        for (uint32_t i = 0; i < n; ++i)
+          if (swarm_of[i] == i) {
+            ++swarms_before;
+            largest_before = std::max(largest_before, sw_size[i]);
+            if (sw_mass[i] < static_cast<uint64_t>(P.boundary)) { ++light_swarms; light_amps += sw_size[i]; }
+          }
+        for (uint32_t i = 0; i < n; ++i) if (sw_mass[swarm_of[i]] < static_cast<uint64_t>(P.boundary)) light_nt += ln[i];
+        std::fprintf(logf, "\nResults before fastidious processing:\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\n\n", swarms_before, largest_before);
+        phase_line(logf, log_to_file, "Counting amplicons in heavy and light swarms");
+        std::fprintf(logf, "Heavy swarms: %" PRIu64 ", with %" PRIu64 " amplicons\n", swarms_before - light_swarms, n - light_amps);
+        std::fprintf(logf, "Light swarms: %" PRIu64 ", with %" PRIu64 " amplicons\n", light_swarms, light_amps);
+        std::fprintf(logf, "Total length of amplicons in light swarms: %" PRIu64 "\n", light_nt);
         uint64_t nl = 0, nh = 0;
         engine_check(swb200_d1_fastidious(ctx, static_cast<uint64_t>(P.boundary), extra.data(), &nl, &nh));
         grafting = nl != 0 && nh != 0;
+        if (!grafting) {
+          std::fprintf(logf, "Only light or heavy swarms found - no need for further analysis.\n");
+        } else {
+          // the reference sizes a Bloom filter here (bits per entry, k = max(0.4 bits, 1) hash functions, m = 7 x nucleotides x bits,
+          // src/algod1.cc:1337-1392); the engine has no filter to size (the graft search is a join), the line is kept for the log's readers
+          uint64_t bits = static_cast<uint64_t>(P.bloom_bits);
+          uint64_t m = std::max<uint64_t>(light_nt * 7 * bits, 64);
+          const unsigned k = std::max(static_cast<unsigned>(0.4 * static_cast<double>(bits)), 1u);
+          std::fprintf(logf, "Bloom filter: bits=%" PRIu64 ", m=%" PRIu64 ", k=%u, size=%.1fMB\n", bits, m, k, static_cast<double>(m) / (8.0 * 1048576.0));
+          phase_line(logf, log_to_file, "Adding light swarm amplicons to Bloom filter");
+          std::fprintf(logf, "Generated %" PRIu64 " variants from light swarms\n",
+                       count_microvariants(db, [&](uint32_t i) { return sw_mass[swarm_of[i]] < static_cast<uint64_t>(P.boundary); }));
+          phase_line(logf, log_to_file, "Checking heavy swarm amplicons against Bloom filter");
+          std::fprintf(logf, "Heavy variants: %" PRIu64 "\n",
+                       count_microvariants(db, [&](uint32_t i) { return sw_mass[swarm_of[i]] >= static_cast<uint64_t>(P.boundary); }));
+          // the reference counts one candidate per COMMON MICROVARIANT of a (heavy, light) pair; the engine decides pairs (ed <= 2)
+          // and reports how many it verified — the one figure of the log that is not the reference's
+          uint64_t st[12] = {0};
+          swb200_get_stats(ctx, st, 12);
+          std::fprintf(logf, "Got %" PRIu64 " graft candidates\n", st[11]);
+        }
       }
       if (swbh_d1_assemble(db, swarm_of.data(), generation.data(), parent.data(), grafting ? extra.data() : nullptr,
                            static_cast<uint64_t>(P.boundary), &res) != 0) fatal(swbh_last_error());
+      if (grafting) {
+        phase_line(logf, log_to_file, "Grafting light swarms on heavy swarms");
+        std::fprintf(logf, "Made %" PRIu64 " grafts\n\n", swbh_result_grafts(res));
+      }
     } else {
       engine_check(swb200_dn_cluster(ctx, static_cast<uint32_t>(P.differences), P.ncb ? 1 : 0, P.pen, swarm_of.data(), generation.data(),
                                      parent.data(), extra.data()));
+      phase_line(logf, log_to_file, "Find qgram vects: ");                  // src/db.cc:831, src/algo.cc:383
+      phase_line(logf, log_to_file, "Clustering:       ");
       if (swbh_dn_assemble(db, swarm_of.data(), generation.data(), parent.data(), extra.data(), &res) != 0) fatal(swbh_last_error());
     }
     for (swb200_ctx *c : ctxs) swb200_destroy(c);
+    // the writers' progress lines: d = 1 prints one per file (src/algod1.cc:795-1045, order of output_results :1064-1095); d > 1 only
+    // around the seeds, where the reference leaves "Collecting seeds:" without its end of line (src/algo.cc:125,163,188)
+    const bool d1 = P.differences == 1;
     if (swbh_write_swarms(db, res, P.mothur, P.differences, P.usearch, P.append_abundance, &text, &len) != 0) fatal(swbh_last_error());
     write_all(out, text, len);
-    if (seedsf) { if (swbh_write_seeds(db, res, P.usearch, &text, &len) != 0) fatal(swbh_last_error()); write_all(seedsf, text, len); }
+    if (d1) phase_line(logf, log_to_file, "Writing swarms:   ");
+    if (seedsf) {
+      if (swbh_write_seeds(db, res, P.usearch, &text, &len) != 0) fatal(swbh_last_error());
+      write_all(seedsf, text, len);
+      if (!d1) { std::fprintf(logf, "Collecting seeds:    "); phase_line(logf, log_to_file, "Sorting seeds:    "); }
+      phase_line(logf, log_to_file, "Writing seeds:    ");
+    }
     if (structf) {
       if ((P.differences == 1 ? swbh_write_structure(db, res, P.usearch, &text, &len) : swbh_dn_write_structure(db, res, P.usearch, &text, &len)) != 0)
         fatal(swbh_last_error());
       write_all(structf, text, len);
+      if (d1) phase_line(logf, log_to_file, "Writing structure:");
     }
     if (uclustf) {
       if (swbh_write_uclust(db, res, P.differences, P.pen, P.usearch, P.append_abundance, static_cast<int>(P.threads), &text, &len) != 0)
         fatal(swbh_last_error());
       write_all(uclustf, text, len);
+      if (d1) phase_line(logf, log_to_file, "Writing UCLUST:   ");
     }
     if (statsf) {
       if ((P.differences == 1 ? swbh_write_stats(db, res, P.usearch, &text, &len) : swbh_dn_write_stats(db, res, P.usearch, &text, &len)) != 0)
         fatal(swbh_last_error());
       write_all(statsf, text, len);
+      if (d1) phase_line(logf, log_to_file, "Writing stats:    ");
     }
     // src/algod1.cc:1484-1487 / src/algo.cc:699-705
     std::fprintf(logf, "\nNumber of swarms:  %" PRIu64 "\nLargest swarm:     %u\nMax generations:   %u\n", swbh_result_swarms(res), swbh_result_largest(res),

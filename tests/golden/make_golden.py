@@ -192,3 +192,21 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- log text (from "Reading sequences" on) of the reference run with -l, for the command-line tests: see LOG_CASES in tests/test_cli.py
+def make_logs():
+    import os
+    import subprocess
+    import tempfile
+    from test_cli import LOG_CASES
+    for name, flags, tag in LOG_CASES:
+        with tempfile.TemporaryDirectory() as td:
+            fl = [os.path.join(td, f) if len(f) == 1 and f.isupper() else f for f in flags]
+            subprocess.run([str(helpers.REF_BIN), "-l", os.path.join(td, "log"), *fl, str(HERE / f"{name}.fasta")], check=True, capture_output=True)
+            log = open(os.path.join(td, "log"), "rb").read()
+            (HERE / f"{name}.{tag}").write_bytes(log[log.index(b"Reading sequences"):])
+
+
+if __name__ == "__main__" and "logs" in sys.argv[1:]:
+    make_logs()

@@ -142,3 +142,26 @@ def test_cli_multi_gpu_job_on_shared_device(built, tmp_path, devices):
         r = helpers.run_ref(fa, outputs=("o", "s", "i", "j"), threads=4)
         for k in "osij":
             assert outs["multi"][k] == r[k], k
+
+
+# name, flags (single upper-case letters are output files in a scratch directory), golden log suffix
+LOG_CASES = [("c1_1k_150", ["-o", "O", "-s", "S", "-i", "I", "-w", "W", "-u", "U"], "log"), ("c1_1k_150", ["-f", "-t", "1", "-o", "O", "-s", "S"], "f.log"),
+             ("c1_1k_150", ["-d", "2", "-o", "O", "-w", "W", "-s", "S"], "d2.log"), ("c1_1k_150", ["-j", "J", "-r", "-o", "O"], "j.log"),
+             ("c1_1k_150", ["-d", "0", "-o", "O", "-w", "W", "-u", "U", "-i", "I", "-s", "S"], "d0.log"),
+             ("tie_1500_60", ["-f", "-b", "10", "-t", "1", "-o", "O"], "f.b10.log")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,flags,tag", LOG_CASES, ids=[c[2] for c in LOG_CASES])
+def test_cli_log_text_matches_reference(built, tmp_path, name, flags, tag):
+    """the log written with -l: per-phase progress lines, "Database info", the fastidious statistics block and the final summary are
+    the reference's, line for line (src/utils/progress.cc:36-80, src/algod1.cc:1291-1475,1484-1487).  One figure differs by
+    design: "Got N graft candidates" — the reference counts common microvariants per (heavy, light) pair, the engine counts pairs."""
+    fl = [str(tmp_path / f) if len(f) == 1 and f.isupper() else f for f in flags]
+    p = subprocess.run([str(CLI), "-l", str(tmp_path / "log"), *fl, str(GOLDEN / f"{name}.fasta")], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    log = (tmp_path / "log").read_bytes()
+    mine = log[log.index(b"Reading sequences"):].splitlines()
+    want = (GOLDEN / f"{name}.{tag}").read_bytes().splitlines()
+    mask = lambda ls: [b"Got N graft candidates" if l.startswith(b"Got ") and l.endswith(b"graft candidates") else l for l in ls]
+    assert mask(mine) == mask(want)
