@@ -36,6 +36,8 @@ struct JoinParams {
   uint32_t *graft_cand;
   unsigned long long *fstats;    // [0] entries stored [1] lookups [2] candidates [3] verified (ed<=2)
   uint32_t *overflow;            // set when a chunk produced more candidates than `cands` holds
+  unsigned long long *bloom;     // blocked Bloom filter over the light pieces (L2-resident): one 64-bit word, 4 bits per piece
+  uint64_t bloom_words;
 };
 
 // 2K bits starting at nucleotide `off`, hashed together with the piece id
@@ -73,6 +75,15 @@ __global__ void k_fj_flags(const uint32_t *label, const unsigned long long *mass
   }
 }
 
+// Bloom word and pattern of a piece hash.  80 % of the heavy lookups find nothing; the filter (16 bits per light piece, ~11 MB at
+// 10 M amplicons: it stays in L2) answers those without touching the 114 MB multimap (ncu, profiles/r2s_k_fj_candidates: the
+// candidate kernel was bound by the latency of its dependent random reads, 40 % issue slots, 13 cycles of long-scoreboard stall
+// per issue)
+__device__ __forceinline__ uint64_t fj_bloom_word(const JoinParams &J, uint64_t h) { return __umul64hi(h * 0x9E3779B97F4A7C15ull, J.bloom_words); }
+__device__ __forceinline__ unsigned long long fj_bloom_pattern(uint64_t h) {
+  return (1ull << ((h >> 8) & 63u)) | (1ull << ((h >> 14) & 63u)) | (1ull << ((h >> 20) & 63u)) | (1ull << ((h >> 26) & 63u));
+}
+
 // light pass: three K-mer entries per light amplicon
 __global__ void __launch_bounds__(256) k_fj_insert(JoinParams J) {
   const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,6 +95,7 @@ __global__ void __launch_bounds__(256) k_fj_insert(JoinParams J) {
   for (uint32_t piece = 0; piece < 3; ++piece) {
     const uint64_t h = piece_hash(w, J.stride, offs[piece], J.K, piece);
     const unsigned long long val = (h << 32) | a;                      // tag = low 32 bits of the hash
+    atomicOr(&J.bloom[fj_bloom_word(J, h)], fj_bloom_pattern(h));
     uint64_t b = __umul64hi(h, J.n_buckets);
     for (bool placed = false; !placed;) {
       unsigned long long *slot = J.table + b * 4;
@@ -133,6 +145,8 @@ __global__ void __launch_bounds__(256) k_fj_candidates(JoinParams J, uint32_t a_
         tag = static_cast<uint32_t>(h);
         b = __umul64hi(h, J.n_buckets);
         lookups++;
+        const unsigned long long pat = fj_bloom_pattern(h);
+        if ((J.bloom[fj_bloom_word(J, h)] & pat) != pat) walking = false;        // no light amplicon has this piece
       }
     }
     while (__any_sync(kFull, walking)) {

@@ -51,6 +51,8 @@ struct TileStoreParams {
   uint32_t q_cap, out_cap;          // join: pairs queued per pass, links staged per tile before one global atomicAdd
   uint32_t cap, rec_words;          // records per tile slot; words per record: 1 + stride (FAT: entry + packed row) or 1 (slim: the
                                     // join gathers the rows it needs from `words`, which must then hold every amplicon)
+  const unsigned long long *row_base; // INDIRECT records (sharded database): a record is `entry, ref`; ref = word offset of the packed row from
+                                    // row_base (the inbox the row arrived in), or bit 63 + word offset into `words` (this rank's own rows)
   unsigned long long *store;        // (t_hi - t_lo) * cap * rec_words
   uint32_t *cursor;                 // records appended per local tile (beyond cap: overflow list)
   unsigned long long *ovf;          // overflow records: `local tile | previous overflow record of the tile << 32`, then the record
@@ -81,6 +83,16 @@ __device__ __forceinline__ uint32_t ts_key(const TileStoreParams &J, unsigned lo
 __device__ __forceinline__ bool ts_compatible(const TileStoreParams &J, unsigned long long e, unsigned long long f) {
   const uint32_t Le = ts_len(J, e), Lf = ts_len(J, f);
   return ts_key(J, e) == ts_key(J, f) && Le + 1 >= Lf && Lf + 1 >= Le;
+}
+
+constexpr unsigned long long kTsRefLocal = 1ull << 63;
+// packed row of a slim / indirect record (rec[0] = entry, rec[1] = ref when indirect)
+__device__ __forceinline__ const uint64_t *ts_row_of(const TileStoreParams &J, const unsigned long long *rec) {
+  if (J.row_base) {
+    const unsigned long long ref = rec[1];
+    return (ref & kTsRefLocal) ? J.words + (ref & ~kTsRefLocal) : ts_u64(J.row_base + ref);
+  }
+  return J.words + static_cast<uint64_t>(ts_id(J, rec[0]) - J.row_first) * J.stride;
 }
 
 // append one fat record (entry + packed row) to local tile t, or to the overflow list when the slot is full
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(256, OCC) k_ts_join(TileStoreParams J) {
       const uint32_t b = (sdesc[sp] >> 13) & (kTsBuckets - 1);
       if (boff[b + 1] - boff[b] >= 2u) {
         const uint32_t i = order[sp];
-        const uint64_t *w = J.words + static_cast<uint64_t>(ts_id(J, recs[static_cast<size_t>(i) * rw]) - J.row_first) * stride;
+        const uint64_t *w = ts_row_of(J, recs + static_cast<size_t>(i) * rw);
         uint64_t *r = rows + static_cast<size_t>(i) * stride;
         for (uint32_t x = 0; x < stride; ++x) cp_async_8(r + x, w + x);
         if (STATS) st_r++;
@@ -484,8 +496,8 @@ __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
         if (ts_compatible(J, ex, rec[0])) {
           if (STATS) st_p++;
           bool pfx_eq;
-          const uint64_t *rx = FAT ? ts_u64(ox + 2) : J.words + static_cast<uint64_t>(ts_id(J, ex) - J.row_first) * J.stride;
-          const uint64_t *ry = FAT ? ts_u64(rec + 1) : J.words + static_cast<uint64_t>(ts_id(J, rec[0]) - J.row_first) * J.stride;
+          const uint64_t *rx = FAT ? ts_u64(ox + 2) : ts_row_of(J, ox + 1);
+          const uint64_t *ry = FAT ? ts_u64(rec + 1) : ts_row_of(J, rec);
           const int cls = tj_classify(rx, ts_len(J, ex), ry, ts_len(J, rec[0]), J.stride, kmask0, kmask1, pfx_eq);
           mine = ts_links<STATS>(J, ex, rec[0], cls, pfx_eq, st_x, l0, l1);
         }
@@ -508,8 +520,8 @@ __global__ void __launch_bounds__(256) k_ts_big(TileStoreParams J) {
         if (ts_compatible(J, ex, oy[1])) {
           if (STATS) st_p++;
           bool pfx_eq;
-          const uint64_t *rx = FAT ? ts_u64(ox + 2) : J.words + static_cast<uint64_t>(ts_id(J, ex) - J.row_first) * J.stride;
-          const uint64_t *ry = FAT ? ts_u64(oy + 2) : J.words + static_cast<uint64_t>(ts_id(J, oy[1]) - J.row_first) * J.stride;
+          const uint64_t *rx = FAT ? ts_u64(ox + 2) : ts_row_of(J, ox + 1);
+          const uint64_t *ry = FAT ? ts_u64(oy + 2) : ts_row_of(J, oy + 1);
           const int cls = tj_classify(rx, ts_len(J, ex), ry, ts_len(J, oy[1]), J.stride, kmask0, kmask1, pfx_eq);
           mine = ts_links<STATS>(J, ex, oy[1], cls, pfx_eq, st_x, l0, l1);
         }

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(kTsRows) k_ts_route(TsRouteParams R) {
       tl[piece] = tile - owner[piece] * R.tiles_per_rank;
       e[piece] = ts_pack(J, h, piece, L, ab, J.row_first + r);
       if (owner[piece] == R.rank) {                        // my own tile: no detour through the inbox
-        ts_append(J, tl[piece], e[piece], w);
+        const uint64_t ref = kTsRefLocal | (static_cast<uint64_t>(r) * J.stride);      // indirect tiles: the row stays where it is
+        ts_append(J, tl[piece], e[piece], J.row_base ? &ref : w);
         owner[piece] = kNone;
         ++kept_local;
       }
@@ -182,7 +183,12 @@ __global__ void __launch_bounds__(256) k_ts_scatter_inbox(TsRouteParams R) {
       } else {
         t = static_cast<uint32_t>(__ldcg(rec + 1));
       }
-      ts_append(J, t, e, ts_u64(rec + 1));
+      if (J.row_base) {                                   // indirect tiles: the record points at the row in this inbox
+        const uint64_t ref = static_cast<uint64_t>((rec + 1) - J.row_base);
+        ts_append(J, t, e, &ref);
+      } else {
+        ts_append(J, t, e, ts_u64(rec + 1));
+      }
       ++kept;
     }
   }
@@ -195,10 +201,19 @@ __global__ void __launch_bounds__(256) k_ts_scatter_inbox(TsRouteParams R) {
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(R.done_ctas + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
   __syncthreads();
-  if (is_last && threadIdx.x < R.world) {
+  if (is_last && threadIdx.x < R.world && !J.row_base) {      // (indirect tiles keep reading the inbox until the join is done: k_ts_release)
     *reinterpret_cast<volatile unsigned long long *>(&ts_ctl(R, threadIdx.x)->freed[R.rank]) = R.epoch;
     __threadfence_system();
     if (threadIdx.x == 0) R.done_ctas[1] = 0;
+  }
+  if (is_last && threadIdx.x == 0 && J.row_base) R.done_ctas[1] = 0;
+}
+
+// indirect tiles: the join has read the rows out of the inbox; tell every sender it may be overwritten by the next epoch
+__global__ void __launch_bounds__(32) k_ts_release(TsRouteParams R) {
+  if (threadIdx.x < R.world) {
+    *reinterpret_cast<volatile unsigned long long *>(&ts_ctl(R, threadIdx.x)->freed[R.rank]) = R.epoch;
+    __threadfence_system();
   }
 }
 

@@ -153,6 +153,7 @@ struct swb200_ctx {
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
   DevBuf<uint8_t> is_light;
+  DevBuf<unsigned long long> fj_bloom;
   DevBuf<uint2> cands;
   DevBuf<unsigned long long> jtab;   // K-mer multimap of the JOIN network
   uint64_t jtab_buckets = 0, jb_lo = 0, jb_hi = 0;
@@ -323,7 +324,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release(); c->cl_bits.release();
   c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->dist_lcnt.release(); c->dist_links.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
-  c->is_light.release(); c->cands.release(); c->jtab.release();
+  c->is_light.release(); c->fj_bloom.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
   c->run_start_d.release(); c->ts_route_cnt.release(); c->dist_own.release();
   c->bk_flag.release(); c->bk_count.release(); c->bk_off.release(); c->bk_links.release(); c->bk_unit.release(); c->bk_act.release();
@@ -609,7 +610,10 @@ static TileStoreParams ts_params(swb200_ctx *c) {
   while (idb < 32 && (1ull << idb) < c->n) ++idb;
   J.id_bits = idb; J.sorted_desc = c->sorted_desc ? 1 : 0; J.ncb = c->ncb;
   J.n_tiles = c->ts_tiles; J.t_lo = c->ts_lo; J.t_hi = c->ts_hi;
-  J.cap = c->ts_cap; J.rec_words = c->ts_fat ? c->stride + 1 : 1;
+  // tile record: 8-byte entry (slim: rows gathered from the database), entry + packed row (fat), or — sharded database — entry + a
+  // reference to the row where it lies: in the inbox it arrived in, or among this rank's own rows
+  J.cap = c->ts_cap; J.rec_words = c->db_sharded ? 2 : (c->ts_fat ? c->stride + 1 : 1);
+  J.row_base = c->db_sharded && c->dist_world ? reinterpret_cast<const unsigned long long *>(c->dist_peer[c->dist_rank] + kDistCtlBytes) : nullptr;
   J.q_cap = c->ts_qcap; J.out_cap = c->ts_outcap;
   J.store = c->ts_store.p; J.cursor = c->ts_cursor.p; J.ovf_head = c->ts_cursor.p + (c->ts_hi - c->ts_lo);
   J.ovf = c->ts_ovf.p; J.ovf_count = c->counters.p + 32; J.ovf_cap = c->ts_ovf_cap;
@@ -627,8 +631,8 @@ static TileStoreParams ts_params(swb200_ctx *c) {
 
 // tile geometry + every buffer of the tile-store path (no stream work: swb200_d1_reserve calls it ahead of time)
 static uint32_t ts_prepare(swb200_ctx *c) {
-  const uint32_t rw = c->ts_fat ? c->stride + 1 : 1;
-  const uint32_t rec_bytes = 8 * (c->stride + 1);                // shared memory per record either way: entry + row
+  const uint32_t rw = c->db_sharded ? 2 : (c->ts_fat ? c->stride + 1 : 1);
+  const uint32_t rec_bytes = 8 * (c->stride + 1) + (c->db_sharded ? 8 : 0);      // shared memory per record either way: entry (+ reference) + row
   uint32_t cap = std::min<uint32_t>(512, (36u * 1024u) / rec_bytes) & ~1u;      // 512 x 48 B: five CTAs of the join per SM (measured best, profiles/r2h)
   cap = std::max<uint32_t>(cap, 64);
   if (c->ts_cap_opt >= 64) cap = std::min(cap, c->ts_cap_opt & ~1u);
@@ -918,12 +922,19 @@ int swb200_d1_network(swb200_ctx *c, int no_cluster_breaking, uint64_t *n_links)
         };
         auto pick = [&](auto occ) {
           constexpr int O = decltype(occ)::value;
-          if (c->ts_fat) { if (c->collect_stats) launch(k_ts_join<true, true, O>, k_ts_big<true, true>); else launch(k_ts_join<true, false, O>, k_ts_big<true, false>); }
+          if (c->ts_fat && !c->db_sharded) { if (c->collect_stats) launch(k_ts_join<true, true, O>, k_ts_big<true, true>); else launch(k_ts_join<true, false, O>, k_ts_big<true, false>); }
           else { if (c->collect_stats) launch(k_ts_join<false, true, O>, k_ts_big<false, true>); else launch(k_ts_join<false, false, O>, k_ts_big<false, false>); }
         };
         if (c->ts_occ >= 6) pick(std::integral_constant<int, 6>{});
         else if (c->ts_occ == 5) pick(std::integral_constant<int, 5>{});
         else pick(std::integral_constant<int, 4>{});
+        if (c->db_sharded) {                       // the rows were read out of the inbox: the senders may overwrite it (next epoch)
+          TsRouteParams R{};
+          R.rank = c->dist_rank; R.world = c->dist_world; R.epoch = c->idx_epoch;
+          for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
+          k_ts_release<<<1, 32, 0, c->stream>>>(R);
+          c->launches += 1;
+        }
         c->launches += 2;
         CK(cudaGetLastError());
       }
@@ -1676,6 +1687,11 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
       const uint64_t slots = std::max<uint64_t>(64, (static_cast<uint64_t>(counts[0]) * 3 * 5 / 2 + 3) / 4 * 4);
       c->t2.alloc(slots);
       J.table = c->t2.p; J.n_buckets = slots / 4;
+      uint64_t bwords = 1024;
+      while (bwords < static_cast<uint64_t>(counts[0]) * 3 / 4) bwords <<= 1;       // >= 16 bits per light piece
+      c->fj_bloom.alloc(bwords);
+      J.bloom = c->fj_bloom.p; J.bloom_words = bwords;
+      CK(cudaMemsetAsync(c->fj_bloom.p, 0, bwords * 8, c->stream));
       CK(cudaMemsetAsync(c->t2.p, 0xFF, slots * 8, c->stream));
       k_fj_insert<<<vb, 256, 0, c->stream>>>(J);
       c->launches++;
