@@ -26,7 +26,9 @@ struct TsCtl {
   unsigned long long cnt[kDistMaxWorld];          // [sender] records routed into this rank's inbox in the current epoch
   unsigned long long ready[kDistMaxWorld];        // [sender] epoch whose records (and count) have all been written
   unsigned long long freed[kDistMaxWorld];        // [receiver] epoch that receiver has finished reading out of ITS inbox ...
-};                                                // ... (written into every sender's control block)
+                                                  // ... (written into every sender's control block)
+  unsigned long long cl_ready[kDistMaxWorld];     // [peer] clustering call that peer is about to launch (k_dist_rendezvous)
+};
 constexpr size_t kTsCtlOffset = 2048;             // inside the kDistCtlBytes control area
 
 struct TsRouteParams {
@@ -214,6 +216,24 @@ __global__ void __launch_bounds__(32) k_ts_release(TsRouteParams R) {
   if (threadIdx.x < R.world) {
     *reinterpret_cast<volatile unsigned long long *>(&ts_ctl(R, threadIdx.x)->freed[R.rank]) = R.epoch;
     __threadfence_system();
+  }
+}
+
+// Ranks that SHARE one GPU (tests, swb200_dist_setup_local with repeated devices): the persistent clustering kernel of a rank
+// fills its share of every SM and spins on the cross-rank barrier, so a peer that is still hashing or joining may not get an SM in
+// a compatible shared-memory configuration — without the index exchange nothing else keeps the ranks in step.  One warp announces
+// "about to cluster, call `epoch`" to every peer and waits for all of them; stream order holds the clustering kernel back.
+__global__ void __launch_bounds__(32) k_dist_rendezvous(TsRouteParams R) {
+  const uint32_t lane = threadIdx.x;
+  if (lane >= R.world) return;
+  *reinterpret_cast<volatile unsigned long long *>(&ts_ctl(R, lane)->cl_ready[R.rank]) = R.epoch;
+  __threadfence_system();
+  volatile unsigned long long *w = &ts_ctl(R, R.rank)->cl_ready[lane];
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  while (*w < R.epoch) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 5000000000ull) { R.err[0] = 1u; break; }
   }
 }
 

@@ -1438,7 +1438,8 @@ int swb200_d1_reserve(swb200_ctx *c) {
                            reinterpret_cast<const void *>(k_ts_join<false, true, 6>), reinterpret_cast<const void *>(k_ts_join<false, false, 6>),
                            reinterpret_cast<const void *>(k_ts_big<true, true>), reinterpret_cast<const void *>(k_ts_big<true, false>),
                            reinterpret_cast<const void *>(k_ts_big<false, true>), reinterpret_cast<const void *>(k_ts_big<false, false>),
-                           reinterpret_cast<const void *>(k_cluster_dist), reinterpret_cast<const void *>(k_cluster_bucket)};
+                           reinterpret_cast<const void *>(k_cluster_dist), reinterpret_cast<const void *>(k_cluster_bucket),
+                           reinterpret_cast<const void *>(k_ts_release), reinterpret_cast<const void *>(k_dist_rendezvous)};
   for (const void *k : kernels) {
     cudaFuncAttributes attr;
     CK(cudaFuncGetAttributes(&attr, k));
@@ -1486,6 +1487,12 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   c->tic();
   void *args_d[] = {&D}, *args_b[] = {&B};
   if (c->dist_grid_div > 1) {                       // ranks sharing one GPU: cooperative kernels are never co-scheduled
+    TsRouteParams R{};                              // ... and the ranks line up first (k_dist_rendezvous says why)
+    R.rank = D.rank; R.world = D.world; R.epoch = c->dist_calls;
+    for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
+    R.err = D.lflags + 3;                           // a peer that never shows up is the barrier's error
+    k_dist_rendezvous<<<1, 32, 0, c->stream>>>(R);
+    c->launches++;
     if (c->dist_kernel == 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);
     else k_cluster_bucket<<<grid, 256, dyn, c->stream>>>(B);
   } else {
