@@ -416,9 +416,10 @@ def main():
             "network": {"kernel": "k_ts_join (+ k_ts_big, idle on this data)", "s": avg[2], "bytes": 2 * n * 8 + rows_ * P_ + 8 * e_,
                         "formula": "every tile entry read once by TMA, one packed row per entry that has a bucket mate (counted), links written",
                         "rows_gathered_per_amplicon": rows_ / n},
-            "cluster": {"kernel": "k_cluster_persistent", "s": avg[3], "bytes": n * 28 + st["cluster_rounds"] * 8 * e_ + 24 * e_, "rounds": st["cluster_rounds"],
-                        "formula": "key + parent initialised, label + generation written, the 8-byte link list re-read every round, parent pass (link + two keys); "
-                                   "relaxation traffic (two random keys per ACTIVE link) not counted: a lower bound"},
+            "cluster": {"kernel": "k_cluster_persistent", "s": avg[3], "bytes": n * 28 + st["cluster_rounds"] * 8 * e_, "rounds": st["cluster_rounds"],
+                        "formula": "packed relaxation word initialised (8 B), label + generation + parent written (12 B) and the word read once more for that (8 B) "
+                                   "per amplicon; the 8-byte link list re-read every round; relaxation traffic (two random words per ACTIVE link) "
+                                   "not counted: a lower bound"},
         }
         if args.join_kernel != 0 or args.enum_mode != 2 or args.cluster_kernel != 0:
             for k in ph:

@@ -72,6 +72,10 @@ const char *swb200_last_error(void);
  * 6 links bucketed by source block, inactive buckets skipped, d1_bucket.cuh (the multi-GPU kernel run on one GPU);
  * 4 frontier bitmap over 8-slot out-rows, d1_frontier.cuh;
  * 3 links counting-sorted by source; 2 one launch per round; 1 label propagation then BFS — same result),
+ * "cluster_pack" (1 default: kernels 0 and 6 and the multi-GPU kernel relax ONE 64-bit word swarm | generation | parent, so
+ * the parent is settled by the same atomicMin and no parent pass is needed; used while the ids leave >= 10 generation bits,
+ * i.e. up to 2^27 amplicons, and redone with 32-bit generations if a swarm is deeper than that; 0 = key + parent pass),
+ * "cluster_gen_bits" (test hook: cap on the generation bits of the packed word),
  * "dist_kernel" (multi-GPU clustering: 0 the bucketed kernel, 1 r1's k_cluster_dist), "dn_filter" (0 auto,
  * 1 all-pairs q-gram filter),
  * "shard_rank"/"shard_world" (this context's share of the network build, SURVEY.md §8e: in JOIN mode the
@@ -213,7 +217,8 @@ double swb200_phase_device_seconds(swb200_ctx *ctx, int phase);
 /* Counters of the last network build (collect_stats=1): [0] variants probed, [1] filter passes,
  * [2] table slots visited, [3] exact comparisons, [4] links, [5] kernel launches since create, [6] packed sequences gathered into shared memory (tile join), [7] rounds of the last swb200_d1_cluster; [8..11] fastidious: light variants stored, heavy variants probed, tag matches, verified matches;
  * [12..15] d>1: q-gram comparisons, alignments, alignments pruned early, accepted links; [16] tile-store records that
- * overflowed their tile slot in the last index, [17] times the network fell back to the enumeration (skew_fallback). */
+ * overflowed their tile slot in the last index, [17] times the network fell back to the enumeration (skew_fallback),
+ * [18] times the clustering was redone with 32-bit generations (a swarm deeper than the packed word holds, "cluster_pack"). */
 int  swb200_get_stats(swb200_ctx *ctx, uint64_t *out, int n);
 
 /* Test hook: enumerate the microvariants of amplicon `seed` on the device exactly as the network

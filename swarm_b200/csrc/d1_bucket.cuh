@@ -36,6 +36,7 @@ struct BucketParams {
   uint32_t *act_list;                             // units to walk in the current round
   uint32_t *act_n;                                // [2] rotating counters of act_list
   uint64_t unit_cap;
+  uint32_t ib, gb;                                // PACK: bits of an amplicon id / of the generation in the packed word (d1_kernels.cuh)
 };
 
 // position of the first block whose links start after link p (boff is non-decreasing): block of link p
@@ -46,15 +47,6 @@ __device__ __forceinline__ uint32_t bk_block_of(const BucketParams &B, unsigned 
     if (B.boff[mid] <= p) lo = mid; else hi = mid;
   }
   return lo;
-}
-
-// offer cand to the owned amplicon with local index lv; a lowered key marks it (and its block) for the next round
-__device__ __forceinline__ bool bk_offer_local(const BucketParams &B, uint32_t *wr, uint32_t lv, unsigned long long cand) {
-  if (cand < B.D.key[lv] && atomicMin(&B.D.key[lv], cand) > cand) {
-    atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
-    return true;
-  }
-  return false;
 }
 
 // CTA-collective: every thread holds U links; those with a remote destination (own[k] is another rank) append the record
@@ -105,9 +97,27 @@ __device__ __forceinline__ bool bk_send_unit(const BucketParams &B, unsigned lon
   return true;
 }
 
+// PACK: the relaxed word is swarm << (gb + ib) | generation << ib | parent and an offer is ((word[u] >> ib) + 1) << ib | u — the
+// atomicMin that lowers the key settles the parent too (k_cluster_persistent in d1_kernels.cuh explains why that is the closed
+// form), so the tail no longer re-reads the links and the whole message log to find the parents (0.26 of 2.9 ms at 8 GPUs).  A
+// final generation of 2^gb - 1 or more raises lflags[6]; the last barrier ORs it over the ranks and the host runs the unpacked kernel.
+template <bool PACK>
 __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   const DistParams &D = B.D;
   const SwGrid grid{D.gbar};
+  const uint32_t ib = B.ib, gb = B.gb;
+  const unsigned long long idmask = PACK ? (1ull << ib) - 1ull : 0ull;
+  const unsigned long long gmask = PACK ? (gb >= 32 ? 0xFFFFFFFFull : (1ull << gb) - 1ull) : 0ull;
+  // offer of source u whose relaxed word is `ws`: its key part plus one, u in the parent field (a generation that wraps into the
+  // swarm field is caught when the words are unpacked, see k_cluster_persistent)
+  auto offer_of = [&](unsigned long long ws, uint32_t u) -> unsigned long long {
+    return PACK ? (((ws | idmask) + 1ull) | u) : ws + 1ull;
+  };
+  // atomicMin of an offer into the owned amplicon lv; true when its KEY went down (its out-links must be offered again)
+  auto lower = [&](uint32_t lv, unsigned long long cand) -> bool {
+    const unsigned long long old = atomicMin(&D.key[lv], cand);
+    return PACK ? (old | idmask) > (cand | idmask) : old > cand;
+  };
   __shared__ DistSmem sm;
   __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
   __shared__ unsigned long long s_prev[kDistMaxWorld], s_cur[kDistMaxWorld];
@@ -128,12 +138,12 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   // ---- init (local); multi-GPU: route the links this rank's join found to the owners of their sources
   for (uint64_t l = tid; l < D.n_local; l += nth) {
     const uint32_t v = dist_global(D, static_cast<uint32_t>(l));
-    D.key[l] = static_cast<unsigned long long>(v) << 32;
-    if (v < D.n) D.parent[v] = kNone;
+    D.key[l] = PACK ? ((static_cast<unsigned long long>(v) << (gb + ib)) | idmask) : (static_cast<unsigned long long>(v) << 32);
+    if (!PACK && v < D.n) D.parent[v] = kNone;
   }
   for (uint64_t w = tid; w < 3ull * D.nwords; w += nth) D.bits[w] = 0;
   for (uint64_t w = tid; w < B.nblk; w += nth) B.bcount[w] = 0;
-  if (tid == 0) { lflags[0] = 0; lflags[1] = 0; lflags[2] = 0; lflags[3] = 0; }
+  if (tid == 0) { lflags[0] = 0; lflags[1] = 0; lflags[2] = 0; lflags[3] = 0; lflags[6] = 0; }
   if (multi) {
     uint2 *sorted = reinterpret_cast<uint2 *>(dist_dyn);
     for (uint64_t base = static_cast<uint64_t>(blockIdx.x) * kDistChunk; base < D.m_local; base += static_cast<uint64_t>(gridDim.x) * kDistChunk) {
@@ -260,18 +270,18 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
       }
 #pragma unroll
       for (int k = 0; k < U; ++k) kd[k] = lv[k] != kNone ? D.key[lv[k]] : 0ull;
+      unsigned long long cand0[U];                                    // key[src] still has its initial value: swarm src, generation 0
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        cand0[k] = offer_of(PACK ? ((static_cast<unsigned long long>(ed[k].x) << (gb + ib)) | idmask) : (static_cast<unsigned long long>(ed[k].x) << 32), ed[k].x);
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const unsigned long long cand = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;   // key[src] is still src << 32
-        if (lv[k] != kNone && cand < kd[k] && atomicMin(&D.key[lv[k]], cand) > cand) {
+        if (lv[k] != kNone && cand0[k] < kd[k] && lower(lv[k], cand0[k])) {
           atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
           ch = 1;
         }
       }
       if (multi) {
-        unsigned long long cand0[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) cand0[k] = (static_cast<unsigned long long>(ed[k].x) << 32) + 1ull;
         if (bk_send_unit<U>(B, counters, s_cnt, s_base, own, ed, cand0, lane)) ch = 1;
       }
       if (smem_hist) {
@@ -336,8 +346,9 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         unsigned long long cand[U], kd[U];
         uint32_t own[U], lv[U];
 #pragma unroll
+        for (int k = 0; k < U; ++k) cand[k] = act[k] ? offer_of(D.key[lu[k]], ed[k].x) : ~0ull;
+#pragma unroll
         for (int k = 0; k < U; ++k) {
-          cand[k] = (act[k] ? D.key[lu[k]] : ~0ull) + 1ull;
           own[k] = act[k] ? (multi ? dist_owner(D, ed[k].y) : D.rank) : kNone;
           lv[k] = own[k] == D.rank ? dist_local(D, ed[k].y) : kNone;
         }
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         for (int k = 0; k < U; ++k) kd[k] = lv[k] != kNone ? D.key[lv[k]] : 0ull;
 #pragma unroll
         for (int k = 0; k < U; ++k)
-          if (lv[k] != kNone && cand[k] < kd[k] && atomicMin(&D.key[lv[k]], cand[k]) > cand[k]) {
+          if (lv[k] != kNone && cand[k] < kd[k] && lower(lv[k], cand[k])) {
             atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
             ch = 1;
           }
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
             if (raw[k].x == kNone) continue;
             const uint32_t lv = dist_local(D, raw[k].x);
             const unsigned long long cand = (static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z;
-            if (cand < kv[k] && atomicMin(&D.key[lv], cand) > cand) {
+            if (cand < kv[k] && lower(lv, cand)) {
               atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
             }
           }
@@ -397,8 +408,8 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
     }
   }
 
-  // ---- parents: smallest u among the in-links that offer exactly the final key — local links, then the message log
-  for (uint64_t base = tid; base < m; base += nth * kDistU) {
+  // ---- parents (unpacked word only): smallest u among the in-links that offer exactly the final key — local links, then the message log
+  for (uint64_t base = tid; !PACK && base < m; base += nth * kDistU) {
     uint2 ed[kDistU];
     unsigned long long ku[kDistU], kv[kDistU];
 #pragma unroll
@@ -416,7 +427,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
     for (int k = 0; k < kDistU; ++k)
       if (ed[k].x != kNone && ku[k] + 1ull == kv[k]) atomicMin(&D.parent[ed[k].y], ed[k].x);
   }
-  if (multi) {
+  if (multi && !PACK) {
     for (uint32_t s = 0; s < D.world; ++s) {
       if (s == D.rank) continue;
       const DistRec *in = dist_upd(D, D.rank, s);
@@ -441,13 +452,22 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
     const uint32_t v = dist_global(D, static_cast<uint32_t>(l));
     if (v >= D.n) continue;
     const unsigned long long kv = D.key[l];
-    D.label[v] = static_cast<uint32_t>(kv >> 32);
-    D.generation[v] = static_cast<uint32_t>(kv);
+    if (PACK) {
+      D.label[v] = static_cast<uint32_t>(kv >> (gb + ib));
+      D.generation[v] = static_cast<uint32_t>((kv >> ib) & gmask);
+      if (((kv >> ib) & gmask) == gmask) lflags[6] = 1;          // deeper than the packed word holds
+      D.parent[v] = (kv & idmask) == idmask ? kNone : static_cast<uint32_t>(kv & idmask);
+    } else {
+      D.label[v] = static_cast<uint32_t>(kv >> 32);
+      D.generation[v] = static_cast<uint32_t>(kv);
+    }
   }
   if (tid == 0) lflags[4] = round + 1;
+  if (PACK && !multi) grid.sync();                                 // lflags[6] complete before the host reads it
   if (multi) {
-    // nobody starts the next call (and appends to an inbox) before every rank has finished reading its own
-    dist_barrier(D, grid, ++epoch, lflags + 3, nullptr, 0);
+    // nobody starts the next call (and appends to an inbox) before every rank has finished reading its own; the barrier also
+    // tells every rank whether ANY rank met a generation the packed word cannot hold (result in lflags[5])
+    dist_barrier(D, grid, ++epoch, lflags + 6, nullptr, 0);
     if (tid < 2 * kDistMaxWorld) D.lcnt[tid] = 0;            // this sender's counters restart with the next call
   }
   dist_stamp(D, tid, tslot);                                 // parents + unpack (+ last barrier)

@@ -598,20 +598,41 @@ __global__ void k_key_unpack(const unsigned long long *key, uint32_t *label, uin
 // key[] (80 MB) out of the 126 MB L2: the working set of this kernel sits right at the L2's capacity, and without the
 // hints the same binary measured 1.1 ms on one box and 2.7 ms on another (gpurun_out/r1s vs r1u).
 constexpr int kClU = 8;
-template <bool HINT>
-__global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *parent,
+// PACK (default whenever 2 * id_bits + 10 <= 64, i.e. up to 2^27 amplicons): the relaxed word is
+//   swarm << (gb + ib) | generation << ib | parent        (ib = bits of an amplicon id, gb = min(32, 64 - 2 ib))
+// and the offer of link u -> v is ((word[u] >> ib) + 1) << ib | u, so ONE 64-bit atomicMin settles the parent together with the
+// key: the lexicographic minimum over (swarm, generation, u) is exactly parent[v] = min { u : u -> v, key[u] + 1 == key[v] }
+// (every in-neighbour's LAST offer carries its final key, earlier ones were larger).  The separate parent pass — the link list and
+// two random keys per link once more, 0.13 of 1.1 ms at 10 M — disappears.  A vertex is marked "lowered" only when its KEY part
+// went down (a smaller parent under the same key changes nothing for its out-links).  A swarm deeper than gb bits hold (a final
+// generation of 2^gb - 1 or more) raises bit 31 of *rounds_out and the host runs the unpacked kernel instead (engine.cu: run_cluster).
+// COARSE: what bounds the late rounds is not the 70 MB link list but the test "was this link's source lowered last round?" — one
+// 4-byte read per link at a random address of the 1.25 MB bitmap: 8.8 M L1TEX gather wavefronts, ~30 us a round however few
+// amplicons still move (profiles/r1b_gather_microbench.txt: one wavefront per clock and SM).  So every round first folds the
+// bitmap into one bit per 2^cs amplicons (a warp per coarse word, ~10 KB in all), every CTA copies that into SHARED memory, and a
+// link only goes to the fine bitmap when its source's coarse bit is set: in the late rounds > 90 % of the links stop at a
+// shared-memory lookup (random 4-byte reads over 32 banks: ~3 wavefronts per warp instead of 32).  Costs one more grid barrier a round.
+template <bool HINT, bool PACK, bool COARSE>
+__global__ void __launch_bounds__(256, 4) k_cluster_persistent(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *parent,
                                                             uint32_t *label, uint32_t *generation, uint32_t n,
                                                             volatile uint32_t *flags, uint32_t *rounds_out, uint32_t *bits,
-                                                            uint32_t nwords) {
+                                                            uint32_t nwords, uint32_t ib, uint32_t gb,
+                                                            uint32_t *coarse_g, uint32_t cs, uint32_t n_cw) {
+  extern __shared__ uint32_t cl_coarse[];                          // COARSE: n_cw words
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned long long idmask = PACK ? (1ull << ib) - 1ull : 0ull;
+  const unsigned long long gmask = PACK ? (gb >= 32 ? 0xFFFFFFFFull : (1ull << gb) - 1ull) : 0ull;
   for (uint64_t v = tid; v < n; v += nth) {
-    key[v] = static_cast<unsigned long long>(v) << 32;
-    if (HINT) __stcs(&parent[v], kNone); else parent[v] = kNone;
+    if (PACK) key[v] = (static_cast<unsigned long long>(v) << (gb + ib)) | idmask;
+    else {
+      key[v] = static_cast<unsigned long long>(v) << 32;
+      if (HINT) __stcs(&parent[v], kNone); else parent[v] = kNone;
+    }
   }
   for (uint64_t w = tid; w < 3ull * nwords; w += nth) bits[w] = 0;
-  if (tid == 0) { flags[0] = 0; flags[1] = 0; flags[2] = 0; }
+  if (tid == 0) { flags[0] = 0; flags[1] = 0; flags[2] = 0; flags[3] = 0; }
   grid.sync();
   uint32_t round = 0;
   for (;; ++round) {
@@ -620,6 +641,20 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
     uint32_t *cl = bits + static_cast<size_t>((round + 2) % 3) * nwords;
     if (tid == 0) flags[(round + 1) % 3] = 0;
     if (round) for (uint64_t w = tid; w < nwords; w += nth) cl[w] = 0;
+    if (COARSE && round) {
+      // one coarse bit per 2^cs amplicons = 2^(cs-5) bitmap words (the bitmaps are padded with zero words to whole coarse words)
+      const uint32_t fw = 1u << (cs - 5u), lane = threadIdx.x & 31u;
+      for (uint64_t cw = tid >> 5; cw < n_cw; cw += nth >> 5) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(rd + ((cw * 32u + lane) << (cs - 5u)));
+        uint32_t acc = 0;
+        for (uint32_t q = 0; q < fw / 4u; ++q) { const uint4 x = src[q]; acc |= x.x | x.y | x.z | x.w; }
+        const uint32_t word = __ballot_sync(kFull, acc != 0u);
+        if (lane == 0) coarse_g[cw] = word;
+      }
+      grid.sync();
+      for (uint32_t w = threadIdx.x; w < n_cw; w += blockDim.x) cl_coarse[w] = __ldcg(&coarse_g[w]);
+      __syncthreads();
+    }
     int ch = 0;
     // kClU links per thread and step, loads issued stage by stage (links, bitmap words, keys): the loop is a chain
     // of dependent random reads, and one link at a time left each warp with a single request in flight
@@ -633,6 +668,10 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
         ed[k] = act[k] ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(0u, 0u);
       }
       if (round) {
+        if (COARSE) {
+#pragma unroll
+          for (int k = 0; k < kClU; ++k) act[k] = act[k] && ((cl_coarse[ed[k].x >> (cs + 5u)] >> ((ed[k].x >> cs) & 31u)) & 1u);
+        }
         uint32_t w[kClU];
 #pragma unroll
         for (int k = 0; k < kClU; ++k) w[k] = act[k] ? rd[ed[k].x >> 5] : 0u;
@@ -642,14 +681,26 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
       unsigned long long ks[kClU], kd[kClU];
 #pragma unroll
       for (int k = 0; k < kClU; ++k) {
-        ks[k] = act[k] ? key[ed[k].x] : ~0ull;
+        // round 0: every source still has its initial word — no load
+        if (round == 0) ks[k] = PACK ? ((static_cast<unsigned long long>(ed[k].x) << (gb + ib)) | idmask) : (static_cast<unsigned long long>(ed[k].x) << 32);
+        else ks[k] = act[k] ? key[ed[k].x] : ~0ull;
         kd[k] = act[k] ? key[ed[k].y] : 0ull;
       }
 #pragma unroll
       for (int k = 0; k < kClU; ++k) {
-        const unsigned long long cand = ks[k] + 1ull;
-        if (act[k] && cand < kd[k]) {
-          if (atomicMin(&key[ed[k].y], cand) > cand) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+        if (PACK) {
+          // (word | idmask) + 1 = the key part plus one with an empty parent field; a generation that wraps into the swarm field
+          // is caught when the words are unpacked (gen == gmask: nothing reachable from it can beat its legitimate offers)
+          const unsigned long long cand = ((ks[k] | idmask) + 1ull) | ed[k].x;
+          if (act[k] && cand < kd[k]) {
+            const unsigned long long old = atomicMin(&key[ed[k].y], cand);
+            if ((old | idmask) > (cand | idmask)) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+          }
+        } else {
+          const unsigned long long cand = ks[k] + 1ull;
+          if (act[k] && cand < kd[k]) {
+            if (atomicMin(&key[ed[k].y], cand) > cand) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+          }
         }
       }
     }
@@ -657,29 +708,45 @@ __global__ void __launch_bounds__(256) k_cluster_persistent(const uint2 *edges, 
     grid.sync();
     if (flags[round % 3] == 0) break;
   }
-  for (uint64_t base = tid; base < m; base += nth * kClU) {
-    uint2 ed[kClU];
-    unsigned long long ks[kClU], kd[kClU];
+  if (!PACK) {
+    for (uint64_t base = tid; base < m; base += nth * kClU) {
+      uint2 ed[kClU];
+      unsigned long long ks[kClU], kd[kClU];
 #pragma unroll
-    for (int k = 0; k < kClU; ++k) {
-      const uint64_t e = base + static_cast<uint64_t>(k) * nth;
-      ed[k] = e < m ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(kNone, kNone);
+      for (int k = 0; k < kClU; ++k) {
+        const uint64_t e = base + static_cast<uint64_t>(k) * nth;
+        ed[k] = e < m ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(kNone, kNone);
+      }
+#pragma unroll
+      for (int k = 0; k < kClU; ++k) {
+        ks[k] = ed[k].x != kNone ? key[ed[k].x] : 0ull;
+        kd[k] = ed[k].x != kNone ? key[ed[k].y] : 0ull;
+      }
+#pragma unroll
+      for (int k = 0; k < kClU; ++k)
+        if (ed[k].x != kNone && ks[k] + 1ull == kd[k]) atomicMin(&parent[ed[k].y], ed[k].x);
     }
-#pragma unroll
-    for (int k = 0; k < kClU; ++k) {
-      ks[k] = ed[k].x != kNone ? key[ed[k].x] : 0ull;
-      kd[k] = ed[k].x != kNone ? key[ed[k].y] : 0ull;
-    }
-#pragma unroll
-    for (int k = 0; k < kClU; ++k)
-      if (ed[k].x != kNone && ks[k] + 1ull == kd[k]) atomicMin(&parent[ed[k].y], ed[k].x);
   }
   for (uint64_t v = tid; v < n; v += nth) {
     const unsigned long long kv = key[v];
-    if (HINT) { __stcs(&label[v], static_cast<uint32_t>(kv >> 32)); __stcs(&generation[v], static_cast<uint32_t>(kv)); }
-    else { label[v] = static_cast<uint32_t>(kv >> 32); generation[v] = static_cast<uint32_t>(kv); }
+    uint32_t lab, gen;
+    if (PACK) {
+      lab = static_cast<uint32_t>(kv >> (gb + ib));
+      gen = static_cast<uint32_t>((kv >> ib) & gmask);
+      if (gen == gmask) flags[3] = 1;                     // deeper than the packed word holds
+      const uint32_t par = (kv & idmask) == idmask ? kNone : static_cast<uint32_t>(kv & idmask);
+      if (HINT) __stcs(&parent[v], par); else parent[v] = par;
+    } else {
+      lab = static_cast<uint32_t>(kv >> 32);
+      gen = static_cast<uint32_t>(kv);
+    }
+    if (HINT) { __stcs(&label[v], lab); __stcs(&generation[v], gen); }
+    else { label[v] = lab; generation[v] = gen; }
   }
-  if (tid == 0 && rounds_out) *rounds_out = round + 1;
+  if (PACK) {
+    grid.sync();
+    if (tid == 0 && rounds_out) *rounds_out = (round + 1) | (flags[3] ? 0x80000000u : 0u);
+  } else if (tid == 0 && rounds_out) *rounds_out = round + 1;
 }
 
 __global__ void k_bfs_unpack(const unsigned long long *key, uint32_t *generation, uint32_t *parent, uint32_t n) {

@@ -149,6 +149,11 @@ struct swb200_ctx {
                           // kernel that walks the whole link list every round; 3 the same over links first sorted by source
                           // (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
                           // 1 label propagation + BFS
+  int cluster_pack = 1;  // k_cluster_persistent / k_cluster_bucket relax ONE packed word swarm | generation | parent (no parent pass); 0 = r1's key + parent pass
+  uint32_t cluster_gen_bits = 0;     // test hook: pretend the packed word has only this many generation bits (exercises the unpacked fallback)
+  unsigned long long cluster_unpacked_reruns = 0;
+  int cluster_coarse = 0; // k_cluster_persistent: coarse "lowered last round" bitmap in shared memory in front of the fine one
+  DevBuf<uint32_t> cl_coarse;
   int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
@@ -322,7 +327,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release(); c->cl_bits.release();
-  c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->dist_lcnt.release(); c->dist_links.release();
+  c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->cl_coarse.release(); c->dist_lcnt.release(); c->dist_links.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->fj_bloom.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
@@ -361,6 +366,9 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
   else if (k == "cluster_kernel" && v >= 0 && v <= 6) c->cluster_kernel = static_cast<int>(v);
   else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
+  else if (k == "cluster_pack" && (v == 0 || v == 1)) c->cluster_pack = static_cast<int>(v);
+  else if (k == "cluster_coarse" && (v == 0 || v == 1)) c->cluster_coarse = static_cast<int>(v);
+  else if (k == "cluster_gen_bits" && v >= 0 && v <= 32) c->cluster_gen_bits = static_cast<uint32_t>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
   else { g_err = "unknown option or bad value: " + k; return SWB200_EINVAL; }
@@ -1089,6 +1097,15 @@ int swb200_d1_get_network(swb200_ctx *c, uint64_t *row_ptr, uint32_t *col) {
   API_END()
 }
 
+// geometry of the packed relaxation word swarm | generation | parent (d1_kernels.cuh: k_cluster_persistent<.., PACK>); false: unpacked
+static bool cluster_pack_bits(const swb200_ctx *c, uint32_t &ib, uint32_t &gb) {
+  ib = 1;
+  while (ib < 32 && (1ull << ib) <= c->n) ++ib;              // 2^ib - 1 >= n: the all-ones parent field is no amplicon
+  gb = 2 * ib <= 64 ? std::min<uint32_t>(32, 64 - 2 * ib) : 0;
+  if (c->cluster_gen_bits) gb = std::min<uint32_t>(gb, c->cluster_gen_bits);
+  return c->cluster_pack && gb >= (c->cluster_gen_bits ? 1u : 10u);
+}
+
 static void run_cluster(swb200_ctx *c) {
   const uint32_t n = c->n;
   const uint64_t m = c->n_edges;
@@ -1126,14 +1143,25 @@ static void run_cluster(swb200_ctx *c) {
     }
     CK(cudaMemsetAsync(c->counters.p + 42, 0, 2 * 8, c->stream));
     const size_t dyn = static_cast<size_t>(kDistChunk) * sizeof(DistRec);
-    CK(cudaFuncSetAttribute(k_cluster_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-    int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cluster_bucket, 256, dyn));
-    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
-    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
-    void *args[] = {&B};
-    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_cluster_bucket), dim3(grid), dim3(256), args, dyn, c->stream));
-    c->launches++;
+    bool pack = cluster_pack_bits(c, B.ib, B.gb);
+    uint32_t *h_deep = static_cast<uint32_t *>(c->staging(64)) + 8;
+    for (;;) {
+      const void *kern = pack ? reinterpret_cast<const void *>(k_cluster_bucket<true>) : reinterpret_cast<const void *>(k_cluster_bucket<false>);
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
+      const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+      const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+      void *args[] = {&B};
+      CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, dyn, c->stream));
+      c->launches++;
+      if (!pack) break;
+      CK(cudaMemcpyAsync(h_deep, D.lflags + 6, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (!*h_deep) break;
+      pack = false;                                            // a generation beyond gb bits: once more with 32-bit generations
+      c->cluster_unpacked_reruns++;
+    }
     CK(cudaMemcpyAsync(reinterpret_cast<uint32_t *>(c->counters.p + 19), reinterpret_cast<uint32_t *>(c->counters.p + 22) + 4, 4, cudaMemcpyDeviceToDevice, c->stream));   // rounds
     if (D.ts) {
       unsigned long long h[128];
@@ -1216,22 +1244,47 @@ static void run_cluster(swb200_ctx *c) {
   }
   if (c->cluster_kernel == 0 || c->cluster_kernel == 5 || c->cluster_kernel == 3) {
     // fused label+generation relaxation as one persistent cooperative kernel over the unsorted link list (d1_kernels.cuh: k_cluster_persistent)
-    int occ = 1;
-    auto kern = c->cluster_hints ? k_cluster_persistent<true> : k_cluster_persistent<false>;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-    const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
-    const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
     const uint2 *e_p = c->edges.p;
     uint64_t m_ = m;
     unsigned long long *key_p = c->key.p;
     uint32_t *par_p = c->parent.p, *lab_p = c->label.p, *gen_p = c->generation.p, n_ = n;
     uint32_t *flags_p = reinterpret_cast<uint32_t *>(c->counters.p + 17), *rounds_p = reinterpret_cast<uint32_t *>(c->counters.p + 19);
     uint32_t nwords = (n + 31) / 32;
+    // coarse "lowered last round" filter in shared memory (k_cluster_persistent<.., COARSE>): one bit per 2^cs amplicons, <= 16 KB
+    uint32_t cs = 7;
+    while ((static_cast<uint64_t>(n) >> cs) + 1 > 131072) ++cs;
+    uint32_t n_cw = static_cast<uint32_t>((((static_cast<uint64_t>(n) + (1ull << cs) - 1) >> cs) + 31) / 32);
+    const bool coarse = c->cluster_coarse != 0;
+    if (coarse) nwords = n_cw * (32u << (cs - 5u));             // bitmaps padded to whole coarse words
     c->cl_bits.alloc(static_cast<size_t>(nwords) * 3);
-    uint32_t *bits_p = c->cl_bits.p;
-    void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords};
-    CK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(grid), dim3(256), args, 0, c->stream));
-    c->launches++;
+    c->cl_coarse.alloc(n_cw);
+    uint32_t *bits_p = c->cl_bits.p, *coarse_p = c->cl_coarse.p;
+    const size_t dyn = coarse ? static_cast<size_t>(n_cw) * 4 : 0;
+    // packed relaxation word swarm | generation | parent (one atomicMin settles the parent too, no parent pass) while the ids leave
+    // >= 10 bits for the generation; a deeper swarm raises bit 31 of the round count and the unpacked kernel runs instead
+    uint32_t ib, gb;
+    bool pack = cluster_pack_bits(c, ib, gb);
+    uint32_t *h_rounds = static_cast<uint32_t *>(c->staging(64)) + 8;
+    for (;;) {
+      const void *kern;
+      if (coarse) kern = pack ? (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, true, true>) : reinterpret_cast<const void *>(k_cluster_persistent<false, true, true>))
+                              : (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, false, true>) : reinterpret_cast<const void *>(k_cluster_persistent<false, false, true>));
+      else kern = pack ? (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, true, false>) : reinterpret_cast<const void *>(k_cluster_persistent<false, true, false>))
+                       : (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, false, false>) : reinterpret_cast<const void *>(k_cluster_persistent<false, false, false>));
+      int occ = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
+      const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
+      const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
+      void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords, &ib, &gb, &coarse_p, &cs, &n_cw};
+      CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, dyn, c->stream));
+      c->launches++;
+      if (!pack) break;
+      CK(cudaMemcpyAsync(h_rounds, rounds_p, 4, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (!(*h_rounds & 0x80000000u)) break;
+      pack = false;                                            // a generation beyond gb bits: once more with 32-bit generations
+      c->cluster_unpacked_reruns++;
+    }
     return;
   }
   if (c->cluster_kernel != 1) {
@@ -1292,7 +1345,7 @@ int swb200_d1_cluster(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generation, u
     if (c->cluster_kernel == 0 || c->cluster_kernel >= 3)
       CK(cudaMemcpyAsync(&rounds, reinterpret_cast<uint32_t *>(c->counters.p + 19), 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->stats[7] = rounds;
+    c->stats[7] = rounds & 0x7FFFFFFFu;
   }
   if (swarm_of) CK(cudaMemcpyAsync(swarm_of, c->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
   if (generation) CK(cudaMemcpyAsync(generation, c->generation.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1438,7 +1491,8 @@ int swb200_d1_reserve(swb200_ctx *c) {
                            reinterpret_cast<const void *>(k_ts_join<false, true, 6>), reinterpret_cast<const void *>(k_ts_join<false, false, 6>),
                            reinterpret_cast<const void *>(k_ts_big<true, true>), reinterpret_cast<const void *>(k_ts_big<true, false>),
                            reinterpret_cast<const void *>(k_ts_big<false, true>), reinterpret_cast<const void *>(k_ts_big<false, false>),
-                           reinterpret_cast<const void *>(k_cluster_dist), reinterpret_cast<const void *>(k_cluster_bucket),
+                           reinterpret_cast<const void *>(k_cluster_dist), reinterpret_cast<const void *>(k_cluster_bucket<true>),
+                           reinterpret_cast<const void *>(k_cluster_bucket<false>),
                            reinterpret_cast<const void *>(k_ts_release), reinterpret_cast<const void *>(k_dist_rendezvous)};
   for (const void *k : kernels) {
     cudaFuncAttributes attr;
@@ -1464,64 +1518,75 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
   for (uint32_t r = 0; r < D.world; ++r) D.peer[r] = c->dist_peer[r];
   D.cap_links = c->dist_cap;
   D.cap_upd = c->dist_cap * kDistLogFactor;
-  D.epoch_base = (++c->dist_calls) << 24;
   D.lflags = reinterpret_cast<uint32_t *>(c->counters.p + 22);
   D.gbar = reinterpret_cast<unsigned int *>(c->counters.p + 40);
   if (const char *dbg = std::getenv("SWB200_DIST_DBG")) D.dbg = static_cast<uint32_t>(std::atoi(dbg));
   if (std::getenv("SWB200_CLUSTER_TS")) {
     c->cl_ts.alloc(128);
-    CK(cudaMemsetAsync(c->cl_ts.p, 0, 128 * 8, c->stream));
     D.ts = c->cl_ts.p;
   }
   const size_t dyn = static_cast<size_t>(kDistChunk) * sizeof(DistRec);
   BucketParams B{};
-  B.D = D;
   B.nblk = D.n_local / kDistBlock;
   B.bcount = c->bk_count.p; B.boff = c->bk_off.p; B.blinks = c->bk_links.p; B.blinks_cap = c->bk_links.n;
   B.unit_blk = c->bk_unit.p; B.act_list = c->bk_act.p; B.unit_cap = c->bk_unit.n - 1; B.act_n = reinterpret_cast<uint32_t *>(c->counters.p + 46);
-  const void *kern = c->dist_kernel == 1 ? reinterpret_cast<const void *>(k_cluster_dist) : reinterpret_cast<const void *>(k_cluster_bucket);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-  int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
-  const unsigned grid = std::max(1u, static_cast<unsigned>(c->sm_count * std::max(occ, 1)) / static_cast<unsigned>(c->dist_grid_div));
+  // packed relaxation word (swarm | generation | parent, no parent pass: d1_bucket.cuh) while the ids of the job leave >= 10
+  // generation bits; every rank derives the same answer from n, and a deeper swarm on ANY rank makes all of them go again unpacked
+  bool pack = cluster_pack_bits(c, B.ib, B.gb) && c->dist_kernel != 1;
+  uint32_t h[7] = {0, 0, 0, 0, 0, 0, 0};
+  uint32_t overflow = 0;
   c->tic();
-  void *args_d[] = {&D}, *args_b[] = {&B};
-  if (c->dist_grid_div > 1) {                       // ranks sharing one GPU: cooperative kernels are never co-scheduled
-    TsRouteParams R{};                              // ... and the ranks line up first (k_dist_rendezvous says why)
-    R.rank = D.rank; R.world = D.world; R.epoch = c->dist_calls;
-    for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
-    R.err = D.lflags + 3;                           // a peer that never shows up is the barrier's error
-    k_dist_rendezvous<<<1, 32, 0, c->stream>>>(R);
+  for (;;) {
+    D.epoch_base = (++c->dist_calls) << 24;
+    if (D.ts) CK(cudaMemsetAsync(c->cl_ts.p, 0, 128 * 8, c->stream));
+    B.D = D;
+    const void *kern = c->dist_kernel == 1 ? reinterpret_cast<const void *>(k_cluster_dist)
+                                           : (pack ? reinterpret_cast<const void *>(k_cluster_bucket<true>) : reinterpret_cast<const void *>(k_cluster_bucket<false>));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
+    const unsigned grid = std::max(1u, static_cast<unsigned>(c->sm_count * std::max(occ, 1)) / static_cast<unsigned>(c->dist_grid_div));
+    void *args_d[] = {&D}, *args_b[] = {&B};
+    if (c->dist_grid_div > 1) {                       // ranks sharing one GPU: cooperative kernels are never co-scheduled
+      TsRouteParams R{};                              // ... and the ranks line up first (k_dist_rendezvous says why)
+      R.rank = D.rank; R.world = D.world; R.epoch = c->dist_calls;
+      for (uint32_t r = 0; r < R.world; ++r) R.peer[r] = c->dist_peer[r];
+      R.err = D.lflags + 3;                           // a peer that never shows up is the barrier's error
+      k_dist_rendezvous<<<1, 32, 0, c->stream>>>(R);
+      c->launches++;
+      if (c->dist_kernel == 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);
+      else if (pack) k_cluster_bucket<true><<<grid, 256, dyn, c->stream>>>(B);
+      else k_cluster_bucket<false><<<grid, 256, dyn, c->stream>>>(B);
+    } else {
+      CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), c->dist_kernel == 1 ? args_d : args_b, dyn, c->stream));
+    }
+    CK(cudaGetLastError());
     c->launches++;
-    if (c->dist_kernel == 1) k_cluster_dist<<<grid, 256, dyn, c->stream>>>(D);
-    else k_cluster_bucket<<<grid, 256, dyn, c->stream>>>(B);
-  } else {
-    CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), c->dist_kernel == 1 ? args_d : args_b, dyn, c->stream));
-  }
-  CK(cudaGetLastError());
-  c->launches++;
-  // read-backs go through PINNED memory: a copy into pageable memory blocks inside the driver until the kernel has finished,
-  // and that kernel may be waiting for a peer whose host thread (ranks sharing one process) then cannot launch
-  uint32_t *hp = static_cast<uint32_t *>(c->staging(4096));
-  CK(cudaMemcpyAsync(hp, D.lflags, 6 * 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hp + 8, c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 4, cudaMemcpyDeviceToHost, c->stream));
-  c->toc(3);
-  uint32_t h[6];
-  for (int i = 0; i < 6; ++i) h[i] = hp[i];
-  const uint32_t overflow = hp[8];
-  c->dist_rounds = h[4];
-  if (D.ts) {
-    unsigned long long t[128];
-    CK(cudaMemcpy(t, c->cl_ts.p, sizeof t, cudaMemcpyDeviceToHost));
-    std::string line = "[cluster_dist rank " + std::to_string(D.rank) + " rounds " + std::to_string(h[4]) +
-                       "] us (" + std::string(c->dist_kernel == 1 ? "route, barrier, compact, then relax/barrier/apply per round, tail" : "init + route, count + scan, then relax + barrier / apply per round, tail") + "):";
-    for (int i = 1; i < 128 && t[i]; ++i) line += " " + std::to_string(static_cast<long long>((t[i] - t[i - 1]) / 1000));
-    std::fprintf(stderr, "%s\n", line.c_str());
-  }
-  if (h[3]) {
-    CK(cudaMemsetAsync(c->counters.p + 40, 0, 2 * 8, c->stream));
-    g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s";
-    return SWB200_ECUDA;
+    // read-backs go through PINNED memory: a copy into pageable memory blocks inside the driver until the kernel has finished,
+    // and that kernel may be waiting for a peer whose host thread (ranks sharing one process) then cannot launch
+    uint32_t *hp = static_cast<uint32_t *>(c->staging(4096));
+    CK(cudaMemcpyAsync(hp, D.lflags, 7 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(hp + 8, c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 4, cudaMemcpyDeviceToHost, c->stream));
+    c->toc(3);
+    for (int i = 0; i < 7; ++i) h[i] = hp[i];
+    overflow = hp[8];
+    c->dist_rounds = h[4];
+    if (D.ts) {
+      unsigned long long t[128];
+      CK(cudaMemcpy(t, c->cl_ts.p, sizeof t, cudaMemcpyDeviceToHost));
+      std::string line = "[cluster_dist rank " + std::to_string(D.rank) + " rounds " + std::to_string(h[4]) +
+                         "] us (" + std::string(c->dist_kernel == 1 ? "route, barrier, compact, then relax/barrier/apply per round, tail" : "init + route, count + scan, then relax + barrier / apply per round, tail") + "):";
+      for (int i = 1; i < 128 && t[i]; ++i) line += " " + std::to_string(static_cast<long long>((t[i] - t[i - 1]) / 1000));
+      std::fprintf(stderr, "%s\n", line.c_str());
+    }
+    if (h[3]) {
+      CK(cudaMemsetAsync(c->counters.p + 40, 0, 2 * 8, c->stream));
+      g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s";
+      return SWB200_ECUDA;
+    }
+    if (!pack || overflow || !h[5]) break;
+    pack = false;                                     // some rank met a generation beyond gb bits (the last barrier's vote, the same on every rank)
+    c->cluster_unpacked_reruns++;
   }
   if (overflow) {
     CK(cudaMemsetAsync(c->dist_peer[D.rank] + offsetof(DistCtl, overflow), 0, 4, c->stream));
@@ -1856,6 +1921,7 @@ int swb200_get_stats(swb200_ctx *c, uint64_t *out, int n) {
   for (int i = 12; i < n && i < 16; ++i) out[i] = c->dnstats[i - 12];
   if (n > 16) out[16] = c->ts_overflow;
   if (n > 17) out[17] = c->ts_fallbacks;
+  if (n > 18) out[18] = c->cluster_unpacked_reruns;
   return SWB200_OK;
 }
 

@@ -555,14 +555,15 @@ class Engine:
         return engine_lib().swb200_phase_device_seconds(self._h, int(phase))
 
     def stats(self):
-        out = np.zeros(18, dtype=np.uint64)
-        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 18))
+        out = np.zeros(19, dtype=np.uint64)
+        self._ck(engine_lib().swb200_get_stats(self._h, _ptr(out, _u64p), 19))
         return {"variants": int(out[0]), "filter_pass": int(out[1]), "slots_visited": int(out[2]),
                 "exact_compares": int(out[3]), "links": int(out[4]), "launches": int(out[5]), "rows_gathered": int(out[6]), "cluster_rounds": int(out[7]),
                 "fast_light_variants": int(out[8]), "fast_heavy_variants": int(out[9]),
                 "fast_tag_matches": int(out[10]), "fast_verified": int(out[11]),
                 "dn_qgram_comparisons": int(out[12]), "dn_alignments": int(out[13]), "dn_pruned": int(out[14]),
-                "dn_links": int(out[15]), "tile_overflow": int(out[16]), "skew_fallbacks": int(out[17])}
+                "dn_links": int(out[15]), "tile_overflow": int(out[16]), "skew_fallbacks": int(out[17]),
+                "cluster_unpacked_reruns": int(out[18])}
 
     def debug_variants(self, seed: int, mode: int, cap: int = 1 << 16):
         h = np.zeros(cap, dtype=np.uint64)

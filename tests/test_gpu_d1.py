@@ -250,6 +250,29 @@ def test_seeded_sets_vs_oracle(built, tmp_path, n, L, seed, mode_ab):
         assert np.array_equal(par, orc.parent)
 
 
+@pytest.mark.parametrize("cluster_kernel", [0, 6])
+def test_packed_relaxation_word_and_its_fallback(built, tmp_path, cluster_kernel):
+    """the clustering kernels relax ONE word swarm | generation | parent (cluster_pack, default): same arrays as r1's key + parent
+    pass (cluster_pack=0) and as the oracle; a swarm deeper than the generation field holds (forced: 2 generation bits) is
+    detected and redone with 32-bit generations, transparently."""
+    fa = helpers.make_fasta(tmp_path / "s.fa", 50000, 120, 77, 1)           # tie-heavy: links in both directions
+    db = HostDb(fa)
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    assert int(orc.generation.max()) >= 3
+    for opt, reruns in (({}, 0), ({"cluster_pack": 0}, 0), ({"cluster_gen_bits": 2}, 1), ({"cluster_gen_bits": 31}, 0)):
+        eng = Engine(0, cluster_kernel=cluster_kernel, **opt)
+        eng.load(db)
+        eng.d1_index()
+        eng.d1_network()
+        sw, gen, par = eng.d1_cluster()
+        st = eng.stats()
+        eng.close()
+        assert st["cluster_unpacked_reruns"] == reruns, (opt, st)
+        assert np.array_equal(sw, orc.swarm_of) and np.array_equal(gen, orc.generation) and np.array_equal(par, orc.parent), opt
+
+
 def test_filter_sizes_and_sharding_give_identical_links(built, tmp_path):
     fa = helpers.make_fasta(tmp_path / "s.fa", 50000, 150, 77, 0)
     db = HostDb(fa)

@@ -91,8 +91,11 @@ def test_virtual_ranks_tie_heavy_and_mixed_lengths(built, tmp_path):
     orc = Oracle(db)
     orc.network()
     orc.cluster()
-    for world, sharded, opt in ((2, True, {}), (4, False, {}), (2, False, {"dist_kernel": 1}), (2, False, {"index_exchange": 0})):
+    # cluster_gen_bits = 2: a swarm deeper than the packed relaxation word holds -> every rank goes again with 32-bit generations
+    for world, sharded, opt in ((2, True, {}), (4, False, {}), (2, False, {"dist_kernel": 1}), (2, False, {"index_exchange": 0}),
+                                (3, True, {"cluster_gen_bits": 2}), (2, False, {"cluster_pack": 0})):
         outs = run_virtual(db, world, sharded, steps=1, **opt)
+        assert all(o[3]["cluster_unpacked_reruns"] == (1 if "cluster_gen_bits" in opt else 0) for o in outs), opt
         links = np.concatenate([o[2] for o in outs])
         links = links[np.lexsort((links[:, 1], links[:, 0]))]
         assert np.array_equal(links, orc.links())
