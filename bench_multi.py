@@ -200,8 +200,9 @@ def run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, peaks_fou
                       "formula": "per rank: own rows read, two records written to the owners' inboxes (NVLink) and read back, two tile records written"},
             "network": {"kernel": "k_ts_join", "s": net_s, "bytes": 2 * per * (8 + P_) + 8 * e_,
                         "formula": "per rank: every tile record + its packed row read once, links written"},
-            "cluster": {"kernel": "k_cluster_dist", "s": clu_s, "bytes": per * 32 + e_ * 36 + e_ * 16 * 2.6,
-                        "formula": "per rank: keys / parents of the owned amplicons, links routed and relaxed, 16-byte update records (2.6 per link measured)",
+            "cluster": {"kernel": "k_cluster_bucket", "s": clu_s, "bytes": per * 28 + e_ * 36 + e_ * 16 * 2.6 * 2 * (world - 1) / world,
+                        "formula": "per rank: relaxation words initialised and unpacked (28 B per owned amplicon), links routed, bucketed and walked (36 B per link), "
+                                   "16-byte offers written to and read from the owners' logs (2.6 per link measured, the remote share)",
                         "rounds": st["cluster_rounds"]},
         }
         roof = roofline_block(peak, peaks_found, ph, None)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parametrised runner for the GPU box (under gpurun): scripts/gpu_run.sh TAG step [step ...]
-#   steps: box | full:<kernel regex>[:skip[:bench args]] | fullp:<kernel regex>[:skip] (ncu --set full of one launch under scripts/probe.py) | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
+#   steps: box | full:<kernel regex>[:skip[:bench args[:mangled-name substring for the source-line table]]] | fullp:<kernel regex>[:skip] (ncu --set full of one launch under scripts/probe.py) | tests[:pytest -k expr] | scale | bench[:extra args] | probe[:args] | launches | full:<kernel regex>[:skip] | sanitize | ts
 # Everything lands in gpurun_out/TAG_*.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
@@ -20,10 +20,13 @@ for step in "$@"; do
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv \
                 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-parity > $O/${TAG}_launches.out 2>&1
               python scripts/ncu_summary.py launches $O/${TAG}_launches.csv > $O/${TAG}_launches.txt; head -20 $O/${TAG}_launches.txt ;;
-    full) IFS=: read -r k skip extra <<< "$arg"; skip=${skip:-0}
+    full) IFS=: read -r k skip extra mangled <<< "$arg"; skip=${skip:-0}; mangled=${mangled:-$k}
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity $extra > $O/${TAG}_full_$k.out 2>&1
-          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1; head -12 $O/${TAG}_$k.txt ;;
+          python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1
+          python scripts/ncu_lines.py $O/${TAG}_$k.ncu-rep $mangled swarm_b200/libswarm_b200.so 30 >> $O/${TAG}_$k.txt 2>&1
+          [ -n "$KEEP_REP" ] || rm -f $O/${TAG}_$k.ncu-rep      # gpurun brings back at most 64 MiB: the summaries travel, the reports do not
+          head -50 $O/${TAG}_$k.txt ;;
     fullp) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python scripts/probe.py 10000000 default= > $O/${TAG}_fullp_$k.out 2>&1

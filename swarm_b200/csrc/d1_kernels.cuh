@@ -606,19 +606,13 @@ constexpr int kClU = 8;
 // two random keys per link once more, 0.13 of 1.1 ms at 10 M — disappears.  A vertex is marked "lowered" only when its KEY part
 // went down (a smaller parent under the same key changes nothing for its out-links).  A swarm deeper than gb bits hold (a final
 // generation of 2^gb - 1 or more) raises bit 31 of *rounds_out and the host runs the unpacked kernel instead (engine.cu: run_cluster).
-// COARSE: what bounds the late rounds is not the 70 MB link list but the test "was this link's source lowered last round?" — one
-// 4-byte read per link at a random address of the 1.25 MB bitmap: 8.8 M L1TEX gather wavefronts, ~30 us a round however few
-// amplicons still move (profiles/r1b_gather_microbench.txt: one wavefront per clock and SM).  So every round first folds the
-// bitmap into one bit per 2^cs amplicons (a warp per coarse word, ~10 KB in all), every CTA copies that into SHARED memory, and a
-// link only goes to the fine bitmap when its source's coarse bit is set: in the late rounds > 90 % of the links stop at a
-// shared-memory lookup (random 4-byte reads over 32 banks: ~3 wavefronts per warp instead of 32).  Costs one more grid barrier a round.
-template <bool HINT, bool PACK, bool COARSE>
+// (Tried and dropped, r2x: a coarse "any of these 128 amplicons lowered?" bitmap copied into shared memory in front of the fine
+// one — fewer random bitmap reads in the late rounds, but the extra grid barrier and fold per round cost more: 1.17 vs 1.04 ms.)
+template <bool HINT, bool PACK>
 __global__ void __launch_bounds__(256, 4) k_cluster_persistent(const uint2 *edges, uint64_t m, unsigned long long *key, uint32_t *parent,
                                                             uint32_t *label, uint32_t *generation, uint32_t n,
                                                             volatile uint32_t *flags, uint32_t *rounds_out, uint32_t *bits,
-                                                            uint32_t nwords, uint32_t ib, uint32_t gb,
-                                                            uint32_t *coarse_g, uint32_t cs, uint32_t n_cw) {
-  extern __shared__ uint32_t cl_coarse[];                          // COARSE: n_cw words
+                                                            uint32_t nwords, uint32_t ib, uint32_t gb) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const uint64_t nth = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -641,20 +635,6 @@ __global__ void __launch_bounds__(256, 4) k_cluster_persistent(const uint2 *edge
     uint32_t *cl = bits + static_cast<size_t>((round + 2) % 3) * nwords;
     if (tid == 0) flags[(round + 1) % 3] = 0;
     if (round) for (uint64_t w = tid; w < nwords; w += nth) cl[w] = 0;
-    if (COARSE && round) {
-      // one coarse bit per 2^cs amplicons = 2^(cs-5) bitmap words (the bitmaps are padded with zero words to whole coarse words)
-      const uint32_t fw = 1u << (cs - 5u), lane = threadIdx.x & 31u;
-      for (uint64_t cw = tid >> 5; cw < n_cw; cw += nth >> 5) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(rd + ((cw * 32u + lane) << (cs - 5u)));
-        uint32_t acc = 0;
-        for (uint32_t q = 0; q < fw / 4u; ++q) { const uint4 x = src[q]; acc |= x.x | x.y | x.z | x.w; }
-        const uint32_t word = __ballot_sync(kFull, acc != 0u);
-        if (lane == 0) coarse_g[cw] = word;
-      }
-      grid.sync();
-      for (uint32_t w = threadIdx.x; w < n_cw; w += blockDim.x) cl_coarse[w] = __ldcg(&coarse_g[w]);
-      __syncthreads();
-    }
     int ch = 0;
     // kClU links per thread and step, loads issued stage by stage (links, bitmap words, keys): the loop is a chain
     // of dependent random reads, and one link at a time left each warp with a single request in flight
@@ -668,10 +648,6 @@ __global__ void __launch_bounds__(256, 4) k_cluster_persistent(const uint2 *edge
         ed[k] = act[k] ? (HINT ? __ldcs(&edges[e]) : edges[e]) : make_uint2(0u, 0u);
       }
       if (round) {
-        if (COARSE) {
-#pragma unroll
-          for (int k = 0; k < kClU; ++k) act[k] = act[k] && ((cl_coarse[ed[k].x >> (cs + 5u)] >> ((ed[k].x >> cs) & 31u)) & 1u);
-        }
         uint32_t w[kClU];
 #pragma unroll
         for (int k = 0; k < kClU; ++k) w[k] = act[k] ? rd[ed[k].x >> 5] : 0u;

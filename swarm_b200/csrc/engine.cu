@@ -152,8 +152,6 @@ struct swb200_ctx {
   int cluster_pack = 1;  // k_cluster_persistent / k_cluster_bucket relax ONE packed word swarm | generation | parent (no parent pass); 0 = r1's key + parent pass
   uint32_t cluster_gen_bits = 0;     // test hook: pretend the packed word has only this many generation bits (exercises the unpacked fallback)
   unsigned long long cluster_unpacked_reruns = 0;
-  int cluster_coarse = 0; // k_cluster_persistent: coarse "lowered last round" bitmap in shared memory in front of the fine one
-  DevBuf<uint32_t> cl_coarse;
   int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
@@ -327,7 +325,7 @@ void swb200_destroy(swb200_ctx *c) {
   c->words.release(); c->abundance.release(); c->ztab.release(); c->hashes.release(); c->len.release();
   c->slots.release(); c->filter.release(); c->edges.release(); c->counters.release();
   c->label.release(); c->generation.release(); c->parent.release(); c->key.release(); c->cl_bits.release();
-  c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->cl_coarse.release(); c->dist_lcnt.release(); c->dist_links.release();
+  c->cl_deg.release(); c->cl_row.release(); c->cl_srcs.release(); c->cl_dsts.release(); c->cl_tot.release(); c->cl_ts.release(); c->dist_lcnt.release(); c->dist_links.release();
   c->mass.release(); c->t2.release(); c->light_ids.release(); c->heavy_ids.release(); c->graft.release();
   c->is_light.release(); c->fj_bloom.release(); c->cands.release(); c->jtab.release();
   c->tj_count.release(); c->tj_cursor.release(); c->tj_big.release(); c->tj_off.release(); c->tj_entries.release(); c->tj_plist_ent.release(); c->tj_plist_tile.release(); c->tj_plist_cnt.release();
@@ -367,7 +365,6 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "cluster_kernel" && v >= 0 && v <= 6) c->cluster_kernel = static_cast<int>(v);
   else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
   else if (k == "cluster_pack" && (v == 0 || v == 1)) c->cluster_pack = static_cast<int>(v);
-  else if (k == "cluster_coarse" && (v == 0 || v == 1)) c->cluster_coarse = static_cast<int>(v);
   else if (k == "cluster_gen_bits" && v >= 0 && v <= 32) c->cluster_gen_bits = static_cast<uint32_t>(v);
   else if (k == "shard_rank" && v >= 0) c->shard_rank = static_cast<int>(v);
   else if (k == "shard_world" && v >= 1) c->shard_world = static_cast<int>(v);
@@ -1250,33 +1247,22 @@ static void run_cluster(swb200_ctx *c) {
     uint32_t *par_p = c->parent.p, *lab_p = c->label.p, *gen_p = c->generation.p, n_ = n;
     uint32_t *flags_p = reinterpret_cast<uint32_t *>(c->counters.p + 17), *rounds_p = reinterpret_cast<uint32_t *>(c->counters.p + 19);
     uint32_t nwords = (n + 31) / 32;
-    // coarse "lowered last round" filter in shared memory (k_cluster_persistent<.., COARSE>): one bit per 2^cs amplicons, <= 16 KB
-    uint32_t cs = 7;
-    while ((static_cast<uint64_t>(n) >> cs) + 1 > 131072) ++cs;
-    uint32_t n_cw = static_cast<uint32_t>((((static_cast<uint64_t>(n) + (1ull << cs) - 1) >> cs) + 31) / 32);
-    const bool coarse = c->cluster_coarse != 0;
-    if (coarse) nwords = n_cw * (32u << (cs - 5u));             // bitmaps padded to whole coarse words
     c->cl_bits.alloc(static_cast<size_t>(nwords) * 3);
-    c->cl_coarse.alloc(n_cw);
-    uint32_t *bits_p = c->cl_bits.p, *coarse_p = c->cl_coarse.p;
-    const size_t dyn = coarse ? static_cast<size_t>(n_cw) * 4 : 0;
+    uint32_t *bits_p = c->cl_bits.p;
     // packed relaxation word swarm | generation | parent (one atomicMin settles the parent too, no parent pass) while the ids leave
     // >= 10 bits for the generation; a deeper swarm raises bit 31 of the round count and the unpacked kernel runs instead
     uint32_t ib, gb;
     bool pack = cluster_pack_bits(c, ib, gb);
     uint32_t *h_rounds = static_cast<uint32_t *>(c->staging(64)) + 8;
     for (;;) {
-      const void *kern;
-      if (coarse) kern = pack ? (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, true, true>) : reinterpret_cast<const void *>(k_cluster_persistent<false, true, true>))
-                              : (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, false, true>) : reinterpret_cast<const void *>(k_cluster_persistent<false, false, true>));
-      else kern = pack ? (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, true, false>) : reinterpret_cast<const void *>(k_cluster_persistent<false, true, false>))
-                       : (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, false, false>) : reinterpret_cast<const void *>(k_cluster_persistent<false, false, false>));
+      const void *kern = pack ? (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, true>) : reinterpret_cast<const void *>(k_cluster_persistent<false, true>))
+                              : (c->cluster_hints ? reinterpret_cast<const void *>(k_cluster_persistent<true, false>) : reinterpret_cast<const void *>(k_cluster_persistent<false, false>));
       int occ = 1;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
       const uint64_t want = (std::max<uint64_t>(m, n) + 255) / 256;
       const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->sm_count) * std::max(occ, 1))));
-      void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords, &ib, &gb, &coarse_p, &cs, &n_cw};
-      CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, dyn, c->stream));
+      void *args[] = {&e_p, &m_, &key_p, &par_p, &lab_p, &gen_p, &n_, &flags_p, &rounds_p, &bits_p, &nwords, &ib, &gb};
+      CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, 0, c->stream));
       c->launches++;
       if (!pack) break;
       CK(cudaMemcpyAsync(h_rounds, rounds_p, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -1,6 +1,8 @@
-"""Multi-GPU plumbing: one process per GPU, seeds sharded across ranks, ONE exchange
-step — the all-gather(v) of the directed link lists — then replicated clustering.  torch.distributed is
-only the transport (NCCL over NVLink on GPUs, gloo in the CPU tests); no algorithm lives here."""
+"""Multi-GPU plumbing for the Python hosts (tests, bench.py): one process per GPU.  torch.distributed only sets up the
+peer-visible buffers (symmetric memory), optionally all-gathers a replicated database, and reduces timings — the exchanges of the
+job itself (index records, links, label offers) are done by the engine's kernels over NVLink peer memory (csrc/d1_tsroute.cuh,
+d1_bucket.cuh).  The C++ host does the same without torch: swb200_dist_setup_local (one process, one thread per GPU; host/main.cc).
+The link all-gather(v) + replicated clustering of round 1 is kept as a cross-check (exchange_engine_links)."""
 from __future__ import annotations
 
 import torch
@@ -78,7 +80,8 @@ def all_gather_db(eng, n_total: int, stride: int, group=None):
         for ptr, row_bytes in ((w_ptr, stride * 8), (l_ptr, 4), (a_ptr, 8)):
             whole = device_view(ptr, per * world * row_bytes)
             each = per * row_bytes // 4
-            dist.all_gather_into_tensor(whole, whole[rank * each:(rank + 1) * each].clone(), group=group)
+            # in place: this rank's shard already lies at its slot of the output (NCCL's in-place all-gather layout), no staging copy
+            dist.all_gather_into_tensor(whole, whole[rank * each:(rank + 1) * each], group=group)
     eng.db_commit()
 
 
