@@ -142,8 +142,20 @@ uint64_t count_microvariants(const swbh_db *db, Pick want) {
   return total;
 }
 
+// what the packed database costs on the device, for the out-of-memory message (the layout is fixed-stride)
+uint64_t g_db_rows = 0, g_db_stride_words = 0, g_db_nucleotides = 0;
+
 void engine_check(int status) {
   if (status == SWB200_OK) return;
+  if (status == SWB200_ENOMEM && g_db_rows) {
+    const double gb = static_cast<double>(g_db_rows) * g_db_stride_words * 8 / 1e9, tight = static_cast<double>(g_db_nucleotides) / 4 / 1e9;
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "GPU engine: %s\nThe packed database is stored with a fixed stride of %" PRIu64 " bytes per sequence (the longest sequence, "
+                  "rounded up to 32 nt): %" PRIu64 " sequences need %.1f GB for %.1f GB of nucleotides.%s", swb200_last_error(),
+                  g_db_stride_words * 8, g_db_rows, gb, tight,
+                  gb > 4 * tight ? "\nA few very long sequences multiply the memory of the whole set; cluster them separately." : "");
+    fatal(buf);
+  }
   if (status == SWB200_EDUPLICATE)                          // same text as src/algod1.cc:1141-1150
     fatal("some fasta entries have identical sequences.\nSwarm expects dereplicated fasta files.\n"
           "Such files can be produced with swarm or vsearch:\n swarm -d 0 -w derep.fasta -o /dev/null input.fasta\nor\n"
@@ -380,6 +392,7 @@ int main(int argc, char **argv) {
   const bool log_to_file = !P.log.empty();
   for (const char *prompt : {"Reading sequences:", "Indexing database:", "Abundance sorting:"}) phase_line(logf, log_to_file, prompt);   // src/db.cc:390,477,675
   std::fprintf(logf, "Database info:     %" PRIu64 " nt in %u sequences, longest %u nt\n", swbh_db_nucleotides(db), n, swbh_db_longest(db));
+  g_db_rows = n; g_db_stride_words = swbh_db_stride_words(db); g_db_nucleotides = swbh_db_nucleotides(db);
 
   swbh_result *res = nullptr;
   char *text = nullptr;
