@@ -24,7 +24,7 @@ for step in "$@"; do
           timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -o $O/${TAG}_$k -f \
             python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity $extra > $O/${TAG}_full_$k.out 2>&1
           python scripts/ncu_summary.py full $O/${TAG}_$k.ncu-rep > $O/${TAG}_$k.txt 2>&1
-          python scripts/ncu_lines.py $O/${TAG}_$k.ncu-rep $mangled swarm_b200/libswarm_b200.so 30 >> $O/${TAG}_$k.txt 2>&1
+          python scripts/ncu_lines2.py $O/${TAG}_$k.ncu-rep 40 >> $O/${TAG}_$k.txt 2>&1
           [ -n "$KEEP_REP" ] || rm -f $O/${TAG}_$k.ncu-rep      # gpurun brings back at most 64 MiB: the summaries travel, the reports do not
           head -50 $O/${TAG}_$k.txt ;;
     fullp) k=${arg%%:*}; skip=0; [[ "$arg" == *:* ]] && skip=${arg#*:}
