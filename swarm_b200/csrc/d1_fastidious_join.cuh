@@ -28,7 +28,7 @@ struct JoinParams {
   uint32_t n, stride;
   uint32_t K;
   const uint8_t *is_light;       // per amplicon
-  unsigned long long *table;     // multimap slots: tag32 | id32, 4-slot buckets
+  unsigned long long *table;     // multimap slots: tag24 | len8 | id32 (len8 = low 8 bits of the light amplicon's length), 4-slot buckets
   uint64_t n_buckets;
   uint2 *cands;                  // (heavy, light)
   unsigned long long *cand_count;
@@ -62,16 +62,17 @@ __device__ __forceinline__ uint64_t piece_hash(const uint64_t *w, uint32_t strid
   return h ^ (h >> 31);
 }
 
-__global__ void k_fj_flags(const uint32_t *label, const unsigned long long *mass, uint64_t boundary, uint32_t n, uint8_t *is_light,
+__global__ void __launch_bounds__(256) k_fj_flags(const uint32_t *label, const unsigned long long *mass, uint64_t boundary, uint32_t n, uint8_t *is_light,
                            uint32_t *graft_cand, uint32_t *counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = i < n;
   const bool light = in && mass[label[i]] < boundary;
   if (in) { is_light[i] = light ? 1 : 0; graft_cand[i] = kNone; }
-  const uint32_t ml = __ballot_sync(kFull, light), mh = __ballot_sync(kFull, in && !light);
-  if ((threadIdx.x & 31u) == 0) {
-    if (ml) atomicAdd(&counts[0], __popc(ml));
-    if (mh) atomicAdd(&counts[1], __popc(mh));
+  // one atomic per CTA and counter (per warp they were 6 * 10^5 atomics on two addresses: 0.31 ms at 10 M, profiles/r2y_launches_c3.txt)
+  const uint32_t nl = __syncthreads_count(light), nh = __syncthreads_count(in && !light);
+  if (threadIdx.x == 0) {
+    if (nl) atomicAdd(&counts[0], nl);
+    if (nh) atomicAdd(&counts[1], nh);
   }
 }
 
@@ -94,7 +95,9 @@ __global__ void __launch_bounds__(256) k_fj_insert(JoinParams J) {
 #pragma unroll
   for (uint32_t piece = 0; piece < 3; ++piece) {
     const uint64_t h = piece_hash(w, J.stride, offs[piece], J.K, piece);
-    const unsigned long long val = (h << 32) | a;                      // tag = low 32 bits of the hash
+    // tag = low 24 bits of the hash; the low 8 bits of the length ride along so that the heavy pass can apply the length filter
+    // |Ll - Lh| <= 2 without a dependent random read of len[l] (15 % of its stall samples, profiles/r2y_k_fj_candidates.txt)
+    const unsigned long long val = ((h & 0xFFFFFFull) << 40) | (static_cast<unsigned long long>(L & 0xFFu) << 32) | a;
     atomicOr(&J.bloom[fj_bloom_word(J, h)], fj_bloom_pattern(h));
     uint64_t b = __umul64hi(h, J.n_buckets);
     for (bool placed = false; !placed;) {
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) k_fj_candidates(JoinParams J, uint32_t a_
       }
       if (walking) {
         const uint64_t h = piece_hash(w, J.stride, off, K, piece);
-        tag = static_cast<uint32_t>(h);
+        tag = static_cast<uint32_t>(h) & 0xFFFFFFu;
         b = __umul64hi(h, J.n_buckets);
         lookups++;
         const unsigned long long pat = fj_bloom_pattern(h);
@@ -163,11 +166,10 @@ __global__ void __launch_bounds__(256) k_fj_candidates(JoinParams J, uint32_t a_
       for (int s = 0; s < 4; ++s) {
         if (full) {
           if (sv[s] == kT2Empty) full = false;
-          else if (static_cast<uint32_t>(sv[s] >> 32) == tag) {
+          else if (static_cast<uint32_t>(sv[s] >> 40) == tag) {
             const uint32_t l = static_cast<uint32_t>(sv[s]);
-            const uint32_t Ll = J.len[l];
-            const uint32_t dl = Ll > L ? Ll - L : L - Ll;
-            if (dl <= 2 && J.graft_cand[l] > a) {
+            const uint32_t dl = (static_cast<uint32_t>(sv[s] >> 32) - L) & 0xFFu;      // (Ll - Lh) mod 256: -2 .. 2 pass (k_fj_verify re-checks the true lengths)
+            if ((dl <= 2u || dl >= 254u) && J.graft_cand[l] > a) {
               if (nc == 0) cv[0] = l; else if (nc == 1) cv[1] = l; else if (nc == 2) cv[2] = l; else cv[3] = l;
               ++nc;
             }
@@ -230,7 +232,8 @@ __global__ void __launch_bounds__(256) k_fj_verify(JoinParams J) {
     const uint64_t *hw = J.words + static_cast<uint64_t>(a) * J.stride;
     const uint64_t *lw = J.words + static_cast<uint64_t>(l) * J.stride;
     const int Lh = static_cast<int>(J.len[a]), Ll = static_cast<int>(J.len[l]);
-    const int dt = Ll - Lh;                                              // the diagonal of the end point, |dt| <= 2 (length filter)
+    const int dt = Ll - Lh;                                              // the diagonal of the end point
+    if (dt < -2 || dt > 2) continue;                                     // (the candidates' length filter works modulo 256)
     constexpr int NONE = -100000;
     int fr[5] = {NONE, NONE, NONE, NONE, NONE};                          // index d + 2
     fr[2] = fj_lce(hw, lw, J.stride, 0, 0, min(Lh, Ll));

@@ -155,6 +155,7 @@ struct swb200_ctx {
   int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
+  uint32_t fast_chunks = 16;         // heavy amplicons are processed in this many ascending id chunks (pruning by graft_cand[l] <= h)
   DevBuf<uint8_t> is_light;
   DevBuf<unsigned long long> fj_bloom;
   DevBuf<uint2> cands;
@@ -361,6 +362,7 @@ int swb200_set_option(swb200_ctx *c, const char *key, int64_t v) {
   else if (k == "join_occupancy" && (v == 0 || (v >= 4 && v <= 6))) c->ts_occ_opt = static_cast<int>(v);
   else if (k == "tile_cmax" && v >= 0 && v <= 1024) c->tj_cmax_override = static_cast<uint32_t>(v);
   else if (k == "fast_kernel" && v >= 0 && v <= 2) c->fast_kernel = static_cast<int>(v);
+  else if (k == "fast_chunks" && v >= 1 && v <= 1024) c->fast_chunks = static_cast<uint32_t>(v);
   else if (k == "dn_filter" && v >= 0 && v <= 1) c->dn_filter = static_cast<int>(v);
   else if (k == "cluster_kernel" && v >= 0 && v <= 6) c->cluster_kernel = static_cast<int>(v);
   else if (k == "cluster_hints" && (v == 0 || v == 1)) c->cluster_hints = static_cast<int>(v);
@@ -1758,7 +1760,7 @@ int swb200_d1_fastidious(swb200_ctx *c, uint64_t boundary, uint32_t *graft_cand,
       J.overflow = reinterpret_cast<uint32_t *>(c->counters.p + 48);
       // heavy amplicons in ascending id chunks (graft_cand[l] <= h prunes the later candidates of l); candidates and verification of
       // a chunk run back to back, the candidate count stays on the device — the host only looks at an overflow flag at the end
-      uint32_t n_chunks = 16;
+      uint32_t n_chunks = c->fast_chunks;
       for (int attempt = 0; attempt < 6; ++attempt) {
         CK(cudaMemsetAsync(c->counters.p + 48, 0, 8, c->stream));
         const uint32_t chunk = std::max<uint32_t>(1, (n + n_chunks - 1) / n_chunks);
