@@ -18,7 +18,7 @@ for line in out.splitlines():
     if m:
         cur = m.group(1)
         body[cur] = []
-    elif cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+    elif cur and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
         body[cur].append(line.split("/*", 2)[1][5:].strip() if False else re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line).strip())
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
 print(f"# cuobjdump -sass {so.name} (sm_100a), CUDA {subprocess.run(['nvcc', '--version'], capture_output=True, text=True).stdout.split('release ')[-1].split(',')[0]}")

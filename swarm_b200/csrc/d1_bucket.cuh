@@ -113,10 +113,12 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
   auto offer_of = [&](unsigned long long ws, uint32_t u) -> unsigned long long {
     return PACK ? (((ws | idmask) + 1ull) | u) : ws + 1ull;
   };
-  // atomicMin of an offer into the owned amplicon lv; true when its KEY went down (its out-links must be offered again)
-  auto lower = [&](uint32_t lv, unsigned long long cand) -> bool {
-    const unsigned long long old = atomicMin(&D.key[lv], cand);
-    return PACK ? (old | idmask) > (cand | idmask) : old > cand;
+  // fire-and-forget atomicMin (RED.MIN) of an offer into the owned amplicon lv whose word was `seen` a moment ago (cand < seen);
+  // true when its KEY is (being) lowered — decided from `seen`: a superset of the true set whose extra members were lowered, and
+  // marked, by a concurrent better offer in this same round (k_cluster_persistent has the argument and the measurement)
+  auto lower = [&](uint32_t lv, unsigned long long cand, unsigned long long seen) -> bool {
+    atomicMin(&D.key[lv], cand);
+    return PACK ? (seen | idmask) > (cand | idmask) : true;
   };
   __shared__ DistSmem sm;
   __shared__ unsigned long long s_pref[kDistMaxWorld + 1];
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         cand0[k] = offer_of(PACK ? ((static_cast<unsigned long long>(ed[k].x) << (gb + ib)) | idmask) : (static_cast<unsigned long long>(ed[k].x) << 32), ed[k].x);
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        if (lv[k] != kNone && cand0[k] < kd[k] && lower(lv[k], cand0[k])) {
+        if (lv[k] != kNone && cand0[k] < kd[k] && lower(lv[k], cand0[k], kd[k])) {
           atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
           ch = 1;
         }
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
         for (int k = 0; k < U; ++k) kd[k] = lv[k] != kNone ? D.key[lv[k]] : 0ull;
 #pragma unroll
         for (int k = 0; k < U; ++k)
-          if (lv[k] != kNone && cand[k] < kd[k] && lower(lv[k], cand[k])) {
+          if (lv[k] != kNone && cand[k] < kd[k] && lower(lv[k], cand[k], kd[k])) {
             atomicOr(&wr[lv[k] >> 5], 1u << (lv[k] & 31u));
             ch = 1;
           }
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(256, 3) k_cluster_bucket(BucketParams B) {
             if (raw[k].x == kNone) continue;
             const uint32_t lv = dist_local(D, raw[k].x);
             const unsigned long long cand = (static_cast<unsigned long long>(raw[k].w) << 32) | raw[k].z;
-            if (cand < kv[k] && lower(lv, cand)) {
+            if (cand < kv[k] && lower(lv, cand, kv[k])) {
               atomicOr(&wr[lv >> 5], 1u << (lv & 31u));
             }
           }

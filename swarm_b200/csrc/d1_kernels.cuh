@@ -669,13 +669,19 @@ __global__ void __launch_bounds__(256, 4) k_cluster_persistent(const uint2 *edge
           // is caught when the words are unpacked (gen == gmask: nothing reachable from it can beat its legitimate offers)
           const unsigned long long cand = ((ks[k] | idmask) + 1ull) | ed[k].x;
           if (act[k] && cand < kd[k]) {
-            const unsigned long long old = atomicMin(&key[ed[k].y], cand);
-            if ((old | idmask) > (cand | idmask)) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+            // fire and forget (RED.MIN): waiting for the atomic's return value was 30 % of the kernel's stall samples
+            // (profiles/r2y_k_cluster_persistent.txt).  "Lowered" is decided from the word loaded before: whenever this offer or a
+            // concurrent better one lowers the key, kd's key was above the offer's — a superset of the true set whose extra
+            // members were lowered (and marked) by somebody else in this same round.
+            atomicMin(&key[ed[k].y], cand);
+            if ((kd[k] | idmask) > (cand | idmask)) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
           }
         } else {
           const unsigned long long cand = ks[k] + 1ull;
           if (act[k] && cand < kd[k]) {
-            if (atomicMin(&key[ed[k].y], cand) > cand) { atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u)); ch = 1; }
+            atomicMin(&key[ed[k].y], cand);
+            atomicOr(&wr[ed[k].y >> 5], 1u << (ed[k].y & 31u));
+            ch = 1;
           }
         }
       }
