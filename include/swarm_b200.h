@@ -68,7 +68,7 @@ const char *swb200_last_error(void);
  * huge groups sharing one K-mer — swb200_d1_network switches to the linear HALF enumeration, like the reference's
  * cost model; 0 = always sweep),
  * "fast_kernel" (0 auto, 1 microvariant multimap, 2 pigeonhole join — fastidious strategies, same result),
- * "fast_chunks" (tuning, default 16: the heavy amplicons are searched in this many ascending id chunks, so that a light amplicon
+ * "fast_chunks" (tuning, default 8: the heavy amplicons are searched in this many ascending id chunks, so that a light amplicon
  * already grafted on an earlier heavy one prunes the later candidates),
  * "cluster_kernel" (0 = 5 fused label/generation relaxation over the link list in one persistent cooperative kernel;
  * 6 links bucketed by source block, inactive buckets skipped, d1_bucket.cuh (the multi-GPU kernel run on one GPU);

@@ -155,7 +155,7 @@ struct swb200_ctx {
   int cluster_hints = 1; // streaming cache policy for the link list / outputs of k_cluster_persistent (0 = plain loads, for comparison)
   int dn_filter = 0;     // 0 auto (pigeonhole join when possible), 1 = all-pairs q-gram filter
   int fast_kernel = 0;   // 0 auto, 1 = microvariant multimap (d1_fastidious.cuh), 2 = pigeonhole join
-  uint32_t fast_chunks = 16;         // heavy amplicons are processed in this many ascending id chunks (pruning by graft_cand[l] <= h)
+  uint32_t fast_chunks = 8;          // heavy amplicons are processed in this many ascending id chunks (pruning by graft_cand[l] <= h): 4.06 ms at 8, 4.29 at 16, 4.82 at 32 (10 M, r2z)
   DevBuf<uint8_t> is_light;
   DevBuf<unsigned long long> fj_bloom;
   DevBuf<uint2> cands;
