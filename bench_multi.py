@@ -79,6 +79,13 @@ def run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, peaks_fou
     pl[:] = Ln[first:first + count].cpu().numpy().view(np.uint32)
     pa[:] = Ab[first:first + count].cpu().numpy().view(np.uint64)
 
+    # compact form of the same rows for the replicated layout's upload: u16 lengths, and the abundance RUNS of the whole database
+    # instead of an abundance array (expanded on every device)
+    pl16 = pinned(count, torch.int16).view(np.uint16)
+    pl16[:] = pl
+    run_ab_t = Ab[torch.from_numpy(runs[:-1].astype(np.int64)).cuda()].cpu().numpy().view(np.uint64)
+    prab, prst = pinned(run_ab_t.shape[0], torch.int64).view(np.uint64), pinned(runs.shape[0], torch.int32).view(np.uint32)
+    prab[:], prst[:] = run_ab_t, runs
     eng = Engine(local, enum_mode=args.enum_mode, join_kernel=args.join_kernel, collect_stats=0, shard_rank=rank, shard_world=world,
                  tile_rows=1 if sharded else 0, job_min_len=lmin, job_max_len=lmax)
     if sharded:
@@ -90,7 +97,7 @@ def run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, peaks_fou
         torch.cuda.empty_cache()
     own_ids = dist_row_ids(n, rank, world)
     res = {k: pinned(own_ids.shape[0], torch.int32).view(np.uint32) for k in ("swarm_of", "generation", "parent")}
-    h2d = pw.nbytes + pl.nbytes + pa.nbytes + (runs.nbytes if sharded else 0)
+    h2d = (pw.nbytes + pl.nbytes + pa.nbytes + runs.nbytes) if sharded else (pw.nbytes + pl16.nbytes + prab.nbytes + prst.nbytes)
     d2h = 3 * 4 * own_ids.shape[0]
     ext = engine_stream(eng)
     inbox_bytes = setup_dist_clustering(eng, n)
@@ -104,8 +111,8 @@ def run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, peaks_fou
         if sharded:
             eng.load_db_rows(pw, stride, pl, pa, n, first, runs)
         else:
-            eng.load_db_shard(pw, stride, pl, pa, n, first)
-            all_gather_db(eng, n, stride)
+            eng.load_db_shard_compact(pw, stride, pl16, n, first, prab, prst)
+            all_gather_db(eng, n, stride, with_abundance=False)
         eng.d1_index()
         eng.d1_network()
         return eng.d1_cluster_dist(res)
@@ -223,7 +230,7 @@ def run_multi(args, cfg, rank, world, local, emit, ClockSampler, peak, peaks_fou
             "phases_ms": {"index": 1e3 * idx_s, "network": 1e3 * net_s, "cluster": 1e3 * clu_s},
             "e2e": {"value": n * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": 1e3 * dt_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps,
-                    "api": ("swb200_load_db_rows" if sharded else "swb200_load_db_shard + all-gather") + " -> d1_index -> d1_network -> d1_cluster_dist (host arrays)"},
+                    "api": ("swb200_load_db_rows" if sharded else "swb200_load_db_shard_compact + all-gather of words and lengths") + " -> d1_index -> d1_network -> d1_cluster_dist (host arrays)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "parity": parity,
             "counters": {"records": cnt[0], "exact_compares": cnt[1], "links": cnt[2], "rows_gathered": cnt[3], "tile_overflow": cnt[5]},
             "swarms": cnt[4],

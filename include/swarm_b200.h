@@ -107,6 +107,12 @@ int  swb200_load_db_compact(swb200_ctx *ctx, const uint64_t *words, uint32_t str
  * that is already in device memory (device pointers, copied). */
 int  swb200_load_db_shard(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words, const uint32_t *len,
                           const uint64_t *abundance, uint32_t n_total, uint32_t first, uint32_t count);
+/* swb200_load_db_shard from fewer host bytes (the multi-GPU end-to-end path is bound by the host's aggregate PCIe rate): 16-bit
+ * lengths for the rank's rows and NO abundance array — the abundance runs of the WHOLE database (as in swb200_load_db_compact)
+ * are expanded on every device, so the row exchange only moves words and lengths (swb200_db_device: d_words, d_len). */
+int  swb200_load_db_shard_compact(swb200_ctx *ctx, const uint64_t *words, uint32_t stride_words, const uint16_t *len16,
+                                  uint32_t n_total, uint32_t first, uint32_t count, const uint64_t *run_abundance,
+                                  const uint32_t *run_start, uint32_t n_runs);
 /* SHARDED database (BASELINE configs[4], SURVEY.md §8e "hash-sharded"): this context keeps only the rows [first, first+count)
  * of the job's sorted database — no rank holds all packed sequences.  run_start (n_runs + 1 entries, as in
  * swb200_load_db_compact) describes the abundance runs of the WHOLE database: it is how a rank decides whether two amplicon ids

@@ -145,10 +145,10 @@ struct swb200_ctx {
   bool too_long = false;             // longest sequence > 5 000 nt: d = 0 only
   bool db_pending = false;           // rows uploaded by load_db_shard, exchange + db_commit still due
   bool sorted_desc = false;          // abundances never increase with the id (the reference's order, src/db.cc:392-406)
-  int cluster_kernel = 0; // 0 frontier relaxation over out-rows, one persistent cooperative kernel (d1_frontier.cuh); 5 r1's persistent
-                          // kernel that walks the whole link list every round; 3 the same over links first sorted by source
-                          // (d1_cluster.cuh; measured slower at 10 M: the sort costs more than it saves); 2 one launch per round;
-                          // 1 label propagation + BFS
+  int cluster_kernel = 0; // 0 (= 5) one persistent cooperative kernel that walks the link list every round (d1_kernels.cuh: k_cluster_persistent,
+                          // the default: fastest on one GPU); 6 links bucketed by source block (d1_bucket.cuh, the multi-GPU kernel at world = 1);
+                          // 4 frontier relaxation over out-rows (d1_frontier.cuh); 3 links first sorted by source (d1_cluster.cuh);
+                          // 2 one launch per round; 1 label propagation + BFS
   int cluster_pack = 1;  // k_cluster_persistent / k_cluster_bucket relax ONE packed word swarm | generation | parent (no parent pass); 0 = r1's key + parent pass
   uint32_t cluster_gen_bits = 0;     // test hook: pretend the packed word has only this many generation bits (exercises the unpacked fallback)
   unsigned long long cluster_unpacked_reruns = 0;
@@ -526,6 +526,37 @@ int swb200_load_db_shard(swb200_ctx *c, const uint64_t *words, uint32_t stride_w
   db_upload(c, c->words.p + static_cast<size_t>(first) * stride_words, words, static_cast<size_t>(count) * stride_words * 8);
   db_upload(c, c->len.p + first, len, static_cast<size_t>(count) * 4);
   db_upload(c, c->abundance.p + first, abundance, static_cast<size_t>(count) * 8);
+  c->db_pending = true;
+  API_END()
+}
+
+// swb200_load_db_shard from fewer host bytes: 16-bit lengths for the rank's rows, and NO abundance upload at all — the abundance
+// runs of the whole database (a few KB) are expanded on every device, so the row exchange only has to move words and lengths
+int swb200_load_db_shard_compact(swb200_ctx *c, const uint64_t *words, uint32_t stride_words, const uint16_t *len16, uint32_t n_total,
+                                 uint32_t first, uint32_t count, const uint64_t *run_abundance, const uint32_t *run_start, uint32_t n_runs) {
+  API_BEGIN(c)
+  if (n_total == 0 || stride_words == 0 || static_cast<uint64_t>(first) + count > n_total || (count && (!words || !len16)) ||
+      !run_abundance || !run_start || n_runs == 0 || n_runs > n_total || run_start[0] != 0 || run_start[n_runs] != n_total || n_total >= 0xFFFFFFF0u) {
+    g_err = "load_db_shard_compact: bad argument";
+    return SWB200_EINVAL;
+  }
+  for (uint32_t r = 0; r < n_runs; ++r)
+    if (run_start[r] >= run_start[r + 1]) { g_err = "load_db_shard_compact: empty or unordered run"; return SWB200_EINVAL; }
+  {
+    const uint64_t per = (static_cast<uint64_t>(n_total) + c->shard_world - 1) / c->shard_world;
+    if (first % per != 0 || count > per) { g_err = "load_db_shard_compact: [first, first + count) is not a shard of ceil(n / shard_world) rows (set \"shard_world\" first)"; return SWB200_EINVAL; }
+  }
+  db_alloc(c, n_total, stride_words);
+  c->ld_len16.alloc(std::max<uint32_t>(count, 1)); c->ld_run_value.alloc(n_runs); c->ld_run_start.alloc(static_cast<size_t>(n_runs) + 1);
+  c->tic();
+  db_upload(c, c->ld_len16.p, len16, static_cast<size_t>(count) * 2);
+  db_upload(c, c->ld_run_value.p, run_abundance, static_cast<size_t>(n_runs) * 8);
+  db_upload(c, c->ld_run_start.p, run_start, (static_cast<size_t>(n_runs) + 1) * 4);
+  if (count) k_expand_len16<<<(count + 255) / 256, 256, 0, c->stream>>>(c->ld_len16.p, c->len.p + first, count);
+  k_expand_runs<<<(n_total + 255) / 256, 256, 0, c->stream>>>(c->ld_run_value.p, c->ld_run_start.p, n_runs, c->abundance.p, n_total);
+  c->launches += 2;
+  db_upload(c, c->words.p + static_cast<size_t>(first) * stride_words, words, static_cast<size_t>(count) * stride_words * 8);
+  CK(cudaGetLastError());
   c->db_pending = true;
   API_END()
 }

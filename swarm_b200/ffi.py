@@ -53,6 +53,7 @@ def engine_lib():
         L.swb200_load_db.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32]
         L.swb200_load_db_compact.argtypes = [vp, _u64p, C.c_uint32, C.POINTER(C.c_uint16), _u64p, _u32p, C.c_uint32, C.c_uint32]
         L.swb200_load_db_shard.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.swb200_load_db_shard_compact.argtypes = [vp, _u64p, C.c_uint32, C.POINTER(C.c_uint16), C.c_uint32, C.c_uint32, C.c_uint32, _u64p, _u32p, C.c_uint32]
         L.swb200_load_db_rows.argtypes = [vp, _u64p, C.c_uint32, _u32p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32]
         L.swb200_db_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.swb200_db_commit.argtypes = [vp]
@@ -429,6 +430,15 @@ class Engine:
         assert words.shape[0] == count * stride and abundance.shape[0] == count
         self._ck(engine_lib().swb200_load_db_shard(self._h, _ptr(words, _u64p), int(stride), _ptr(lengths, _u32p),
                                                   _ptr(abundance, _u64p), int(n_total), int(first), int(count)))
+        self.n = int(n_total)
+
+    def load_db_shard_compact(self, words, stride, len16, n_total, first, run_abundance, run_start):
+        """load_db_shard from fewer host bytes: u16 lengths of this rank's rows, abundance runs of the WHOLE database (no abundance array)"""
+        count = len16.shape[0]
+        assert words.shape[0] == count * stride and len16.dtype == np.uint16 and run_start.shape[0] == run_abundance.shape[0] + 1
+        self._ck(engine_lib().swb200_load_db_shard_compact(self._h, _ptr(words, _u64p), int(stride), _ptr(len16, C.POINTER(C.c_uint16)), int(n_total),
+                                                          int(first), int(count), _ptr(run_abundance, _u64p), _ptr(run_start, _u32p),
+                                                          int(run_abundance.shape[0])))
         self.n = int(n_total)
 
     def load_db_rows(self, words, stride, lengths, abundance, n_total, first, run_start):

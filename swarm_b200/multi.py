@@ -66,7 +66,7 @@ def engine_stream(eng):
     return torch.cuda.ExternalStream(eng.stream())
 
 
-def all_gather_db(eng, n_total: int, stride: int, group=None):
+def all_gather_db(eng, n_total: int, stride: int, group=None, with_abundance: bool = True):
     """the one exchange of the upload path: every rank pushed its own rows over PCIe (swb200_load_db_shard); the
     rows of the other ranks arrive device-to-device over NVLink (NCCL all-gather, in place on the engine's buffers)"""
     world = dist.get_world_size(group)
@@ -77,7 +77,8 @@ def all_gather_db(eng, n_total: int, stride: int, group=None):
     per = (n_total + world - 1) // world
     w_ptr, l_ptr, a_ptr = eng.db_device()
     with torch.cuda.stream(engine_stream(eng)):
-        for ptr, row_bytes in ((w_ptr, stride * 8), (l_ptr, 4), (a_ptr, 8)):
+        # (after swb200_load_db_shard_compact every device already holds all abundances: expanded from the run table)
+        for ptr, row_bytes in ((w_ptr, stride * 8), (l_ptr, 4)) + (((a_ptr, 8),) if with_abundance else ()):
             whole = device_view(ptr, per * world * row_bytes)
             each = per * row_bytes // 4
             # in place: this rank's shard already lies at its slot of the output (NCCL's in-place all-gather layout), no staging copy

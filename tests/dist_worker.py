@@ -13,7 +13,7 @@ import torch.distributed as dist
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from swarm_b200 import Engine, HostDb  # noqa: E402
-from swarm_b200.ffi import dist_row_ids  # noqa: E402
+from swarm_b200.ffi import compact_form, dist_row_ids  # noqa: E402
 from swarm_b200.multi import all_gather_db, exchange_engine_links, setup_dist_clustering, shard_rows  # noqa: E402
 
 
@@ -35,8 +35,13 @@ def main():
     # sharded upload + sharded join
     eng = Engine(local, shard_rank=rank, shard_world=world)
     w = db.words.reshape(n, db.stride)[first:first + count].reshape(-1).copy()
-    eng.load_db_shard(w, db.stride, db.len[first:first + count].copy(), db.abundance[first:first + count].copy(), n, first)
-    all_gather_db(eng, n, db.stride)
+    if os.environ.get("SWB200_TEST_PLAIN_SHARD"):
+        eng.load_db_shard(w, db.stride, db.len[first:first + count].copy(), db.abundance[first:first + count].copy(), n, first)
+        all_gather_db(eng, n, db.stride)
+    else:                                                      # compact: u16 lengths, abundance runs of the whole database, no abundance exchange
+        l16, rab, rst = compact_form(db.len, db.abundance)
+        eng.load_db_shard_compact(w, db.stride, l16[first:first + count].copy(), n, first, rab, rst)
+        all_gather_db(eng, n, db.stride, with_abundance=False)
     setup_dist_clustering(eng, n)
     ids = dist_row_ids(n, rank, world).astype(np.int64)       # the rows this rank owns (block-cyclic)
     for it in range(repeat):

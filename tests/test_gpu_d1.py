@@ -569,6 +569,33 @@ def test_compact_loader_gives_the_same_database(built, name):
     assert res.swarms_text() == (GOLDEN / f"{name}.f.o").read_bytes()
 
 
+def test_shard_compact_loader_world1(built, tmp_path):
+    """swb200_load_db_shard_compact with a single shard (no exchange needed) + swb200_db_commit == swb200_load_db: same links, same
+    swarms; the abundance array is rebuilt on the device from the run table alone.  (Two shards + NCCL all-gather: tests/dist_worker.py,
+    bench.py --gpus N.)"""
+    from swarm_b200.ffi import compact_form
+    fa = helpers.make_fasta(tmp_path / "s.fa", 30000, 150, 5, 1)
+    db = HostDb(fa)
+    l16, rab, rst = compact_form(db.len, db.abundance)
+    ref = run_engine(db, ENUM_JOIN)
+    eng = Engine(0)
+    eng.load_db_shard_compact(db.words, db.stride, l16, db.n, 0, rab, rst)
+    eng.db_commit()
+    eng.d1_index()
+    eng.d1_network()
+    links = eng.d1_export_links()
+    links = links[np.lexsort((links[:, 1], links[:, 0]))]
+    sw, gen, par = eng.d1_cluster()
+    eng.close()
+    assert np.array_equal(links, ref[0]) and np.array_equal(sw, ref[1]) and np.array_equal(gen, ref[2]) and np.array_equal(par, ref[3])
+    eng = Engine(0)
+    bad = rst.copy()
+    bad[-1] -= 1                                                 # the runs do not cover [0, n)
+    with pytest.raises(EngineError):
+        eng.load_db_shard_compact(db.words, db.stride, l16, db.n, 0, rab, bad)
+    eng.close()
+
+
 def test_compact_loader_rejects_bad_runs(built):
     db = HostDb(GOLDEN / "handmade.fasta")
     eng = Engine(0)
