@@ -169,6 +169,8 @@ def reference_arm(args, cfg, rank, world):
         emit({"impl": "reference", "unavailable": "oracle/_ref/swarm_timed was not built (needs /root/reference at build time)"})
         return
     sample, same = reference_sample(args, cfg, True)
+    if world > 1:                                         # our arm clusters world x --amplicons as ONE job: the reference runs a bounded sample of it
+        same = False
     fa = make_dataset(sample, L, args.seed, f"/dev/shm/swb200_{sample}x{L}_s{args.seed}.fa")
     threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
     # bounded repeats: one run of the full 10 M workload is ~20 s of wall time (FASTA parse + sort included, untimed)
@@ -182,7 +184,7 @@ def reference_arm(args, cfg, rank, world):
             times.append(t)
     ms = 1e3 * sum(times) / len(times)
     val = sample / (ms * 1e-3)
-    wl = f"{args.amplicons} x {L} bp synthetic amplicons, d={d}" + (" --fastidious" if fast else "") + f" ({label})"
+    wl = f"{args.amplicons * world} x {L} bp synthetic amplicons, d={d}" + (" --fastidious" if fast else "") + f" ({label})"
     emit({"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": world, "steps": runs, "warmup": warm,
           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
           "config": {"workload": wl, "same_config": bool(same),
