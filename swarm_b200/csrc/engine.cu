@@ -1603,8 +1603,9 @@ int swb200_d1_cluster_dist(swb200_ctx *c, uint32_t *swarm_of, uint32_t *generati
       g_err = "d1_cluster_dist: a peer did not reach a barrier within 5 s";
       return SWB200_ECUDA;
     }
-    if (!pack || overflow || !h[5]) break;
-    pack = false;                                     // some rank met a generation beyond gb bits (the last barrier's vote, the same on every rank)
+    // some rank met a generation beyond gb bits?  (the last barrier's vote, the same on every rank; a single rank reads its own flag)
+    if (!pack || overflow || !(D.world > 1 ? h[5] : h[6])) break;
+    pack = false;
     c->cluster_unpacked_reruns++;
   }
   if (overflow) {
