@@ -24,6 +24,9 @@ int  swbh_db_parse(const char *text, uint64_t size, int usearch_abundance, int64
 void swbh_db_free(swbh_db *db);
 /* workers of the FASTA ingest (0 = hardware concurrency, at most 32; 1 = serial).  Results do not depend on it. */
 void swbh_set_threads(int threads);
+/* The output writers below format large results with the same workers (swarms / rows cut into ranges of equal work, texts
+ * concatenated in order: identical bytes for any worker count).  Test hook: the amount of work from which they do so. */
+void swbh_set_writer_grain(uint64_t weight);
 
 uint32_t swbh_db_count(const swbh_db *db);            /* db_getsequencecount   src/db.cc:806-809 */
 uint32_t swbh_db_longest(const swbh_db *db);          /* db_getlongestsequence src/db.cc:812-815 */

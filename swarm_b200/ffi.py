@@ -103,6 +103,8 @@ def host_lib():
         L.swbh_db_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.POINTER(vp)]
         L.swbh_set_threads.argtypes = [C.c_int]
         L.swbh_set_threads.restype = None
+        L.swbh_set_writer_grain.argtypes = [C.c_uint64]
+        L.swbh_set_writer_grain.restype = None
         L.swbh_db_free.argtypes = [vp]
         L.swbh_db_free.restype = None
         for f in ("count", "longest", "stride_words"):

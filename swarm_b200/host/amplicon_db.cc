@@ -632,6 +632,7 @@ bool db_parse_parallel(const char *text, uint64_t size, const DbOptions &opt, Am
 }  // namespace
 
 void set_ingest_threads(int threads) { g_threads.store(threads); }
+unsigned host_threads() { return ingest_threads(); }
 static uint64_t ingest_min_bytes() {          // SWARM_B200_INGEST_MIN_BYTES: test hook, lets small inputs take the parallel path
   const char *e = std::getenv("SWARM_B200_INGEST_MIN_BYTES");
   return e ? std::strtoull(e, nullptr, 10) : (1u << 20);

@@ -62,6 +62,7 @@ struct AmpliconDb {
 std::string db_parse(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db);
 std::string db_parse_serial(const char *text, uint64_t size, const DbOptions &opt, AmpliconDb &db);
 void set_ingest_threads(int threads);
+unsigned host_threads();             // the worker count set_ingest_threads chose (ingest, output writers)
 std::string db_read_file(const std::string &path, const DbOptions &opt, AmpliconDb &db);
 
 // id printers (src/db.cc:946-1026)

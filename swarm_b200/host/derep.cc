@@ -61,85 +61,101 @@ uint64_t swbh_derep_clusters(const swbh_derep *r) { return r->seed.size(); }
 uint32_t swbh_derep_largest(const swbh_derep *r) { return r->largest; }
 uint64_t swbh_derep_heaviest(const swbh_derep *r) { return r->heaviest; }
 
+// The writers format clusters [c0, c1) per worker and concatenate in order (result.h: parallel_text): identical bytes for any
+// worker count; 10 M reads are hundreds of MB of text.
 // -o / -r : src/derep.cc:244-273, :206-241
 int swbh_d0_write_swarms(const swbh_db *dbh, const swbh_derep *r, int mothur, int usearch, int64_t append, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0; o.append_abundance = append;
-  std::string s;
-  s.reserve(r->members.size() * 16);
-  if (mothur) s += "swarm_0\t" + std::to_string(r->seed.size());
-  for (size_t c = 0; c < r->seed.size(); ++c) {
-    for (uint64_t m = r->first[c]; m < r->first[c + 1]; ++m) {
-      if (mothur) s += m == r->first[c] ? '\t' : ',';
-      else if (m != r->first[c]) s += ' ';
-      swb::append_id(s, dbh->db, r->members[m], o);
-    }
-    if (!mothur) s += '\n';
-  }
-  if (mothur) s += '\n';
-  return swb::give_text(s, out, out_len);
+  std::string head, tail;
+  if (mothur) { head = "swarm_0\t" + std::to_string(r->seed.size()); tail = "\n"; }
+  return swb::parallel_text(
+      r->seed.size(), [&](uint64_t c) { return r->first[c]; },
+      [&](uint64_t c0, uint64_t c1, std::string &s) {
+        for (uint64_t c = c0; c < c1; ++c) {
+          for (uint64_t m = r->first[c]; m < r->first[c + 1]; ++m) {
+            if (mothur) s += m == r->first[c] ? '\t' : ',';
+            else if (m != r->first[c]) s += ' ';
+            swb::append_id(s, dbh->db, r->members[m], o);
+          }
+          if (!mothur) s += '\n';
+        }
+      },
+      head, tail, out, out_len);
 }
 
 // -w : src/derep.cc:190-203 (cluster order, not re-sorted)
 int swbh_d0_write_seeds(const swbh_db *dbh, const swbh_derep *r, int usearch, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0;
-  std::string s;
-  for (size_t c = 0; c < r->seed.size(); ++c) {
-    s += '>';
-    swb::append_id_new_abundance(s, dbh->db, r->seed[c], r->mass[c], o);
-    s += '\n';
-    swb::append_sequence(s, dbh->db, r->seed[c]);
-    s += '\n';
-  }
-  return swb::give_text(s, out, out_len);
+  return swb::parallel_text(
+      r->seed.size(), [](uint64_t c) { return c * 16; },
+      [&](uint64_t c0, uint64_t c1, std::string &s) {
+        for (uint64_t c = c0; c < c1; ++c) {
+          s += '>';
+          swb::append_id_new_abundance(s, dbh->db, r->seed[c], r->mass[c], o);
+          s += '\n';
+          swb::append_sequence(s, dbh->db, r->seed[c]);
+          s += '\n';
+        }
+      },
+      "", "", out, out_len);
 }
 
 // -u : src/derep.cc:145-187
 int swbh_d0_write_uclust(const swbh_db *dbh, const swbh_derep *r, int usearch, int64_t append, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0; o.append_abundance = append;
   const swb::AmpliconDb &db = dbh->db;
-  std::string s;
-  for (size_t c = 0; c < r->seed.size(); ++c) {
-    const uint32_t seed = r->seed[c];
-    s += "C\t" + std::to_string(c) + "\t" + std::to_string(r->size[c]) + "\t*\t*\t*\t*\t*\t";
-    swb::append_id(s, db, seed, o);
-    s += "\t*\nS\t" + std::to_string(c) + "\t" + std::to_string(db.len[seed]) + "\t*\t*\t*\t*\t*\t";
-    swb::append_id(s, db, seed, o);
-    s += "\t*\n";
-    for (uint64_t m = r->first[c] + 1; m < r->first[c + 1]; ++m) {
-      const uint32_t a = r->members[m];
-      s += "H\t" + std::to_string(c) + "\t" + std::to_string(db.len[a]) + "\t100.0\t+\t0\t0\t=\t";
-      swb::append_id(s, db, a, o);
-      s += '\t';
-      swb::append_id(s, db, seed, o);
-      s += '\n';
-    }
-  }
-  return swb::give_text(s, out, out_len);
+  return swb::parallel_text(
+      r->seed.size(), [&](uint64_t c) { return r->first[c] * 4 + c * 8; },
+      [&](uint64_t c0, uint64_t c1, std::string &s) {
+        for (uint64_t c = c0; c < c1; ++c) {
+          const uint32_t seed = r->seed[c];
+          s += "C\t"; swb::append_uint(s, c); s += '\t'; swb::append_uint(s, r->size[c]); s += "\t*\t*\t*\t*\t*\t";
+          swb::append_id(s, db, seed, o);
+          s += "\t*\nS\t"; swb::append_uint(s, c); s += '\t'; swb::append_uint(s, db.len[seed]); s += "\t*\t*\t*\t*\t*\t";
+          swb::append_id(s, db, seed, o);
+          s += "\t*\n";
+          for (uint64_t m = r->first[c] + 1; m < r->first[c + 1]; ++m) {
+            const uint32_t a = r->members[m];
+            s += "H\t"; swb::append_uint(s, c); s += '\t'; swb::append_uint(s, db.len[a]); s += "\t100.0\t+\t0\t0\t=\t";
+            swb::append_id(s, db, a, o);
+            s += '\t';
+            swb::append_id(s, db, seed, o);
+            s += '\n';
+          }
+        }
+      },
+      "", "", out, out_len);
 }
 
 // -i : src/derep.cc:121-142
 int swbh_d0_write_structure(const swbh_db *dbh, const swbh_derep *r, int usearch, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0;
-  std::string s;
-  for (size_t c = 0; c < r->seed.size(); ++c)
-    for (uint64_t m = r->first[c] + 1; m < r->first[c + 1]; ++m) {
-      swb::append_id_noabundance(s, dbh->db, r->seed[c], o); s += '\t';
-      swb::append_id_noabundance(s, dbh->db, r->members[m], o);
-      s += "\t0\t" + std::to_string(c + 1) + "\t0\n";
-    }
-  return swb::give_text(s, out, out_len);
+  return swb::parallel_text(
+      r->seed.size(), [&](uint64_t c) { return r->first[c] * 3; },
+      [&](uint64_t c0, uint64_t c1, std::string &s) {
+        for (uint64_t c = c0; c < c1; ++c)
+          for (uint64_t m = r->first[c] + 1; m < r->first[c + 1]; ++m) {
+            swb::append_id_noabundance(s, dbh->db, r->seed[c], o); s += '\t';
+            swb::append_id_noabundance(s, dbh->db, r->members[m], o);
+            s += "\t0\t"; swb::append_uint(s, c + 1); s += "\t0\n";
+          }
+      },
+      "", "", out, out_len);
 }
 
 // -s : src/derep.cc:103-118
 int swbh_d0_write_stats(const swbh_db *dbh, const swbh_derep *r, int usearch, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0;
-  std::string s;
-  for (size_t c = 0; c < r->seed.size(); ++c) {
-    s += std::to_string(r->size[c]) + "\t" + std::to_string(r->mass[c]) + "\t";
-    swb::append_id_noabundance(s, dbh->db, r->seed[c], o);
-    s += "\t" + std::to_string(dbh->db.abundance[r->seed[c]]) + "\t" + std::to_string(r->singletons[c]) + "\t0\t0\n";
-  }
-  return swb::give_text(s, out, out_len);
+  return swb::parallel_text(
+      r->seed.size(), [](uint64_t c) { return c * 4; },
+      [&](uint64_t c0, uint64_t c1, std::string &s) {
+        for (uint64_t c = c0; c < c1; ++c) {
+          swb::append_uint(s, r->size[c]); s += '\t'; swb::append_uint(s, r->mass[c]); s += '\t';
+          swb::append_id_noabundance(s, dbh->db, r->seed[c], o);
+          s += '\t'; swb::append_uint(s, dbh->db.abundance[r->seed[c]]); s += '\t'; swb::append_uint(s, r->singletons[c]); s += "\t0\t0\n";
+        }
+      },
+      "", "", out, out_len);
 }
 
 }  // extern "C"

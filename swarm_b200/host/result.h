@@ -4,6 +4,8 @@
 #include "amplicon_db.h"
 
 #include <cstdint>
+#include <functional>
+#include <string>
 #include <vector>
 
 struct swbh_db {
@@ -32,6 +34,17 @@ struct swbh_result {
 };
 
 namespace swb {
+// Output text built by several workers (the reference writes serially; 10 M amplicons are 117 MB of -o / -s text, 2.4 s of the
+// drop-in's 4.8 s wall clock when formatted by one thread): the units [0, n_units) — swarms, rows — are cut into contiguous ranges
+// of equal weight (`weight_before(u)` = non-decreasing work before unit u), every worker formats its range into its own buffer with
+// `body(u0, u1, text)`, and the buffers are copied, in order, into one malloc'd block behind `head`.  Identical bytes for any
+// worker count.  Small outputs (total weight below the grain) stay on the calling thread.
+int parallel_text(uint64_t n_units, const std::function<uint64_t(uint64_t)> &weight_before,
+                  const std::function<void(uint64_t, uint64_t, std::string &)> &body, const std::string &head, const std::string &tail,
+                  char **out, uint64_t *out_len);
+void set_writer_grain(uint64_t weight);          // test hook: parallel formatting from this total weight on (default 200 000)
+void append_uint(std::string &s, uint64_t v);    // decimal digits, no allocation
+
 template <typename F>
 void for_each_member(const swbh_result &r, uint32_t sw, F &&f) {   // list order incl. grafted light swarms
   for (uint64_t k = 0; k < r.own_size[sw]; ++k) f(r.members[r.first[sw] + k]);

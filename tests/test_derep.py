@@ -38,6 +38,17 @@ def test_oracle_and_writers_match_reference(built, name, usearch):
             a = int(orc.d0_next[a])
         assert chain == np.flatnonzero(rep == s).tolist()
     _check_texts(DerepResult(db, rep, mass, size, singles), name)
+    # the writers split the clusters over several workers for large results: same bytes with the grain lowered to these inputs
+    from swarm_b200.ffi import host_lib
+    L = host_lib()
+    try:
+        L.swbh_set_writer_grain(1)
+        for workers in (2, 5):
+            L.swbh_set_threads(workers)
+            _check_texts(DerepResult(db, rep, mass, size, singles), name)
+    finally:
+        L.swbh_set_writer_grain(200000)
+        L.swbh_set_threads(0)
 
 
 def test_length_is_part_of_the_key(built):

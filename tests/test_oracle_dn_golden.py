@@ -60,6 +60,32 @@ def test_dn_matches_reference(built, name, d, ncb, pen, tag):
     assert [db.header(a) for a in orc.order] == flat
 
 
+@pytest.mark.parametrize("name,d", [("tie_1500_60", 2), ("c1_1k_150", 2), ("w65_300", 3)])
+def test_dn_writers_identical_for_any_worker_count(built, name, d):
+    """the d>1 writers split their swarms over several workers like the d=1 ones: identical bytes for 1, 2, 5 workers"""
+    from swarm_b200.ffi import host_lib
+    db = HostDb(GOLDEN / f"{name}.fasta", check_dup_sequences=True)
+    orc = Oracle(db)
+    sw, gen, par, pdiff = orc.dn_cluster(d, pen=scoring())
+    L = host_lib()
+
+    def texts():
+        res = DnResult(db, sw, gen, par, pdiff)
+        out = [res.swarms_text(), res.stats_text(), res.structure_text()]
+        res.close()
+        return out
+
+    want = texts()
+    try:
+        L.swbh_set_writer_grain(1)
+        for workers in (1, 2, 5):
+            L.swbh_set_threads(workers)
+            assert texts() == want, workers
+    finally:
+        L.swbh_set_writer_grain(200000)
+        L.swbh_set_threads(0)
+
+
 @pytest.mark.parametrize("d", [20, 60, 255])
 def test_wide_d_related_sequences_match_reference(built, tmp_path, d):
     """far beyond d = 6 the reference aligns with its 16-bit SIMD kernels; on RELATED sequences (variants of one seed,

@@ -144,6 +144,62 @@ def test_uclust_band_does_not_change_the_records(built, tmp_path):
     assert want.count(b"\nH\t") == n - 1
 
 
+def _all_texts(db, orc, pairs):
+    rp = np.zeros(db.n + 1, dtype=np.uint64)
+    np.add.at(rp, pairs[:, 0].astype(np.int64) + 1, 1)
+    rp = np.cumsum(rp).astype(np.uint64)
+    out = [network_text(db, rp, pairs[:, 1])]
+    for gc in (None, orc.graft_cand):
+        res = D1Result(db, orc.swarm_of, orc.generation, orc.parent, graft_cand=gc, boundary=3)
+        out += [res.swarms_text(), res.swarms_text(mothur=True), res.stats_text(), res.structure_text(), res.seeds_text()]
+        res.close()
+    return out
+
+
+def test_writers_identical_for_any_worker_count(case):
+    """the output writers cut their swarms / rows into ranges of equal work for several workers (host/d1_result.cc: parallel_text):
+    identical bytes for 1, 2, 3 and 7 workers, with the grain lowered so that even these small inputs are split — including ranges
+    that start inside runs of attached (grafted) swarms, whose output numbers come from a prefix count"""
+    from swarm_b200.ffi import host_lib
+    name, db, _ = case
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    orc.fastidious(boundary=3)
+    pairs = orc.links()
+    L = host_lib()
+    want = _all_texts(db, orc, pairs)
+    assert want[1] == (GOLDEN / f"{name}.o").read_bytes() and want[6] == (GOLDEN / f"{name}.f.o").read_bytes()
+    try:
+        L.swbh_set_writer_grain(1)
+        for workers in (1, 2, 3, 7):
+            L.swbh_set_threads(workers)
+            assert _all_texts(db, orc, pairs) == want, workers
+    finally:
+        L.swbh_set_writer_grain(200000)
+        L.swbh_set_threads(0)
+
+
+def test_writers_with_default_grain_on_300k(built, tmp_path):
+    """above the default grain the writers really run on several workers: same bytes as one worker"""
+    import helpers
+    from swarm_b200.ffi import host_lib
+    db = HostDb(helpers.make_fasta(tmp_path / "w.fa", 300000, 120, 8, 1))
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    orc.fastidious(boundary=3)
+    pairs = orc.links()
+    L = host_lib()
+    try:
+        L.swbh_set_threads(1)
+        want = _all_texts(db, orc, pairs)
+        L.swbh_set_threads(6)
+        assert _all_texts(db, orc, pairs) == want
+    finally:
+        L.swbh_set_threads(0)
+
+
 def test_network_matches_reference(case):
     name, db, orc = case
     pairs = orc.links()
