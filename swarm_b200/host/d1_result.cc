@@ -313,7 +313,7 @@ int swbh_write_structure(const swbh_db *dbh, const swbh_result *r, int usearch, 
   std::vector<uint32_t> number(r->seed.size() + 1, 0);
   for (size_t sw = 0; sw < r->seed.size(); ++sw) number[sw + 1] = number[sw] + (r->attached[sw] ? 0u : 1u);
   return swb::parallel_text(
-      r->seed.size(), [&](uint64_t sw) { return r->first[sw] * 3; },
+      r->seed.size(), [&](uint64_t sw) { return (r->first[sw] - sw) * 3; },      // one line per member that is not a seed
       [&](uint64_t s0, uint64_t s1, std::string &s) {
         for (uint32_t sw = static_cast<uint32_t>(s0); sw < s1; ++sw) {
           if (r->attached[sw]) continue;
@@ -450,7 +450,7 @@ int swbh_dn_write_structure(const swbh_db *dbh, const swbh_result *r, int usearc
   { std::vector<uint64_t> cur(cstart.begin(), cstart.end() - 1);
     for (uint32_t a = 0; a < n; ++a) if (r->parent[a] != 0xFFFFFFFFu) child[cur[r->parent[a]]++] = a; }
   return swb::parallel_text(
-      r->seed.size(), [&](uint64_t sw) { return r->first[sw] * 3; },
+      r->seed.size(), [&](uint64_t sw) { return (r->first[sw] - sw) * 3; },      // one line per member that is not a seed
       [&](uint64_t s0, uint64_t s1, std::string &s) {
         for (uint32_t sw = static_cast<uint32_t>(s0); sw < s1; ++sw)
           for (uint64_t k = 0; k < r->own_size[sw]; ++k) {

@@ -131,7 +131,7 @@ int swbh_d0_write_uclust(const swbh_db *dbh, const swbh_derep *r, int usearch, i
 int swbh_d0_write_structure(const swbh_db *dbh, const swbh_derep *r, int usearch, char **out, uint64_t *out_len) {
   swb::DbOptions o; o.usearch_abundance = usearch != 0;
   return swb::parallel_text(
-      r->seed.size(), [&](uint64_t c) { return r->first[c] * 3; },
+      r->seed.size(), [&](uint64_t c) { return (r->first[c] - c) * 3; },      // one line per member that is not a seed
       [&](uint64_t c0, uint64_t c1, std::string &s) {
         for (uint64_t c = c0; c < c1; ++c)
           for (uint64_t m = r->first[c] + 1; m < r->first[c + 1]; ++m) {
