@@ -354,11 +354,31 @@ int swbh_write_seeds(const swbh_db *dbh, const swbh_result *r, int usearch, char
     v <<= 8 * (8 - k);                                        // a shorter header sorts first, as with strcmp
     keys[sw] = {r->mass[sw], v, sw};
   }
-  std::sort(keys.begin(), keys.end(), [&](const Key &x, const Key &y) {
+  auto less = [&](const Key &x, const Key &y) {
     if (x.mass != y.mass) return x.mass > y.mass;
     if (x.head != y.head) return x.head < y.head;
     return std::strcmp(db.header(r->seed[x.sw]), db.header(r->seed[y.sw])) < 0;
-  });
+  };
+  {
+    // T sorted runs on T workers, then pairwise merges (log2 T passes, the merges of a pass in parallel); headers are unique, so
+    // the order is total and the result does not depend on T
+    unsigned T = keys.size() >= swb::g_writer_grain.load() ? std::max(1u, std::min(swb::host_threads(), 16u)) : 1u;
+    while (T & (T - 1)) T &= T - 1;                          // a power of two
+    std::vector<size_t> cut(T + 1);
+    for (unsigned t = 0; t <= T; ++t) cut[t] = keys.size() * t / T;
+    auto each = [&](unsigned count, const std::function<void(unsigned)> &f) {
+      if (count <= 1) { if (count) f(0); return; }
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < count; ++t) pool.emplace_back(f, t);
+      for (auto &th : pool) th.join();
+    };
+    each(T, [&](unsigned t) { std::sort(keys.begin() + static_cast<int64_t>(cut[t]), keys.begin() + static_cast<int64_t>(cut[t + 1]), less); });
+    for (unsigned width = 1; width < T; width *= 2)
+      each(T / (2 * width), [&](unsigned p) {
+        const size_t a = cut[2 * width * p], m = cut[2 * width * p + width], b = cut[2 * width * (p + 1)];
+        std::inplace_merge(keys.begin() + static_cast<int64_t>(a), keys.begin() + static_cast<int64_t>(m), keys.begin() + static_cast<int64_t>(b), less);
+      });
+  }
   std::vector<uint32_t> sorter(keys.size());
   for (size_t k = 0; k < keys.size(); ++k) sorter[k] = keys[k].sw;
   return swb::parallel_text(
