@@ -200,6 +200,26 @@ def test_writers_with_default_grain_on_300k(built, tmp_path):
         L.swbh_set_threads(0)
 
 
+def test_oracle_and_parallel_writers_reproduce_the_reference_digests_at_1M(built, tmp_path):
+    """1 M x 150 bp (the generator stream of the bench, seed 42): the CPU oracle's clustering, written by the host writers on 8
+    workers, hashes to the digests of the reference's own -o / -s / -i files (tests/golden/scale_hashes.json[c2_1m]) — pins the
+    oracle and the multi-worker writers at a size where every range boundary falls inside real data"""
+    from swarm_b200.ffi import host_lib
+    db = HostDb(helpers.make_fasta(tmp_path / "m.fa", 1000000, 150, 42, 0))
+    orc = Oracle(db)
+    orc.network()
+    orc.cluster()
+    L = host_lib()
+    try:
+        L.swbh_set_threads(8)
+        res = D1Result(db, orc.swarm_of, orc.generation, orc.parent)
+        got = helpers.output_hashes(res.swarms_text(), res.stats_text(), res.structure_text())
+        res.close()
+    finally:
+        L.swbh_set_threads(0)
+    assert helpers.compare_case("c2_1m", got) == []
+
+
 def test_network_matches_reference(case):
     name, db, orc = case
     pairs = orc.links()
