@@ -74,6 +74,28 @@ print("rank", rank, "ok")
 '''
 
 
+@pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 100000, 1234567])
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 16])
+def test_dist_rows_partition_the_amplicons(built, n, world):
+    """multi-GPU clustering returns, on rank r, the rows of the amplicons it owns (block-cyclic, blocks of 4 096 ids:
+    swb200_dist_row_count / swb200_dist_row_id, pure host functions): over all ranks every amplicon exactly once, ascending on a
+    rank, and the peer buffer size the host is told to allocate grows with the job"""
+    from swarm_b200.ffi import dist_buffer_bytes, dist_row_ids, engine_lib
+    L = engine_lib()
+    seen = np.zeros(n, dtype=np.uint8)
+    for r in range(world):
+        ids = dist_row_ids(n, r, world).astype(np.int64)
+        assert ids.shape[0] == L.swb200_dist_row_count(n, r, world)
+        assert np.all(np.diff(ids) > 0) and (ids.shape[0] == 0 or ids[-1] < n)
+        assert np.all((ids // 4096) % world == r)
+        for i in (0, ids.shape[0] // 2, ids.shape[0] - 1):
+            if 0 <= i < ids.shape[0]:
+                assert L.swb200_dist_row_id(r, world, int(i)) == ids[i]
+        seen[ids] += 1
+    assert np.all(seen == 1)
+    assert dist_buffer_bytes(2 * n, world) >= dist_buffer_bytes(n, world) > 4096
+
+
 def test_link_allgather_world2_gloo(built, tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
